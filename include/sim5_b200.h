@@ -1,0 +1,216 @@
+/*
+ * sim5_b200.h -- batched C-ABI of the B200-native SIM5 photon hot path.
+ *
+ * This is the NEW entry point that replaces the caller-owned serial pixel loop
+ * of the reference (examples/04-disk-image-eqplane/disk-image.c:53-105 and
+ * python/sim5diskraytrace.py:163-205): one call traces a whole image (or a row
+ * block of it) on one B200 with hand-written sm_100a FP64 kernels.
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types cross the boundary.
+ * There is no CPU fallback: every entry point returns SIM5_ERR_NO_DEVICE when no
+ * CUDA device is usable.
+ *
+ * The scalar reference API (geodesic_init_inf, raytrace, rf, ...) is declared in
+ * sim5lib.h next to this file and is implemented on top of the same device code.
+ */
+#ifndef SIM5_B200_H
+#define SIM5_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ */
+/* error codes (negative = failure), cf. the reference's TRUE/FALSE +  */
+/* optional int* error convention (sim5kerr-geod.c:59-98)              */
+/* ------------------------------------------------------------------ */
+#define SIM5_OK                  0
+#define SIM5_ERR_NO_DEVICE      -1   /* no CUDA device / driver: the library never computes on the CPU */
+#define SIM5_ERR_BAD_PARAM      -2
+#define SIM5_ERR_CUDA           -3   /* a CUDA runtime call failed; see sim5_last_error() */
+#define SIM5_ERR_NOT_IMPL       -4
+#define SIM5_ERR_NO_OUTPUT      -5   /* a plane selected in `outputs` has a NULL pointer */
+
+/* ------------------------------------------------------------------ */
+/* trace modes                                                         */
+/* ------------------------------------------------------------------ */
+#define SIM5_MODE_EQPLANE        0   /* thin-disk image: init_inf + midplane crossing (+ azimuth) + gfactorK + NT flux */
+#define SIM5_MODE_POLARIZED      1   /* EQPLANE + local tetrad g-factor, emission angle, Walker-Penrose chi, Chandrasekhar delta */
+#define SIM5_MODE_STEPWISE       2   /* raytrace() stepping through an optically thin torus */
+#define SIM5_MODE_HISTOGRAM      3   /* transfer function: g-factor histograms over a (spin, inclination) lattice */
+
+/* output plane selector bits (all planes are row-major [ny][nx], index iy*nx+ix) */
+#define SIM5_OUT_R            0x001  /* radius of the disk hit                      (double) */
+#define SIM5_OUT_PHI          0x002  /* azimuth travelled from infinity             (double) */
+#define SIM5_OUT_G            0x004  /* g-factor                                    (double) */
+#define SIM5_OUT_FLUX         0x008  /* observed flux F(r)*g^4                      (double) */
+#define SIM5_OUT_CHI          0x010  /* polarization angle at the observer          (double) */
+#define SIM5_OUT_DELTA        0x020  /* polarization degree at emission             (double) */
+#define SIM5_OUT_MUE          0x040  /* cosine of the emission angle                (double) */
+#define SIM5_OUT_INTENSITY    0x080  /* STEPWISE: integrated intensity              (double) */
+#define SIM5_OUT_TAU          0x100  /* STEPWISE: integrated optical depth          (double) */
+#define SIM5_OUT_STEPS        0x200  /* STEPWISE: number of raytrace() calls        (int32)  */
+#define SIM5_OUT_STATUS       0x400  /* classification / termination byte           (uint8)  */
+#define SIM5_OUT_QERR         0x800  /* STEPWISE: raytrace_error() at the end       (double) */
+
+/* flags */
+#define SIM5_FLAG_DEVICE_PTRS   0x1  /* pointers in sim5_image_out are device pointers (no staging, no D2H) */
+#define SIM5_FLAG_NO_REFILL     0x2  /* debugging: disable warp-level lane refill / compaction */
+
+/* ------------------------------------------------------------------ */
+/* per-pixel status byte                                               */
+/*   bits 0..4 : class / termination code                              */
+/*   bits 5..7 : geodesic type code                                    */
+/* ------------------------------------------------------------------ */
+#define SIM5_ST_HIT0             0   /* order-0 crossing at r >= r_emit_min */
+#define SIM5_ST_HIT1             1   /* order-1 crossing at r >= r_emit_min */
+#define SIM5_ST_MISS             2   /* crossings exist but none at r >= r_emit_min (incl. r = NaN) */
+#define SIM5_ST_NOCROSS0         3   /* geodesic_find_midplane_crossing(order 0) returned NaN */
+#define SIM5_ST_NOCROSS1         4   /* order 0 fell inside r_emit_min, order 1 returned NaN */
+#define SIM5_ST_HIT2             5   /* order-2 crossing (only if max_order >= 2) */
+#define SIM5_ST_NOCROSS2         6
+/* stepwise terminations */
+#define SIM5_ST_HORIZON          8   /* r < 1.05 r_bh */
+#define SIM5_ST_ESCAPE           9   /* r > 1.01 r_start */
+#define SIM5_ST_ERRBREAK        10   /* rtd.error > 1e-2 */
+#define SIM5_ST_MAXSTEPS        11
+#define SIM5_ST_NOSTART         12   /* ray never reaches r_start (r_start < pericentre) or start position undefined */
+/* init errors: 16 + GD_ERROR_* of geodesic_init_inf */
+#define SIM5_ST_INITERR         16
+#define SIM5_ST_CLASS(s)        ((s) & 0x1f)
+#define SIM5_ST_GTYPE(s)        (((s) >> 5) & 0x7)
+/* geodesic type codes in bits 5..7 (GEOD_TYPE_* of sim5kerr-geod.h:19-23 compressed) */
+#define SIM5_GT_NONE             0
+#define SIM5_GT_RR               1
+#define SIM5_GT_RC               2
+#define SIM5_GT_CC               3
+#define SIM5_GT_RR_DBL           4
+#define SIM5_GT_RR_BH            5
+
+/* ------------------------------------------------------------------ */
+/* harness-defined emission models. They are NOT part   */
+/* of the reference; oracle driver and kernels share these numbers.    */
+/* ------------------------------------------------------------------ */
+/* Chandrasekhar (1960) pure-scattering limb polarization degree, mu = 0, 0.05, ..., 1 ;
+ * linear interpolation between the knots. */
+#define SIM5_CHANDRA_N 21
+static const double SIM5_CHANDRA_DELTA[SIM5_CHANDRA_N] = {
+    0.11713, 0.08979, 0.07448, 0.06311, 0.05410, 0.04667, 0.04041,
+    0.03502, 0.03033, 0.02619, 0.02252, 0.01923, 0.01627, 0.01358,
+    0.01112, 0.00888, 0.00682, 0.00492, 0.00316, 0.00152, 0.00000
+};
+
+typedef struct sim5_image_params {
+    int32_t  struct_size;        /* = sizeof(sim5_image_params); ABI guard */
+    int32_t  mode;               /* SIM5_MODE_* */
+    uint32_t outputs;            /* SIM5_OUT_* mask */
+    uint32_t flags;              /* SIM5_FLAG_* */
+    int32_t  nx, ny;             /* image size in pixels */
+    int32_t  row_begin, row_end; /* rows [row_begin,row_end) traced by this call; 0,0 = all rows.
+                                    Planes are always addressed with the FULL image index iy*nx+ix
+                                    unless SIM5_FLAG_DEVICE_PTRS is set and row_base_is_zero != 0 */
+    int32_t  max_order;          /* highest crossing order tried (reference example: 1) */
+    int32_t  device;             /* CUDA device ordinal */
+    /* geometry -- pixel rule of disk-image.c:57-58:
+     *   alpha = ((ix+.5)/nx-.5)*2*rmax ; beta = ((iy+.5)/ny-.5)*2*rmax*(ny/nx) */
+    double   bh_spin;
+    double   incl;               /* radians */
+    double   rmax;
+    double   r_emit_min;         /* <= 0 : r_ms(bh_spin) as in disk-image.c:41,83 */
+    /* Novikov-Thorne disk, disk_nt_setup(M, a, mdot, alpha, 0) sim5disk-nt.c:37 */
+    double   disk_mass;
+    double   disk_mdot;
+    double   disk_alpha;
+    /* STEPWISE */
+    double   precision_factor;   /* raytrace_prepare() argument */
+    double   r_start;            /* rays are started at this radius on the way in */
+    double   step_max;           /* *step passed to raytrace() each call */
+    int32_t  max_steps;          /* safety bound on raytrace() calls per ray */
+    int32_t  reserved0;
+    double   torus_rc;           /* torus centre radius */
+    double   torus_w;            /* radial width */
+    double   torus_h;            /* vertical scale height (in units of cylindrical radius) */
+    double   torus_ell;          /* constant specific angular momentum of the torus */
+    double   torus_j0;           /* emissivity normalisation */
+    double   torus_k0;           /* absorption normalisation */
+    /* HISTOGRAM */
+    int32_t  n_spin, n_incl, n_bins;
+    int32_t  lattice_begin, lattice_end; /* images [begin,end) of the n_spin*n_incl lattice (multi-GPU split); 0,0 = all */
+    int32_t  reserved1;
+    double   spin_max;           /* a_j = spin_max*j/(n_spin-1) */
+    double   incl_min_deg, incl_max_deg; /* i_k = min + (max-min)*k/(n_incl-1) degrees */
+    double   g_min, g_max;       /* histogram range */
+    double   rmax_offset;        /* rmax = r_ms(a_j) + rmax_offset */
+} sim5_image_params;
+
+typedef struct sim5_image_out {
+    double  *r;
+    double  *phi;
+    double  *g;
+    double  *flux;
+    double  *chi;
+    double  *delta;
+    double  *mue;
+    double  *intensity;
+    double  *tau;
+    double  *qerr;
+    int32_t *steps;
+    uint8_t *status;
+    double  *hist;               /* [n_spin][n_incl][n_bins] */
+} sim5_image_out;
+
+typedef struct sim5_trace_stats {
+    int64_t  rays;               /* rays traced by this call */
+    int64_t  class_count[32];    /* histogram of SIM5_ST_CLASS over the traced rays */
+    int64_t  gtype_count[8];     /* histogram of SIM5_ST_GTYPE */
+    int64_t  total_steps;        /* STEPWISE: sum of raytrace() calls */
+    double   kernel_ms;          /* device time of the trace kernel(s), CUDA events on the launch stream */
+    double   total_ms;           /* device time of the whole call incl. copies */
+    int32_t  kernel_launches;    /* kernels launched by this call */
+    int32_t  sm_count;
+    int32_t  grid_ctas, cta_threads;
+} sim5_trace_stats;
+
+/* lifecycle ------------------------------------------------------------- */
+int  sim5_gpu_init(int device);        /* create context/streams/scratch on `device`; idempotent */
+void sim5_gpu_shutdown(void);
+int  sim5_gpu_device_count(void);      /* 0 when no usable device */
+const char* sim5_last_error(void);
+const char* sim5_version(void);
+
+/* pinned host memory for output planes (so the D2H leg of the call can overlap tracing) */
+void* sim5_host_alloc(size_t bytes);
+void  sim5_host_free(void* p);
+/* device memory helpers for SIM5_FLAG_DEVICE_PTRS users (e.g. a torch tensor's data_ptr works too) */
+void* sim5_device_alloc(size_t bytes);
+void  sim5_device_free(void* p);
+int   sim5_device_to_host(void* dst, const void* src, size_t bytes);
+
+/* defaults: fills every field with the SURVEY.md 8(d) definition of BASELINE config `cfg` (1..5) */
+int  sim5_default_params(int cfg, sim5_image_params* p);
+
+/* THE batched entry: replaces the per-pixel loop of disk-image.c:53-105 */
+int  sim5_trace_image(const sim5_image_params* p, const sim5_image_out* out, sim5_trace_stats* stats);
+
+/* FP64 DFMA-chain microbenchmark: returns measured TFLOP/s (2 flop per DFMA) of the device, <0 on error.
+ * This is the roofline denominator for the compute-bound FP64 path (MEASURED_PEAKS.json has no FP64 entry). */
+double sim5_fp64_peak_tflops(int device, int iters);
+
+/* batched element-wise access to the device functions (parity tests call these through the C-ABI).
+ * Each mirrors one reference function; n elements, SoA arrays. */
+int sim5_batch_rf(int64_t n, const double* x, const double* y, const double* z, double* out);           /* sim5elliptic.c:18 */
+int sim5_batch_rd(int64_t n, const double* x, const double* y, const double* z, double* out);           /* sim5elliptic.c:58 */
+int sim5_batch_rc(int64_t n, const double* x, const double* y, double* out);                            /* sim5elliptic.c:104 */
+int sim5_batch_rj(int64_t n, const double* x, const double* y, const double* z, const double* p, double* out); /* sim5elliptic.c:144 */
+int sim5_batch_sncndn(int64_t n, const double* u, const double* m, double* sn, double* cn, double* dn); /* sim5elliptic.c:535 */
+/* unary/binary libm-compatible device functions (correctly-rounded double-double implementations):
+ * op: 0 sin, 1 cos, 2 log, 3 atan2(y=a,x=b), 4 acos, 5 asin, 6 atan, 7 pow(a,1./3.), 8 pow(a,1.5), 9 pow(a,4.), 10 exp */
+int sim5_batch_libm(int op, int64_t n, const double* a, const double* b, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIM5_B200_H */

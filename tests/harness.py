@@ -1,0 +1,139 @@
+"""Test-side helpers: load the checkers (oracle/_ref = unmodified reference, oracle/ = our C port),
+allocate SoA planes, run images through any of the implementations, and compare results.
+
+Only tests/, bench.py's cpu_baseline / reference arm and __graft_entry__.smoke() import this.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from sim5_b200 import abi  # noqa: E402
+
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libsim5ref.so")
+ORACLE_SO = os.path.join(ROOT, "oracle", "libsim5oracle.so")
+
+_NP = {C.c_double: np.float64, C.c_int32: np.int32, C.c_uint8: np.uint8}
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def have_oracle():
+    return os.path.exists(ORACLE_SO)
+
+
+_libs = {}
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def load_ref():
+    if "ref" not in _libs:
+        lib = C.CDLL(REF_SO)
+        lib.ref_trace_image.restype = C.c_double
+        lib.ref_trace_image.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(abi.ImageOut), C.c_int, C.c_int,
+                                        C.POINTER(abi.TraceStats)]
+        lib.ref_trace_histogram.restype = C.c_double
+        lib.ref_trace_histogram.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(C.c_double), C.c_int, C.c_int]
+        lib.ref_r_ms.restype = C.c_double
+        lib.ref_r_ms.argtypes = [C.c_double]
+        lib.ref_r_bh.restype = C.c_double
+        lib.ref_r_bh.argtypes = [C.c_double]
+        lib.ref_max_threads.restype = C.c_int
+        _libs["ref"] = lib
+    return _libs["ref"]
+
+
+def load_oracle():
+    if "oracle" not in _libs:
+        lib = C.CDLL(ORACLE_SO)
+        lib.orc_trace_image.restype = C.c_double
+        lib.orc_trace_image.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(abi.ImageOut), C.c_int,
+                                        C.POINTER(abi.TraceStats)]
+        lib.orc_trace_histogram.restype = C.c_double
+        lib.orc_trace_histogram.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(C.c_double), C.c_int]
+        _libs["oracle"] = lib
+    return _libs["oracle"]
+
+
+class Planes:
+    """Host SoA output planes for one image + the ImageOut struct pointing at them."""
+
+    def __init__(self, p, fill=None):
+        n = p.nx * p.ny
+        self.arrays = {}
+        self.out = abi.ImageOut()
+        for name, bit, ct in abi.PLANES:
+            if p.outputs & bit:
+                a = np.zeros(n, dtype=_NP[ct])
+                if fill is not None:
+                    a[...] = fill
+                self.arrays[name] = a
+                setattr(self.out, name, a.ctypes.data)
+        self.shape = (p.ny, p.nx)
+
+    def __getitem__(self, k):
+        return self.arrays[k]
+
+    def image(self, k):
+        return self.arrays[k].reshape(self.shape)
+
+
+def run_ref(p, nthreads=0, quiet=True):
+    lib = load_ref()
+    pl = Planes(p)
+    st = abi.TraceStats()
+    dt = lib.ref_trace_image(C.byref(p), C.byref(pl.out), nthreads, 1 if quiet else 0, C.byref(st))
+    assert dt >= 0, "ref_trace_image failed (%r)" % dt
+    return pl, st, dt
+
+
+def run_oracle(p, nthreads=0):
+    lib = load_oracle()
+    pl = Planes(p)
+    st = abi.TraceStats()
+    dt = lib.orc_trace_image(C.byref(p), C.byref(pl.out), nthreads, C.byref(st))
+    assert dt >= 0, "orc_trace_image failed (%r)" % dt
+    return pl, st, dt
+
+
+def batch_call(lib, name, ins, nout=1, extra=()):
+    """Call an n-element SoA function `name(n?, in..., out...)` of the ref / oracle library."""
+    ins = [np.ascontiguousarray(a, dtype=np.float64) for a in ins]
+    n = ins[0].size
+    outs = [np.empty(n, dtype=np.float64) for _ in range(nout)]
+    fn = getattr(lib, name)
+    fn.restype = None
+    args = list(extra) + [C.c_long(n)] + [_dp(a) for a in ins] + [_dp(o) for o in outs]
+    fn(*args)
+    return outs[0] if nout == 1 else outs
+
+
+def rel_err(x, ref, floor=0.0):
+    """|x-ref| / max(|ref|, floor) with exact-equal (incl. both-NaN) counted as 0."""
+    x = np.asarray(x, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    den = np.maximum(np.abs(ref), floor if floor > 0 else np.finfo(np.float64).tiny)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        e = np.abs(x - ref) / den
+    same = (x == ref) | (np.isnan(x) & np.isnan(ref))
+    e = np.where(same, 0.0, e)
+    e = np.where(np.isnan(e), np.inf, e)
+    return e
+
+
+def err_summary(x, ref, floor=0.0):
+    e = rel_err(x, ref, floor)
+    if e.size == 0:
+        return {"max": 0.0, "p999": 0.0, "exact": 1.0, "n": 0}
+    return {"max": float(e.max()), "p999": float(np.quantile(e, 0.999)), "exact": float(np.mean(e == 0.0)),
+            "n": int(e.size)}
