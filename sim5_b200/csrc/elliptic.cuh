@@ -1,0 +1,472 @@
+/*
+ * elliptic.cuh -- Carlson symmetric integrals, Legendre/Jacobi wrappers and the Byrd&Friedman
+ * radial/polar integrals used by the analytic Kerr geodesic solver, as sm_100a device code.
+ *
+ * Behavioural contract: every function returns bit-for-bit what the reference's CPU function of the
+ * same name returns (src/sim5elliptic.c, lines cited per function), given IEEE add/mul/div/sqrt with
+ * no FMA contraction (the kernels are built with -fmad=false) and the correctly-rounded elementary
+ * functions of crmath.cuh in place of glibc's libm.  Operation ORDER therefore follows the reference
+ * expressions exactly; everything else (structure, naming, loop shape) is ours.
+ */
+#ifndef SIM5_ELLIPTIC_CUH
+#define SIM5_ELLIPTIC_CUH
+
+#include "crmath.cuh"
+
+namespace s5 {
+
+using crm::cr_sincos;
+using crm::cr_log;
+using crm::cr_atan;
+using crm::cr_atan2;
+using crm::cr_acos;
+using crm::cr_asin;
+
+S5_HD S5_INL double sq(double x) { return x * x; }
+S5_HD S5_INL double max3(double a, double b, double c) { return fmax(fmax(a, b), c); }
+
+#define S5_CARLSON_TOL 0.0003
+
+/* R_F(x,y,z), duplication theorem with the 5th-order series tail.  sim5elliptic.c:18-52 */
+S5_HD S5_NOINL double rf(double x, double y, double z)
+{
+    constexpr double THIRD = 1.0 / 3.0;
+    constexpr double K1 = 1.0 / 24.0, K2 = 0.1, K3 = 3.0 / 44.0, K4 = 1.0 / 14.0;
+    double mu, dx, dy, dz;
+    do {
+        double sx = sqrt(x), sy = sqrt(y), sz = sqrt(z);
+        double lam = sx * (sy + sz) + sy * sz;
+        x = 0.25 * (x + lam);
+        y = 0.25 * (y + lam);
+        z = 0.25 * (z + lam);
+        mu = THIRD * (x + y + z);
+        dx = (mu - x) / mu;
+        dy = (mu - y) / mu;
+        dz = (mu - z) / mu;
+    } while (max3(fabs(dx), fabs(dy), fabs(dz)) > S5_CARLSON_TOL);
+    double e2 = dx * dy - dz * dz;
+    double e3 = dx * dy * dz;
+    return (1.0 + (K1 * e2 - K2 - K3 * e3) * e2 + K4 * e3) / sqrt(mu);
+}
+
+/* R_D(x,y,z).  sim5elliptic.c:58-98 */
+S5_HD S5_NOINL double rd(double x, double y, double z)
+{
+    constexpr double K1 = 3.0 / 14.0, K2 = 1.0 / 6.0, K3 = 9.0 / 22.0, K4 = 3.0 / 26.0, K5 = 0.25 * K3, K6 = 1.5 * K4;
+    double acc = 0.0, w = 1.0, mu, dx, dy, dz;
+    do {
+        double sx = sqrt(x), sy = sqrt(y), sz = sqrt(z);
+        double lam = sx * (sy + sz) + sy * sz;
+        acc += w / (sz * (z + lam));
+        w = 0.25 * w;
+        x = 0.25 * (x + lam);
+        y = 0.25 * (y + lam);
+        z = 0.25 * (z + lam);
+        mu = 0.2 * (x + y + 3.0 * z);
+        dx = (mu - x) / mu;
+        dy = (mu - y) / mu;
+        dz = (mu - z) / mu;
+    } while (max3(fabs(dx), fabs(dy), fabs(dz)) > S5_CARLSON_TOL);
+    double ea = dx * dy, eb = dz * dz;
+    double ec = ea - eb, ed = ea - 6.0 * eb;
+    double ee = ed + ec + ec;
+    return 3.0 * acc + w * (1.0 + ed * (-K1 + K5 * ed - K6 * dz * ee)
+        + dz * (K2 * ee + dz * (-K3 * ec + dz * K4 * ea))) / (mu * sqrt(mu));
+}
+
+/* R_C(x,y), Cauchy principal value for y < 0.  sim5elliptic.c:104-137 */
+S5_HD S5_NOINL double rc(double x, double y)
+{
+    constexpr double THIRD = 1.0 / 3.0, K1 = 0.3, K2 = 1.0 / 7.0, K3 = 0.375, K4 = 9.0 / 22.0;
+    double pre, mu, s;
+    if (y > 0.0) {
+        pre = 1.0;
+    } else {
+        double xs = x - y;
+        pre = sqrt(x) / sqrt(xs);
+        x = xs;
+        y = -y;
+    }
+    do {
+        double lam = 2.0 * sqrt(x) * sqrt(y) + y;
+        x = 0.25 * (x + lam);
+        y = 0.25 * (y + lam);
+        mu = THIRD * (x + y + y);
+        s = (y - mu) / mu;
+    } while (fabs(s) > S5_CARLSON_TOL);
+    return pre * (1.0 + s * s * (K1 + s * (K2 + s * (K3 + s * K4)))) / sqrt(mu);
+}
+
+/* R_J(x,y,z,p), principal value for p < 0; returns 0 on out-of-range arguments like the reference.
+ * sim5elliptic.c:144-206 */
+S5_HD S5_NOINL double rj(double x, double y, double z, double p)
+{
+    constexpr double K1 = 3.0 / 14.0, K2 = 1.0 / 3.0, K3 = 3.0 / 22.0, K4 = 3.0 / 26.0,
+                     K5 = 0.75 * K3, K6 = 1.5 * K4, K7 = 0.5 * K2, K8 = K3 + K3;
+    /* pow(5.0*DBL_MIN,1./3.) and 0.3*pow(0.1*DBL_MAX,1./3.) */
+    const double LO = 0x1.13c484138708ep-340, HI = 0x1.674da50c1a606p+338;
+    if ((fmin(fmin(x, y), z) < 0.0) || (fmin(fmin(x + y, x + z), fmin(y + z, fabs(p))) < LO) ||
+        (fmax(fmax(x, y), fmax(z, fabs(p))) > HI)) return 0.0;
+
+    double ca = 0.0, cb = 0.0, rcx = 0.0, acc = 0.0, w = 1.0;
+    double xt, yt, zt, pt;
+    if (p > 0.0) {
+        xt = x; yt = y; zt = z; pt = p;
+    } else {
+        xt = fmin(fmin(x, y), z);
+        zt = fmax(fmax(x, y), z);
+        yt = x + y + z - xt - zt;
+        ca = 1.0 / (yt - p);
+        cb = ca * (zt - yt) * (yt - xt);
+        pt = yt + cb;
+        double rho = xt * zt / yt;
+        double tau = p * pt / yt;
+        rcx = rc(rho, tau);
+    }
+    double mu, dx, dy, dz, dp;
+    do {
+        double sx = sqrt(xt), sy = sqrt(yt), sz = sqrt(zt);
+        double lam = sx * (sy + sz) + sy * sz;
+        double al = sq(pt * (sx + sy + sz) + sx * sy * sz);
+        double be = pt * sq(pt + lam);
+        acc += w * rc(al, be);
+        w = 0.25 * w;
+        xt = 0.25 * (xt + lam);
+        yt = 0.25 * (yt + lam);
+        zt = 0.25 * (zt + lam);
+        pt = 0.25 * (pt + lam);
+        mu = 0.2 * (xt + yt + zt + pt + pt);
+        dx = (mu - xt) / mu;
+        dy = (mu - yt) / mu;
+        dz = (mu - zt) / mu;
+        dp = (mu - pt) / mu;
+    } while (fmax(fmax(fabs(dx), fabs(dy)), fmax(fabs(dz), fabs(dp))) > S5_CARLSON_TOL);
+    double ea = dx * (dy + dz) + dy * dz;
+    double eb = dx * dy * dz;
+    double ec = dp * dp;
+    double ed = ea - 3.0 * ec;
+    double ee = eb + 2.0 * dp * (ea - ec);
+    double res = 3.0 * acc + w * (1.0 + ed * (-K1 + K5 * ed - K6 * ee) + eb * (K7 + dp * (-K8 + dp * K4))
+        + dp * ea * (K2 - dp * K3) - K2 * dp * ec) / (mu * sqrt(mu));
+    if (p <= 0.0) res = ca * (cb * res + 3.0 * (rcx - rf(xt, yt, zt)));
+    return res;
+}
+
+/* K(m).  sim5elliptic.c:217-225 */
+S5_HD S5_INL double elliptic_k(double m)
+{
+    if (m == 1.0) m = 1.0 - 1e-8;
+    return rf(0.0, 1.0 - m, 1.0);
+}
+
+/* F(phi,m) from sin(phi) and from cos(phi).  sim5elliptic.c:273-284, 254-271 */
+S5_HD S5_INL double elliptic_f_sin(double s, double m)
+{
+    if (m == 1.0) m = 0.99999999;
+    if (s == 0.0) return 0.0;
+    double s2 = sq(s);
+    return s * rf(1. - s2, 1.0 - s2 * m, 1.0);
+}
+S5_HD S5_INL double elliptic_f_cos(double c, double m)
+{
+    if (m == 1.0) m = 0.99999999;
+    if (c == 1.0) return 0.0;
+    double base = 0.0;
+    if (c < 0.0) {
+        c = -c;
+        base = 2.0 * rf(0.0, 1.0 - m, 1.0);
+    }
+    double s2 = 1.0 - sq(c);
+    return base + ((base == 0.0) ? (+1) : (-1)) * sqrt(s2) * rf(1.0 - s2, 1.0 - s2 * m, 1.0);
+}
+/* F(phi,m).  sim5elliptic.c:236-252 */
+S5_HD S5_INL double elliptic_f(double phi, double m)
+{
+    if (m == 1.0) m = 0.99999999;
+    if (phi == 0.0) return 0.0;
+    int k = 0;
+    while (fabs(phi) > M_PI / 2.) { (phi > 0) ? k++ : k--; phi += (phi > 0) ? -M_PI : +M_PI; }
+    double s, c;
+    cr_sincos(phi, &s, &c);
+    double s2 = s * s;
+    double v = (phi > 0 ? +1 : -1) * sqrt(s2) * rf(1 - s2, 1.0 - s2 * m, 1.0);
+    if (k != 0) v += 2. * k * elliptic_k(m);
+    return v;
+}
+
+/* E(phi,m) from cos(phi).  sim5elliptic.c:319-337 */
+S5_HD S5_INL double elliptic_e_cos(double c, double m)
+{
+    if (m == 1.0) m = 0.99999999;
+    if (c == 1.0) return 0.0;
+    double base = 0.0;
+    if (c < 0.0) {
+        c = -c;
+        base = 2.0 * (rf(0.0, 1.0 - m, 1.0) - m * rd(0.0, 1.0 - m, 1.0) / 3.0);
+    }
+    double c2 = sq(c);
+    double s = sqrt(1.0 - c2);
+    double q = 1.0 - m + c2 * m;
+    return base + ((base == 0.0) ? (+1) : (-1)) * s * (rf(c2, q, 1.0) - sq(s * sqrt(m)) * rd(c2, q, 1.0) / 3.0);
+}
+/* E(phi,m) from sin(phi).  sim5elliptic.c:339-355 */
+S5_HD S5_INL double elliptic_e_sin(double s, double m)
+{
+    if (m == 1.0) m = 0.99999999;
+    if (s == 0.0) return 0.0;
+    double s2 = s * s;
+    double c2 = 1.0 - s2;
+    double q = 1.0 - s2 * m;
+    return s * (rf(c2, q, 1.0) - sq(s * sqrt(m)) * rd(c2, q, 1.0) / 3.0);
+}
+
+/* complete Pi(n,m).  sim5elliptic.c:365-378 */
+S5_HD S5_INL double elliptic_pi_complete(double n, double m)
+{
+    if (isinf(n)) return 0.0;
+    if (m == 1.0) m = 0.99999999;
+    if (n == 1.0) n = 0.99999999;
+    double q = 1.0 - m;
+    return rf(0.0, q, 1.0) + n * rj(0.0, q, 1.0, 1.0 - n) / 3.0;
+}
+/* Pi(phi,n,m) from cos(phi).  sim5elliptic.c:425-450 */
+S5_HD S5_INL double elliptic_pi_cos(double c, double n, double m)
+{
+    if (isinf(n)) return 0.0;
+    if (c == 1.0) return 0.0;
+    if (c == 0.0) return elliptic_pi_complete(n, m);
+    if (m == 1.0) m = 0.99999999;
+    double base = 0.0;
+    if (c < 0.0) {
+        c = -c;
+        base = 2.0 * ((rf(0.0, 1.0 - m, 1.0) + n * rj(0.0, 1.0 - m, 1.0, 1.0 - n) / 3.0));
+    }
+    double c2 = sq(c);
+    double s = sqrt(1.0 - c2);
+    double ns2 = -n * (1.0 - c2);
+    double q = 1.0 - (1.0 - c2) * m;
+    return base + ((base == 0.0) ? (+1) : (-1)) * s * (rf(c2, q, 1.0) - ns2 * rj(c2, q, 1.0, 1.0 + ns2) / 3.0);
+}
+/* Pi(phi,n,m) from sin(phi).  sim5elliptic.c:453-474 */
+S5_HD S5_INL double elliptic_pi_sin(double s, double n, double m)
+{
+    double s2 = s * s;
+    if (isinf(n)) return 0.0;
+    if (m == 1.0) m = 0.99999999;
+    if (s == 0.0) return 0.0;
+    if (s == 1.0) return elliptic_pi_complete(n, m);
+    double c2 = 1.0 - s2;
+    double ns2 = -n * s2;
+    double q = 1.0 - s2 * m;
+    return s * (rf(c2, q, 1.0) - ns2 * rj(c2, q, 1.0, 1.0 + ns2) / 3.0);
+}
+
+/* inverse Jacobi functions.  sim5elliptic.c:480-486, 492-514, 522-528 */
+S5_HD S5_INL double jacobi_isn(double z, double m)
+{
+    if (fabs(m - 0.0) < 1e-8) return cr_asin(z);
+    if (fabs(m - 1.0) < 1e-8) return cr_log(sqrt((1. + z) / (1. - z)));
+    return z * rf(1.0 - z * z, 1.0 - m * z * z, 1.0);
+}
+S5_HD S5_INL double jacobi_icn(double z, double m)
+{
+    if ((z > +1.0) && (z < +1.0 + 1e-8)) z = +1.0;
+    if ((z < -1.0) && (z > -1.0 - 1e-8)) z = -1.0;
+    if ((m > +1.0) && (m < +1.0 + 1e-8)) m = 1.0;
+    if ((m < 0.0) && (m > 0.0 - 1e-8)) m = 0.0;
+
+    if (z == 0.0) return elliptic_k(m);
+    if (z == 1.0) return 0.0;
+    if (m == 0.0) return cr_acos(z);
+    if (m == 1.0) return cr_log((1. + sqrt(1. - z)) / z);
+
+    double v = sqrt(1. - z * z) * rf(z * z, 1.0 - m * (1. - z * z), 1.0);
+    return (z > 0.0) ? v : 2. / sqrt(1. - m) * elliptic_f_sin(-z, m / (m - 1.)) + v;
+}
+S5_HD S5_INL double jacobi_itn(double z, double m)
+{
+    if (m == 0.0) return cr_atan(z);
+    if (m == 1.0) return cr_log(z + sqrt(1. + z * z));
+    return jacobi_isn(sqrt(z * z / (1. + z * z)), m);
+}
+
+/* sn, cn, dn by descending Landen (AGM) + back substitution.  sim5elliptic.c:535-596 */
+S5_HD S5_NOINL void jacobi_sncndn(double u, double m, double* sn_, double* cn_, double* dn_)
+{
+    if (m == 1.0) m = 0.999999999;
+    const double CA = 1.0e-8;
+    double sn, cn, dn;
+    double emc = 1.0 - m;
+    double d = 1.0;
+    if (emc != 0.0) {
+        bool neg = (emc < 0.0);
+        if (neg) {
+            d = 1.0 - emc;
+            emc /= -1.0 / d;
+            u *= (d = sqrt(d));
+        }
+        double a = 1.0, c = 0.0;
+        double am[13], gm[13];
+        int last = 0;
+        dn = 1.0;
+        for (int i = 0; i < 13; i++) {
+            last = i;
+            am[i] = a;
+            gm[i] = (emc = sqrt(emc));
+            c = 0.5 * (a + emc);
+            if (fabs(a - emc) <= CA * a) break;
+            emc *= a;
+            a = c;
+        }
+        u *= c;
+        cr_sincos(u, &sn, &cn);
+        if (sn != 0.0) {
+            a = cn / sn;
+            c *= a;
+            for (int i = last; i >= 0; i--) {
+                double b = am[i];
+                a *= c;
+                c *= dn;
+                dn = (gm[i] + a) / (b + a);
+                a = c / b;
+            }
+            a = 1.0 / sqrt(c * c + 1.0);
+            sn = (sn >= 0.0 ? a : -a);
+            cn = c * sn;
+        }
+        if (neg) {
+            a = dn;
+            dn = cn;
+            cn = a;
+            sn /= d;
+        }
+    } else {
+        cn = 1.0 / cosh(u);
+        dn = cn;
+        sn = tanh(u);
+    }
+    *sn_ = sn; *cn_ = cn; *dn_ = dn;
+}
+S5_HD S5_INL double jacobi_sn(double u, double m) { double s, c, d; jacobi_sncndn(u, m, &s, &c, &d); return s; }
+S5_HD S5_INL double jacobi_cn(double u, double m) { double s, c, d; jacobi_sncndn(u, m, &s, &c, &d); return c; }
+S5_HD S5_INL double jacobi_dn(double u, double m) { double s, c, d; jacobi_sncndn(u, m, &s, &c, &d); return d; }
+
+/* int (1-b sn^2)/(1-a sn^2) du, B&F 340.01.  sim5elliptic.c:676-690 */
+S5_HD S5_INL double integral_Z1(double a, double b, double u, double m)
+{
+    double sn, cn, dn;
+    jacobi_sncndn(u, m, &sn, &cn, &dn);
+    return 1. / a * ((a - b) * elliptic_pi_cos(cn, a, m) + b * u);
+}
+/* the same at u = 0: sn=0, cn=1 => Pi = 0 (or 0 for infinite a); keeps the reference's signed-zero/NaN result */
+S5_HD S5_INL double integral_Z1_at0(double a, double b)
+{
+    return 1. / a * ((a - b) * 0.0 + b * 0.0);
+}
+
+/* glibc's catan(), restricted to the two shapes integral_R1 can produce: a real argument (x, +-0)
+ * and a purely imaginary one (+-0, y).  Returns the complex result.  (glibc s_catan_template.c) */
+S5_HD S5_INL void catan_axis(double re, double im, double* ore, double* oim)
+{
+    if (re == 0.0 && im == 0.0) { *ore = re; *oim = im; return; }
+    double absx = fabs(re), absy = fabs(im);
+    if (absx < absy) { double t = absx; absx = absy; absy = t; }
+    double den = (1 - absx) * (1 + absx);          /* absy == 0 < eps/2 */
+    if (den == 0) den = 0;
+    *ore = 0.5 * cr_atan2(2 * re, den);
+    if (fabs(im) == 1) {
+        *oim = copysign(0.5, im) * (0.6931471805599453 - cr_log(fabs(re)));
+    } else {
+        double r2 = 0.0;                           /* |re| is 0 or the argument is real: r2 = re*re */
+        if (fabs(re) >= 4.930380657631324e-32) r2 = re * re;
+        double num = im + 1;
+        num = r2 + num * num;
+        double dd_ = im - 1;
+        dd_ = r2 + dd_ * dd_;
+        double f = num / dd_;
+        if (f < 0.5) {
+            *oim = 0.25 * cr_log(f);
+        } else {
+            num = 4 * im;
+            *oim = 0.25 * crm::cr_log1p(num / dd_);
+        }
+    }
+}
+
+/* int du/(1+a cn u), B&F 341.03 / 361.54.  sim5elliptic.c:755-792 (complex arithmetic spelled out) */
+S5_HD S5_INL double integral_R1(double a, double u, double m)
+{
+    double a2 = sq(a);
+    double n = a2 / (a2 - 1.);
+    double sn, cn, dn;
+    jacobi_sncndn(u, m, &sn, &cn, &dn);
+    double mma = (m + (1. - m) * a2) / (1. - a2);
+    double f1re;
+    if (fabs(mma) > 1e-5) {
+        /* csqrt(1/mma) * catan( csqrt(mma)*sn/dn ) */
+        double inv = 1. / mma;
+        double s1re, s1im, wre, wim;
+        if (inv < 0.0) { s1re = 0.0; s1im = sqrt(-inv); } else { s1re = fabs(sqrt(inv)); s1im = 0.0; }
+        if (mma < 0.0) { wre = 0.0; wim = sqrt(-mma); } else { wre = fabs(sqrt(mma)); wim = 0.0; }
+        wre = wre * sn / dn;
+        wim = wim * sn / dn;
+        double cre, cim;
+        catan_axis(wre, wim, &cre, &cim);
+        f1re = s1re * cre - s1im * cim;
+    } else {
+        f1re = sn / dn;
+    }
+    double ellpi = elliptic_pi_cos(cn, n, m);
+    return 1. / (1. - a2) * (ellpi + a * f1re);
+}
+
+/* int_a^X dx/((x-p) sqrt((x-a)(x-b)(x-c)(x-d))), B&F 258.39.  sim5elliptic.c:1017-1029 */
+S5_HD S5_INL double integral_R_rp_re(double a, double b, double c, double d, double p, double X)
+{
+    double m2 = ((b - c) * (a - d)) / ((a - c) * (b - d));
+    double sn = sqrt(((b - d) * (X - a)) / ((a - d) * (X - b)));
+    double u1 = jacobi_isn(sn, m2);
+    double a2 = (a - d) / (b - d);
+    double c2 = ((p - b) * (a - d)) / ((p - a) * (b - d));
+    return -2.0 / sqrt((a - c) * (b - d)) / (p - a) * (integral_Z1(c2, a2, u1, m2) - integral_Z1_at0(c2, a2));
+}
+/* X -> infinity.  sim5elliptic.c:1032-1044 */
+S5_HD S5_INL double integral_R_rp_re_inf(double a, double b, double c, double d, double p)
+{
+    double m2 = ((b - c) * (a - d)) / ((a - c) * (b - d));
+    double sn = sqrt((b - d) / (a - d));
+    double u1 = jacobi_isn(sn, m2);
+    double a2 = (a - d) / (b - d);
+    double c2 = ((p - b) * (a - d)) / ((p - a) * (b - d));
+    return -2.0 / sqrt((a - c) * (b - d)) / (p - a) * (integral_Z1(c2, a2, u1, m2) - integral_Z1_at0(c2, a2));
+}
+/* int_X1^inf dx/((x-p) sqrt((x-a)(x-b)(x-c)(x-c*))), c = u+iv, B&F 260.04.  sim5elliptic.c:1081-1112 */
+S5_HD S5_INL double integral_R_rp_cc2_inf(double a, double b, double cre, double cim, double p, double X1)
+{
+    double u = cre;
+    double v2 = sq(cim);
+    double A = sqrt(sq(a - u) + v2);
+    double B = sqrt(sq(b - u) + v2);
+    double m = (sq(A + B) - sq(a - b)) / (4. * A * B);
+    double g = 1. / sqrt(A * B);
+    double alpha1 = (B * a + b * A - p * A - p * B) / (B * a - b * A + p * A - p * B);
+    double alpha2 = (B + A) / (B - A);
+    double u1 = elliptic_f_cos((X1 * (A - B) + a * B - b * A) / (X1 * (A + B) - a * B - b * A), m);
+    double u2 = elliptic_f_cos((A - B) / (A + B), m);
+    double t0 = alpha2 * (u2 - u1);
+    double t1 = (alpha1 - alpha2) * (integral_R1(alpha1, u2, m) - integral_R1(alpha1, u1, m));
+    return (B - A) * g / (B * a + b * A - p * A - p * B) * (t0 + t1);
+}
+/* int_X^b dx/((p-x^2) sqrt((a^2+x^2)(b^2-x^2))), B&F 213.02.  sim5elliptic.c:1142-1159 */
+S5_HD S5_INL double integral_T_mp(double a2, double b2, double p, double X)
+{
+    double m = b2 / (a2 + b2);
+    double n = b2 / (b2 - p);
+    if (X >= 0.0)
+        return 1. / sqrt(a2 + b2) / (p - b2) * elliptic_pi_cos(X / sqrt(b2), n, m);
+    else
+        return 1. / sqrt(a2 + b2) / (p - b2) * (2. * elliptic_pi_complete(n, m) - elliptic_pi_cos(-X / sqrt(b2), n, m));
+}
+
+} /* namespace s5 */
+#endif
