@@ -1,0 +1,210 @@
+"""ctypes/numpy binding of libsim5b200.so (a Python binding for the batched
+entry that needs no SWIG).  Mirrors the reference's Python-side usage (python/sim5diskraytrace.py:
+DiskRaytrace.image) at image granularity: one call traces the whole image on the GPU.
+
+There is no CPU path: if the CUDA library is missing or no device is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsim5b200.so")
+
+_lib = None
+
+
+class Sim5Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libsim5b200.so (built in-tree by sim5_b200/csrc/Makefile or __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Sim5Error("CUDA library %s is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                            "sim5_b200 has no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.sim5_gpu_init.argtypes = [C.c_int]
+        L.sim5_gpu_init.restype = C.c_int
+        L.sim5_gpu_device_count.restype = C.c_int
+        L.sim5_last_error.restype = C.c_char_p
+        L.sim5_version.restype = C.c_char_p
+        L.sim5_host_alloc.argtypes = [C.c_size_t]
+        L.sim5_host_alloc.restype = C.c_void_p
+        L.sim5_host_free.argtypes = [C.c_void_p]
+        L.sim5_device_alloc.argtypes = [C.c_size_t]
+        L.sim5_device_alloc.restype = C.c_void_p
+        L.sim5_device_free.argtypes = [C.c_void_p]
+        L.sim5_device_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.sim5_device_to_host.restype = C.c_int
+        L.sim5_default_params.argtypes = [C.c_int, C.POINTER(abi.ImageParams)]
+        L.sim5_default_params.restype = C.c_int
+        L.sim5_trace_image.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(abi.ImageOut), C.POINTER(abi.TraceStats)]
+        L.sim5_trace_image.restype = C.c_int
+        L.sim5_fp64_peak_tflops.argtypes = [C.c_int, C.c_int]
+        L.sim5_fp64_peak_tflops.restype = C.c_double
+        dp = C.POINTER(C.c_double)
+        L.sim5_batch_rf.argtypes = [C.c_int64, dp, dp, dp, dp]
+        L.sim5_batch_rd.argtypes = [C.c_int64, dp, dp, dp, dp]
+        L.sim5_batch_rc.argtypes = [C.c_int64, dp, dp, dp]
+        L.sim5_batch_rj.argtypes = [C.c_int64, dp, dp, dp, dp, dp]
+        L.sim5_batch_sncndn.argtypes = [C.c_int64, dp, dp, dp, dp, dp]
+        L.sim5_batch_libm.argtypes = [C.c_int, C.c_int64, dp, dp, dp]
+        for f in ("sim5_batch_rf", "sim5_batch_rd", "sim5_batch_rc", "sim5_batch_rj", "sim5_batch_sncndn", "sim5_batch_libm"):
+            getattr(L, f).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc, what="sim5 call"):
+    if rc != abi.OK:
+        msg = lib().sim5_last_error()
+        raise Sim5Error("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def init(device=0):
+    check(lib().sim5_gpu_init(device), "sim5_gpu_init")
+
+
+def last_error():
+    m = lib().sim5_last_error()
+    return m.decode() if m else ""
+
+
+_NP = {C.c_double: np.float64, C.c_int32: np.int32, C.c_uint8: np.uint8}
+
+
+class PinnedArray:
+    """numpy view over pinned host memory from sim5_host_alloc (freed with the object)."""
+
+    def __init__(self, n, dtype):
+        self.nbytes = int(n) * np.dtype(dtype).itemsize
+        self.ptr = lib().sim5_host_alloc(max(self.nbytes, 1))
+        if not self.ptr:
+            raise Sim5Error("sim5_host_alloc failed: " + last_error())
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().sim5_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class HostPlanes:
+    """Output planes of one image in pinned host memory + the sim5_image_out struct pointing at them."""
+
+    def __init__(self, p, pinned=True):
+        n = p.nx * p.ny
+        self.out = abi.ImageOut()
+        self.arrays = {}
+        self._keep = []
+        self.shape = (p.ny, p.nx)
+        for name, bit, ct in abi.PLANES:
+            if p.outputs & bit:
+                if pinned:
+                    pa = PinnedArray(n, _NP[ct])
+                    self._keep.append(pa)
+                    a = pa.array
+                else:
+                    a = np.zeros(n, dtype=_NP[ct])
+                self.arrays[name] = a
+                setattr(self.out, name, a.ctypes.data)
+        if p.mode == abi.MODE_HISTOGRAM:
+            nh = p.n_spin * p.n_incl * p.n_bins
+            a = np.zeros(nh, dtype=np.float64)
+            self.arrays["hist"] = a
+            self.out.hist = a.ctypes.data
+
+    def __getitem__(self, k):
+        return self.arrays[k]
+
+    def image(self, k):
+        return self.arrays[k].reshape(self.shape)
+
+
+def trace_image(p, planes=None, pinned=True):
+    """Trace one image (or its rows [row_begin,row_end)) on the GPU.  Returns (HostPlanes, TraceStats)."""
+    if planes is None:
+        planes = HostPlanes(p, pinned=pinned)
+    st = abi.TraceStats()
+    check(lib().sim5_trace_image(C.byref(p), C.byref(planes.out), C.byref(st)), "sim5_trace_image")
+    return planes, st
+
+
+def trace_image_device(p, out_struct):
+    """Trace with caller-owned DEVICE planes (e.g. torch tensors' data_ptr()); nothing is copied to the host."""
+    p.flags |= abi.FLAG_DEVICE_PTRS
+    st = abi.TraceStats()
+    check(lib().sim5_trace_image(C.byref(p), C.byref(out_struct), C.byref(st)), "sim5_trace_image")
+    return st
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _batch(fn, ins, nout=1, pre=()):
+    ins = [np.ascontiguousarray(a, dtype=np.float64) for a in ins]
+    n = ins[0].size
+    outs = [np.empty(n, dtype=np.float64) for _ in range(nout)]
+    check(fn(*pre, C.c_int64(n), *[_dp(a) for a in ins], *[_dp(o) for o in outs]), fn.__name__)
+    return outs[0] if nout == 1 else outs
+
+
+def batch_rf(x, y, z):
+    return _batch(lib().sim5_batch_rf, [x, y, z])
+
+
+def batch_rd(x, y, z):
+    return _batch(lib().sim5_batch_rd, [x, y, z])
+
+
+def batch_rc(x, y):
+    return _batch(lib().sim5_batch_rc, [x, y])
+
+
+def batch_rj(x, y, z, p):
+    return _batch(lib().sim5_batch_rj, [x, y, z, p])
+
+
+def batch_sncndn(u, m):
+    return _batch(lib().sim5_batch_sncndn, [u, m], nout=3)
+
+
+LIBM_OPS = {"sin": 0, "cos": 1, "log": 2, "atan2": 3, "acos": 4, "asin": 5, "atan": 6,
+            "pow_third": 7, "pow_1p5": 8, "pow_4": 9, "exp": 10}
+
+
+def batch_libm(op, a, b=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if b is None:
+        b = np.zeros_like(a)
+    return _batch(lib().sim5_batch_libm, [a, b], pre=(C.c_int(LIBM_OPS[op]),))
+
+
+def fp64_peak_tflops(device=0, iters=8192):
+    v = lib().sim5_fp64_peak_tflops(device, iters)
+    if v < 0:
+        raise Sim5Error("sim5_fp64_peak_tflops failed: " + last_error())
+    return v
+
+
+def write_text_dump(path, planes, p):
+    """Text dump compatible with the reference example (disk-image.c:116-120): `y x flux g` per line,
+    blank line after each row."""
+    f_img = planes.image("flux")
+    g_img = planes.image("g")
+    with open(path, "w") as fh:
+        for iy in range(p.ny):
+            for ix in range(p.nx):
+                fh.write("%d  %d  %e  %e\n" % (iy, ix, np.float32(f_img[iy, ix]), np.float32(g_img[iy, ix])))
+            fh.write("\n")

@@ -1,0 +1,909 @@
+/*
+ * capi.cu -- the C-ABI of libsim5b200.so: context, the batched sim5_trace_image entry, batched
+ * element-wise entries, the FP64 peak microbenchmark, and the scalar sim5lib.h API executed as
+ * one-thread device launches.
+ *
+ * No function in this file computes ray physics on the host.  Host code only (a) evaluates the
+ * per-image constants of image_consts.h with the host libm, (b) moves bytes, (c) launches kernels.
+ * Without a usable CUDA device every entry fails (SIM5_ERR_NO_DEVICE / NaN / FALSE) and says so on
+ * stderr once.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <mutex>
+#include <string>
+
+#include "sim5_b200.h"
+#include "kernels.cuh"
+
+using s5::DevOut;
+using s5::DevStats;
+
+/* ------------------------------------------------------------------ */
+/* context                                                             */
+/* ------------------------------------------------------------------ */
+namespace {
+
+struct Scratch {                  /* mapped pinned memory shared by host and device for scalar calls */
+    s5::Geodesic g;
+    s5::RayData rtd;
+    s5::Metric m;
+    s5::Tetrad t;
+    double v[96];
+    int iv[8];
+};
+
+struct Plane { void* p = nullptr; size_t bytes = 0; };
+
+struct Context {
+    bool ready = false;
+    bool warned = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    Scratch* h_scr = nullptr;
+    Scratch* d_scr = nullptr;
+    S5ImageConsts* h_consts = nullptr;    /* pinned staging */
+    S5ImageConsts* d_consts = nullptr;
+    size_t consts_cap = 0;
+    unsigned long long* d_counter = nullptr;
+    DevStats* d_stats = nullptr;
+    DevStats* h_stats = nullptr;          /* pinned */
+    Plane planes[12];
+    Plane hist;
+    void* batch[8] = {nullptr};
+    size_t batch_bytes[8] = {0};
+    std::string last_error;
+    std::mutex mu;
+    /* disk_nt_setup() state of the scalar API */
+    sim5_image_params disk_params;
+    bool disk_set = false;
+};
+
+Context g_ctx;
+
+void set_error(const std::string& s) { g_ctx.last_error = s; }
+
+bool cuda_ok(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return true;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return false;
+}
+#define CK(call) do { if (!cuda_ok((call), #call)) return SIM5_ERR_CUDA; } while (0)
+
+int no_device(const char* why)
+{
+    set_error(std::string("no usable CUDA device (") + why + "); libsim5b200 has no CPU path");
+    if (!g_ctx.warned) {
+        fprintf(stderr, "sim5_b200: %s\n", g_ctx.last_error.c_str());
+        g_ctx.warned = true;
+    }
+    return SIM5_ERR_NO_DEVICE;
+}
+
+int ensure_init(int device)
+{
+    Context& c = g_ctx;
+    if (c.ready && (device < 0 || device == c.device)) return SIM5_OK;
+    if (c.ready) sim5_gpu_shutdown();
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return no_device(e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"); }
+    if (device < 0) device = 0;
+    if (device >= n) { set_error("device ordinal out of range"); return SIM5_ERR_BAD_PARAM; }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+        return no_device(buf);
+    }
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c.ev0)); CK(cudaEventCreate(&c.ev1)); CK(cudaEventCreate(&c.ev2)); CK(cudaEventCreate(&c.ev3));
+    CK(cudaHostAlloc((void**)&c.h_scr, sizeof(Scratch), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&c.d_scr, c.h_scr, 0));
+    c.consts_cap = 1;
+    CK(cudaHostAlloc((void**)&c.h_consts, sizeof(S5ImageConsts), cudaHostAllocDefault));
+    CK(cudaMalloc((void**)&c.d_consts, sizeof(S5ImageConsts)));
+    CK(cudaMalloc((void**)&c.d_counter, sizeof(unsigned long long)));
+    CK(cudaMalloc((void**)&c.d_stats, sizeof(DevStats)));
+    CK(cudaHostAlloc((void**)&c.h_stats, sizeof(DevStats), cudaHostAllocDefault));
+    /* the stepper keeps ~100 doubles of live state per thread and calls non-inlined Carlson routines */
+    cudaDeviceSetLimit(cudaLimitStackSize, 8192);
+    c.ready = true;
+    return SIM5_OK;
+}
+
+int reserve(Plane& pl, size_t bytes)
+{
+    if (pl.bytes >= bytes && pl.p) return SIM5_OK;
+    if (pl.p) { cudaFree(pl.p); pl.p = nullptr; pl.bytes = 0; }
+    CK(cudaMalloc(&pl.p, bytes));
+    pl.bytes = bytes;
+    return SIM5_OK;
+}
+
+int reserve_consts(size_t n)
+{
+    Context& c = g_ctx;
+    if (c.consts_cap >= n) return SIM5_OK;
+    cudaFreeHost(c.h_consts); cudaFree(c.d_consts);
+    CK(cudaHostAlloc((void**)&c.h_consts, n * sizeof(S5ImageConsts), cudaHostAllocDefault));
+    CK(cudaMalloc((void**)&c.d_consts, n * sizeof(S5ImageConsts)));
+    c.consts_cap = n;
+    return SIM5_OK;
+}
+
+template <class K>
+int persistent_grid(K kernel, int threads)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return g_ctx.sm_count * per_sm;
+}
+
+const struct { unsigned bit; size_t elem; } kPlaneInfo[12] = {
+    {SIM5_OUT_R, 8}, {SIM5_OUT_PHI, 8}, {SIM5_OUT_G, 8}, {SIM5_OUT_FLUX, 8}, {SIM5_OUT_CHI, 8}, {SIM5_OUT_DELTA, 8},
+    {SIM5_OUT_MUE, 8}, {SIM5_OUT_INTENSITY, 8}, {SIM5_OUT_TAU, 8}, {SIM5_OUT_QERR, 8}, {SIM5_OUT_STEPS, 4}, {SIM5_OUT_STATUS, 1},
+};
+void* host_plane(const sim5_image_out* o, int i)
+{
+    switch (i) {
+        case 0: return o->r; case 1: return o->phi; case 2: return o->g; case 3: return o->flux;
+        case 4: return o->chi; case 5: return o->delta; case 6: return o->mue; case 7: return o->intensity;
+        case 8: return o->tau; case 9: return o->qerr; case 10: return o->steps; case 11: return o->status;
+    }
+    return nullptr;
+}
+void set_dev_plane(DevOut* d, int i, void* p)
+{
+    switch (i) {
+        case 0: d->r = (double*)p; break; case 1: d->phi = (double*)p; break; case 2: d->g = (double*)p; break;
+        case 3: d->flux = (double*)p; break; case 4: d->chi = (double*)p; break; case 5: d->delta = (double*)p; break;
+        case 6: d->mue = (double*)p; break; case 7: d->intensity = (double*)p; break; case 8: d->tau = (double*)p; break;
+        case 9: d->qerr = (double*)p; break; case 10: d->steps = (int*)p; break; case 11: d->status = (unsigned char*)p; break;
+    }
+}
+
+void lattice_params(const sim5_image_params* p, int img, sim5_image_params* q)
+{
+    int js = img / p->n_incl, ki = img % p->n_incl;
+    *q = *p;
+    q->mode = SIM5_MODE_EQPLANE;
+    q->row_begin = 0; q->row_end = 0;
+    q->outputs = SIM5_OUT_G | SIM5_OUT_FLUX;
+    q->bh_spin = (p->n_spin > 1) ? p->spin_max * (double)js / (double)(p->n_spin - 1) : p->spin_max;
+    if (q->bh_spin < 1e-4) q->bh_spin = 1e-4;
+    double ideg = (p->n_incl > 1) ? p->incl_min_deg + (p->incl_max_deg - p->incl_min_deg) * (double)ki / (double)(p->n_incl - 1) : p->incl_min_deg;
+    q->incl = ideg / 180.0 * M_PI;
+    q->rmax = s5_host_r_ms(q->bh_spin) + p->rmax_offset;
+    q->r_emit_min = 0.0;
+}
+
+int trace_histogram(const sim5_image_params* p, const sim5_image_out* out, sim5_trace_stats* stats)
+{
+    Context& c = g_ctx;
+    if (!out->hist) { set_error("HISTOGRAM mode needs out->hist"); return SIM5_ERR_NO_OUTPUT; }
+    if (p->n_spin < 1 || p->n_incl < 1 || p->n_bins < 1 || !(p->g_max > p->g_min)) { set_error("bad lattice"); return SIM5_ERR_BAD_PARAM; }
+    int nimg = p->n_spin * p->n_incl;
+    int lb = p->lattice_begin, le = p->lattice_end;
+    if (lb == 0 && le == 0) le = nimg;
+    if (lb < 0 || le > nimg || lb >= le) { set_error("bad lattice range"); return SIM5_ERR_BAD_PARAM; }
+    int rc = reserve_consts((size_t)nimg);
+    if (rc) return rc;
+    for (int img = lb; img < le; img++) {
+        sim5_image_params q;
+        lattice_params(p, img, &q);
+        s5_fill_image_consts(&q, &c.h_consts[img]);
+    }
+    size_t hbytes = (size_t)nimg * p->n_bins * sizeof(double);
+    bool devptr = (p->flags & SIM5_FLAG_DEVICE_PTRS) != 0;
+    double* d_hist = out->hist;
+    if (!devptr) { rc = reserve(c.hist, hbytes); if (rc) return rc; d_hist = (double*)c.hist.p; }
+    CK(cudaEventRecord(c.ev0, c.stream));
+    CK(cudaMemcpyAsync(c.d_consts + lb, c.h_consts + lb, (size_t)(le - lb) * sizeof(S5ImageConsts), cudaMemcpyHostToDevice, c.stream));
+    CK(cudaMemsetAsync(d_hist + (size_t)lb * p->n_bins, 0, (size_t)(le - lb) * p->n_bins * sizeof(double), c.stream));
+    CK(cudaMemsetAsync(c.d_counter, 0, sizeof(unsigned long long), c.stream));
+    CK(cudaMemsetAsync(c.d_stats, 0, sizeof(DevStats), c.stream));
+    int grid = persistent_grid(s5::k_trace_histogram, S5_CTA_THREADS);
+    CK(cudaEventRecord(c.ev1, c.stream));
+    s5::k_trace_histogram<<<grid, S5_CTA_THREADS, 0, c.stream>>>(c.d_consts, lb, le, d_hist, c.d_counter, c.d_stats);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c.ev2, c.stream));
+    if (!devptr) CK(cudaMemcpyAsync(out->hist + (size_t)lb * p->n_bins, d_hist + (size_t)lb * p->n_bins, (size_t)(le - lb) * p->n_bins * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaMemcpyAsync(c.h_stats, c.d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaEventRecord(c.ev3, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->rays = (int64_t)(le - lb) * p->nx * p->ny;
+        for (int i = 0; i < 32; i++) stats->class_count[i] = (int64_t)c.h_stats->cls[i];
+        for (int i = 0; i < 8; i++) stats->gtype_count[i] = (int64_t)c.h_stats->gtype[i];
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c.ev1, c.ev2); stats->kernel_ms = ms;
+        cudaEventElapsedTime(&ms, c.ev0, c.ev3); stats->total_ms = ms;
+        stats->kernel_launches = 1; stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = S5_CTA_THREADS;
+    }
+    return SIM5_OK;
+}
+
+} /* anonymous namespace */
+
+/* ------------------------------------------------------------------ */
+/* lifecycle                                                           */
+/* ------------------------------------------------------------------ */
+extern "C" int sim5_gpu_init(int device)
+{
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    return ensure_init(device);
+}
+
+extern "C" void sim5_gpu_shutdown(void)
+{
+    Context& c = g_ctx;
+    if (!c.ready) return;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    for (auto& pl : c.planes) { if (pl.p) cudaFree(pl.p); pl = Plane(); }
+    if (c.hist.p) cudaFree(c.hist.p); c.hist = Plane();
+    for (int i = 0; i < 8; i++) { if (c.batch[i]) cudaFree(c.batch[i]); c.batch[i] = nullptr; c.batch_bytes[i] = 0; }
+    cudaFreeHost(c.h_scr); cudaFreeHost(c.h_consts); cudaFree(c.d_consts); cudaFree(c.d_counter); cudaFree(c.d_stats); cudaFreeHost(c.h_stats);
+    cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1); cudaEventDestroy(c.ev2); cudaEventDestroy(c.ev3);
+    cudaStreamDestroy(c.stream); cudaStreamDestroy(c.copy_stream);
+    c.ready = false;
+}
+
+extern "C" int sim5_gpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char* sim5_last_error(void) { return g_ctx.last_error.c_str(); }
+extern "C" const char* sim5_version(void) { return "sim5_b200 0.1 (sm_100a, fp64)"; }
+
+extern "C" void* sim5_host_alloc(size_t bytes)
+{
+    if (ensure_init(-1) != SIM5_OK) return nullptr;
+    void* p = nullptr;
+    if (!cuda_ok(cudaHostAlloc(&p, bytes, cudaHostAllocDefault), "cudaHostAlloc")) return nullptr;
+    return p;
+}
+extern "C" void sim5_host_free(void* p) { if (p) cudaFreeHost(p); }
+extern "C" void* sim5_device_alloc(size_t bytes)
+{
+    if (ensure_init(-1) != SIM5_OK) return nullptr;
+    void* p = nullptr;
+    if (!cuda_ok(cudaMalloc(&p, bytes), "cudaMalloc")) return nullptr;
+    return p;
+}
+extern "C" void sim5_device_free(void* p) { if (p) cudaFree(p); }
+extern "C" int sim5_device_to_host(void* dst, const void* src, size_t bytes)
+{
+    if (ensure_init(-1) != SIM5_OK) return SIM5_ERR_NO_DEVICE;
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return SIM5_OK;
+}
+
+/* the open parameters of the five BASELINE configs */
+extern "C" int sim5_default_params(int cfg, sim5_image_params* p)
+{
+    if (!p || cfg < 1 || cfg > 5) return SIM5_ERR_BAD_PARAM;
+    memset(p, 0, sizeof(*p));
+    p->struct_size = (int32_t)sizeof(*p);
+    p->max_order = 1;
+    p->disk_mass = 10.0; p->disk_mdot = 0.1; p->disk_alpha = 0.1;
+    p->precision_factor = 0.01; p->r_start = 50.0; p->step_max = 1e9; p->max_steps = 100000;
+    p->torus_rc = 10.0; p->torus_w = 2.0; p->torus_h = 0.3; p->torus_j0 = 1.0; p->torus_k0 = 0.05;
+    p->n_spin = 64; p->n_incl = 32; p->n_bins = 256;
+    p->spin_max = 0.998; p->incl_min_deg = 5.0; p->incl_max_deg = 85.0;
+    p->g_min = 0.0; p->g_max = 2.0; p->rmax_offset = 20.0;
+    switch (cfg) {
+        case 1: p->mode = SIM5_MODE_EQPLANE; p->nx = p->ny = 512; p->bh_spin = 0.9; p->incl = 70.0 / 180.0 * M_PI;
+                p->rmax = s5_host_r_ms(p->bh_spin) + 8.0; p->outputs = SIM5_OUT_R | SIM5_OUT_G | SIM5_OUT_FLUX | SIM5_OUT_STATUS; break;
+        case 2: p->mode = SIM5_MODE_EQPLANE; p->nx = p->ny = 4096; p->bh_spin = 0.998; p->incl = 75.0 / 180.0 * M_PI;
+                p->rmax = s5_host_r_ms(p->bh_spin) + 20.0; p->outputs = SIM5_OUT_R | SIM5_OUT_PHI | SIM5_OUT_G | SIM5_OUT_FLUX | SIM5_OUT_STATUS; break;
+        case 3: p->mode = SIM5_MODE_POLARIZED; p->nx = p->ny = 2048; p->bh_spin = 0.94; p->incl = 75.0 / 180.0 * M_PI;
+                p->rmax = s5_host_r_ms(p->bh_spin) + 20.0;
+                p->outputs = SIM5_OUT_R | SIM5_OUT_PHI | SIM5_OUT_G | SIM5_OUT_FLUX | SIM5_OUT_CHI | SIM5_OUT_DELTA | SIM5_OUT_STATUS; break;
+        case 4: p->mode = SIM5_MODE_STEPWISE; p->nx = p->ny = 1024; p->bh_spin = 0.9; p->incl = 60.0 / 180.0 * M_PI;
+                p->rmax = 25.0; p->outputs = SIM5_OUT_INTENSITY | SIM5_OUT_TAU | SIM5_OUT_STEPS | SIM5_OUT_STATUS; break;
+        case 5: p->mode = SIM5_MODE_HISTOGRAM; p->nx = p->ny = 1024; p->bh_spin = 0.998; p->incl = 75.0 / 180.0 * M_PI;
+                p->rmax = 0.0; p->outputs = 0; break;
+    }
+    {   /* ellK(torus_rc, a), sim5kerr.c:1050-1071 */
+        double r = p->torus_rc, a = p->bh_spin;
+        p->torus_ell = (r * r - 2. * a * sqrt(r) + a * a) / (sqrt(r) * r - 2. * sqrt(r) + a);
+    }
+    return SIM5_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* the batched entry                                                   */
+/* ------------------------------------------------------------------ */
+extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out* out, sim5_trace_stats* stats)
+{
+    if (!p || !out) { set_error("null params/out"); return SIM5_ERR_BAD_PARAM; }
+    if (p->struct_size != (int32_t)sizeof(sim5_image_params)) { set_error("sim5_image_params.struct_size mismatch"); return SIM5_ERR_BAD_PARAM; }
+    if (p->nx <= 0 || p->ny <= 0) { set_error("empty image"); return SIM5_ERR_BAD_PARAM; }
+    if (p->mode < SIM5_MODE_EQPLANE || p->mode > SIM5_MODE_HISTOGRAM) { set_error("unknown mode"); return SIM5_ERR_BAD_PARAM; }
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    int rc = ensure_init(p->device);
+    if (rc) return rc;
+    Context& c = g_ctx;
+    if (p->mode == SIM5_MODE_HISTOGRAM) return trace_histogram(p, out, stats);
+
+    int rb = p->row_begin, re = p->row_end;
+    if (rb == 0 && re == 0) re = p->ny;
+    if (rb < 0 || re > p->ny || rb > re) { set_error("bad row range"); return SIM5_ERR_BAD_PARAM; }
+    if (p->max_order < 0 || p->max_order > 2) { set_error("max_order must be 0..2"); return SIM5_ERR_BAD_PARAM; }
+    if (p->mode == SIM5_MODE_STEPWISE && (p->max_steps < 1 || !(p->precision_factor > 0))) { set_error("bad stepper parameters"); return SIM5_ERR_BAD_PARAM; }
+    for (int i = 0; i < 12; i++)
+        if ((p->outputs & kPlaneInfo[i].bit) && !host_plane(out, i)) { set_error("selected output plane is NULL"); return SIM5_ERR_NO_OUTPUT; }
+
+    size_t npix = (size_t)(re - rb) * (size_t)p->nx;
+    bool devptr = (p->flags & SIM5_FLAG_DEVICE_PTRS) != 0;
+    DevOut d;
+    memset(&d, 0, sizeof d);
+    d.base_row = devptr ? 0 : rb;
+    for (int i = 0; i < 12; i++) {
+        if (!(p->outputs & kPlaneInfo[i].bit)) continue;
+        if (devptr) { set_dev_plane(&d, i, host_plane(out, i)); continue; }
+        rc = reserve(c.planes[i], (npix ? npix : 1) * kPlaneInfo[i].elem);
+        if (rc) return rc;
+        set_dev_plane(&d, i, c.planes[i].p);
+    }
+
+    s5_fill_image_consts(p, c.h_consts);
+    CK(cudaEventRecord(c.ev0, c.stream));
+    CK(cudaMemcpyAsync(c.d_consts, c.h_consts, sizeof(S5ImageConsts), cudaMemcpyHostToDevice, c.stream));
+    CK(cudaMemsetAsync(c.d_counter, 0, sizeof(unsigned long long), c.stream));
+    CK(cudaMemsetAsync(c.d_stats, 0, sizeof(DevStats), c.stream));
+    int grid = 0;
+    CK(cudaEventRecord(c.ev1, c.stream));
+    if (npix > 0) {
+        if (p->mode == SIM5_MODE_STEPWISE) {
+            grid = persistent_grid(s5::k_trace_stepwise, S5_CTA_THREADS);
+            s5::k_trace_stepwise<<<grid, S5_CTA_THREADS, 0, c.stream>>>(c.d_consts, d, c.d_counter, c.d_stats);
+        } else {
+            grid = persistent_grid(s5::k_trace_eqplane, S5_CTA_THREADS);
+            s5::k_trace_eqplane<<<grid, S5_CTA_THREADS, 0, c.stream>>>(c.d_consts, d, c.d_counter, c.d_stats);
+        }
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(c.ev2, c.stream));
+    if (!devptr && npix > 0) {
+        for (int i = 0; i < 12; i++) {
+            if (!(p->outputs & kPlaneInfo[i].bit)) continue;
+            char* dst = (char*)host_plane(out, i) + (size_t)rb * p->nx * kPlaneInfo[i].elem;
+            CK(cudaMemcpyAsync(dst, c.planes[i].p, npix * kPlaneInfo[i].elem, cudaMemcpyDeviceToHost, c.stream));
+        }
+    }
+    CK(cudaMemcpyAsync(c.h_stats, c.d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaEventRecord(c.ev3, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->rays = (int64_t)npix;
+        for (int i = 0; i < 32; i++) stats->class_count[i] = (int64_t)c.h_stats->cls[i];
+        for (int i = 0; i < 8; i++) stats->gtype_count[i] = (int64_t)c.h_stats->gtype[i];
+        stats->total_steps = (int64_t)c.h_stats->steps;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c.ev1, c.ev2); stats->kernel_ms = ms;
+        cudaEventElapsedTime(&ms, c.ev0, c.ev3); stats->total_ms = ms;
+        stats->kernel_launches = npix > 0 ? 1 : 0;
+        stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = S5_CTA_THREADS;
+    }
+    return SIM5_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* FP64 peak                                                           */
+/* ------------------------------------------------------------------ */
+extern "C" double sim5_fp64_peak_tflops(int device, int iters)
+{
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (ensure_init(device) != SIM5_OK) return -1.0;
+    Context& c = g_ctx;
+    if (iters < 1) iters = 4096;
+    int grid = c.sm_count * 8;
+    if (reserve(c.planes[0], 4096) != SIM5_OK) return -1.0;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(c.ev0, c.stream);
+        s5::k_dfma_peak<<<grid, 256, 0, c.stream>>>((double*)c.planes[0].p, iters, 1.0);
+        cudaEventRecord(c.ev1, c.stream);
+        if (!cuda_ok(cudaStreamSynchronize(c.stream), "dfma peak")) return -1.0;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+        double flops = (double)grid * 256.0 * (double)iters * 64.0 * 2.0;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    return best;
+}
+
+/* ------------------------------------------------------------------ */
+/* batched element-wise entries                                        */
+/* ------------------------------------------------------------------ */
+namespace {
+int stage_in(int slot, const double* h, size_t n)
+{
+    Context& c = g_ctx;
+    size_t bytes = (n ? n : 1) * sizeof(double);
+    if (c.batch_bytes[slot] < bytes) {
+        if (c.batch[slot]) cudaFree(c.batch[slot]);
+        c.batch[slot] = nullptr; c.batch_bytes[slot] = 0;
+        CK(cudaMalloc(&c.batch[slot], bytes));
+        c.batch_bytes[slot] = bytes;
+    }
+    if (h && n) CK(cudaMemcpyAsync(c.batch[slot], h, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    return SIM5_OK;
+}
+int stage_out(int slot, double* h, size_t n)
+{
+    if (h && n) CK(cudaMemcpyAsync(h, g_ctx.batch[slot], n * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
+    return SIM5_OK;
+}
+int batch_grid(int64_t n) { int64_t b = (n + 127) / 128; int64_t cap = (int64_t)g_ctx.sm_count * 16; return (int)(b < 1 ? 1 : (b > cap ? cap : b)); }
+#define B(i) ((double*)g_ctx.batch[i])
+#define BATCH_BEGIN() std::lock_guard<std::mutex> lk(g_ctx.mu); if (n < 0) return SIM5_ERR_BAD_PARAM; { int rc_ = ensure_init(-1); if (rc_) return rc_; }
+#define BATCH_END() CK(cudaGetLastError()); CK(cudaStreamSynchronize(g_ctx.stream)); return SIM5_OK;
+}
+
+extern "C" int sim5_batch_rf(int64_t n, const double* x, const double* y, const double* z, double* out)
+{
+    BATCH_BEGIN();
+    int rc; if ((rc = stage_in(0, x, n)) || (rc = stage_in(1, y, n)) || (rc = stage_in(2, z, n)) || (rc = stage_in(3, nullptr, n))) return rc;
+    s5::k_batch_rf<<<batch_grid(n), 128, 0, g_ctx.stream>>>(n, B(0), B(1), B(2), B(3));
+    if ((rc = stage_out(3, out, n))) return rc;
+    BATCH_END();
+}
+extern "C" int sim5_batch_rd(int64_t n, const double* x, const double* y, const double* z, double* out)
+{
+    BATCH_BEGIN();
+    int rc; if ((rc = stage_in(0, x, n)) || (rc = stage_in(1, y, n)) || (rc = stage_in(2, z, n)) || (rc = stage_in(3, nullptr, n))) return rc;
+    s5::k_batch_rd<<<batch_grid(n), 128, 0, g_ctx.stream>>>(n, B(0), B(1), B(2), B(3));
+    if ((rc = stage_out(3, out, n))) return rc;
+    BATCH_END();
+}
+extern "C" int sim5_batch_rc(int64_t n, const double* x, const double* y, double* out)
+{
+    BATCH_BEGIN();
+    int rc; if ((rc = stage_in(0, x, n)) || (rc = stage_in(1, y, n)) || (rc = stage_in(3, nullptr, n))) return rc;
+    s5::k_batch_rc<<<batch_grid(n), 128, 0, g_ctx.stream>>>(n, B(0), B(1), B(3));
+    if ((rc = stage_out(3, out, n))) return rc;
+    BATCH_END();
+}
+extern "C" int sim5_batch_rj(int64_t n, const double* x, const double* y, const double* z, const double* p, double* out)
+{
+    BATCH_BEGIN();
+    int rc; if ((rc = stage_in(0, x, n)) || (rc = stage_in(1, y, n)) || (rc = stage_in(2, z, n)) || (rc = stage_in(4, p, n)) || (rc = stage_in(3, nullptr, n))) return rc;
+    s5::k_batch_rj<<<batch_grid(n), 128, 0, g_ctx.stream>>>(n, B(0), B(1), B(2), B(4), B(3));
+    if ((rc = stage_out(3, out, n))) return rc;
+    BATCH_END();
+}
+extern "C" int sim5_batch_sncndn(int64_t n, const double* u, const double* m, double* sn, double* cn, double* dn)
+{
+    BATCH_BEGIN();
+    int rc; if ((rc = stage_in(0, u, n)) || (rc = stage_in(1, m, n)) || (rc = stage_in(3, nullptr, n)) || (rc = stage_in(4, nullptr, n)) || (rc = stage_in(5, nullptr, n))) return rc;
+    s5::k_batch_sncndn<<<batch_grid(n), 128, 0, g_ctx.stream>>>(n, B(0), B(1), B(3), B(4), B(5));
+    if ((rc = stage_out(3, sn, n)) || (rc = stage_out(4, cn, n)) || (rc = stage_out(5, dn, n))) return rc;
+    BATCH_END();
+}
+extern "C" int sim5_batch_libm(int op, int64_t n, const double* a, const double* b, double* out)
+{
+    BATCH_BEGIN();
+    int rc; if ((rc = stage_in(0, a, n)) || (rc = stage_in(1, b, b ? n : 0)) || (rc = stage_in(1, nullptr, n)) || (rc = stage_in(3, nullptr, n))) return rc;
+    if (!b) CK(cudaMemsetAsync(g_ctx.batch[1], 0, (n ? n : 1) * sizeof(double), g_ctx.stream));
+    s5::k_batch_libm<<<batch_grid(n), 128, 0, g_ctx.stream>>>(op, n, B(0), B(1), B(3));
+    if ((rc = stage_out(3, out, n))) return rc;
+    BATCH_END();
+}
+
+/* ------------------------------------------------------------------ */
+/* scalar sim5lib.h API: one-thread device launches                    */
+/* ------------------------------------------------------------------ */
+template <class F> __global__ void k_call(F f) { f(); }
+
+namespace {
+
+template <class F> bool dev_call(F f)
+{
+    k_call<<<1, 1, 0, g_ctx.stream>>>(f);
+    if (!cuda_ok(cudaGetLastError(), "scalar launch")) return false;
+    return cuda_ok(cudaStreamSynchronize(g_ctx.stream), "scalar sync");
+}
+bool scalar_ready() { return ensure_init(-1) == SIM5_OK; }
+#define H (g_ctx.h_scr)
+#define D (g_ctx.d_scr)
+#define LOCK std::lock_guard<std::mutex> lk(g_ctx.mu)
+const double kNaN = NAN;
+
+/* double f(double...) helpers */
+double call_d1(int op, double a0, double a1, double a2, double a3, double a4, double a5)
+{
+    LOCK;
+    if (!scalar_ready()) return kNaN;
+    Scratch* d = D;
+    bool ok = dev_call([=] __device__ () {
+        double r = NAN;
+        switch (op) {
+            case 0: r = s5::rf(a0, a1, a2); break;
+            case 1: r = s5::rd(a0, a1, a2); break;
+            case 2: r = s5::rc(a0, a1); break;
+            case 3: r = s5::rj(a0, a1, a2, a3); break;
+            case 4: r = s5::elliptic_k(a0); break;
+            case 5: r = s5::elliptic_f(a0, a1); break;
+            case 6: r = s5::elliptic_f_cos(a0, a1); break;
+            case 7: r = s5::elliptic_f_sin(a0, a1); break;
+            case 8: r = s5::elliptic_e_cos(a0, a1); break;
+            case 9: r = s5::elliptic_e_sin(a0, a1); break;
+            case 10: r = s5::elliptic_pi_complete(a0, a1); break;
+            case 11: r = s5::elliptic_pi_cos(a0, a1, a2); break;
+            case 12: r = s5::elliptic_pi_sin(a0, a1, a2); break;
+            case 13: r = s5::jacobi_isn(a0, a1); break;
+            case 14: r = s5::jacobi_icn(a0, a1); break;
+            case 15: r = s5::jacobi_itn(a0, a1); break;
+            case 16: r = s5::jacobi_sn(a0, a1); break;
+            case 17: r = s5::jacobi_cn(a0, a1); break;
+            case 18: r = s5::jacobi_dn(a0, a1); break;
+            case 19: r = s5::integral_Z1(a0, a1, a2, a3); break;
+            case 20: r = s5::integral_R1(a0, a1, a2); break;
+            case 21: r = s5::integral_R_rp_re(a0, a1, a2, a3, a4, a5); break;
+            case 22: r = s5::integral_R_rp_re_inf(a0, a1, a2, a3, a4); break;
+            case 23: r = s5::integral_T_mp(a0, a1, a2, a3); break;
+            case 24: r = s5::r_bh(a0); break;
+            case 25: r = s5::OmegaK(a0, a1); break;
+            case 26: r = s5::gfactorK(a0, a1, a2); break;
+        }
+        d->v[0] = r;
+    });
+    return ok ? H->v[0] : kNaN;
+}
+
+} /* anonymous namespace */
+
+#define DFUN1(name, op) extern "C" double name(double a) { return call_d1(op, a, 0, 0, 0, 0, 0); }
+#define DFUN2(name, op) extern "C" double name(double a, double b) { return call_d1(op, a, b, 0, 0, 0, 0); }
+#define DFUN3(name, op) extern "C" double name(double a, double b, double c) { return call_d1(op, a, b, c, 0, 0, 0); }
+#define DFUN4(name, op) extern "C" double name(double a, double b, double c, double d) { return call_d1(op, a, b, c, d, 0, 0); }
+DFUN3(rf, 0) DFUN3(rd, 1) DFUN2(rc, 2) DFUN4(rj, 3)
+DFUN1(elliptic_k, 4) DFUN2(elliptic_f, 5) DFUN2(elliptic_f_cos, 6) DFUN2(elliptic_f_sin, 7)
+DFUN2(elliptic_e_cos, 8) DFUN2(elliptic_e_sin, 9) DFUN2(elliptic_pi_complete, 10)
+DFUN3(elliptic_pi_cos, 11) DFUN3(elliptic_pi_sin, 12)
+DFUN2(jacobi_isn, 13) DFUN2(jacobi_icn, 14) DFUN2(jacobi_itn, 15)
+DFUN2(jacobi_sn, 16) DFUN2(jacobi_cn, 17) DFUN2(jacobi_dn, 18)
+DFUN4(integral_Z1, 19) DFUN3(integral_R1, 20)
+extern "C" double integral_R_rp_re(double a, double b, double c, double d, double p, double X) { return call_d1(21, a, b, c, d, p, X); }
+extern "C" double integral_R_rp_re_inf(double a, double b, double c, double d, double p) { return call_d1(22, a, b, c, d, p, 0); }
+DFUN4(integral_T_mp, 23)
+DFUN1(r_bh, 24) DFUN2(OmegaK, 25) DFUN3(gfactorK, 26)
+
+/* r_ms is a per-image constant in every caller; it needs cbrt of the host libm to match the reference bit for bit */
+extern "C" double r_ms(double a) { return s5_host_r_ms(a); }
+
+struct c_complex { double re, im; };
+
+extern "C" double integral_R_rp_cc2_inf(double a, double b, c_complex c, double p, double X1)
+{
+    LOCK; if (!scalar_ready()) return kNaN;
+    Scratch* d = D;
+    bool ok = dev_call([=] __device__ () { d->v[0] = s5::integral_R_rp_cc2_inf(a, b, c.re, c.im, p, X1); });
+    return ok ? H->v[0] : kNaN;
+}
+
+extern "C" void jacobi_sncndn(double u, double m, double* sn, double* cn, double* dn)
+{
+    LOCK;
+    if (!scalar_ready()) { *sn = *cn = *dn = kNaN; return; }
+    Scratch* d = D;
+    bool ok = dev_call([=] __device__ () { s5::jacobi_sncndn(u, m, &d->v[0], &d->v[1], &d->v[2]); });
+    *sn = ok ? H->v[0] : kNaN; *cn = ok ? H->v[1] : kNaN; *dn = ok ? H->v[2] : kNaN;
+}
+
+/* ---- metric / tetrads -------------------------------------------------------------------------- */
+extern "C" void kerr_metric(double a, double r, double m, s5::Metric* g)
+{
+    LOCK; if (!scalar_ready()) { memset(g, 0xff, sizeof *g); return; }
+    Scratch* d = D;
+    dev_call([=] __device__ () { s5::kerr_metric(a, r, m, &d->m); });
+    *g = H->m;
+}
+extern "C" void kerr_metric_contravariant(double a, double r, double m, s5::Metric* g)
+{
+    LOCK; if (!scalar_ready()) { memset(g, 0xff, sizeof *g); return; }
+    Scratch* d = D;
+    dev_call([=] __device__ () { s5::kerr_metric_contravariant(a, r, m, &d->m); });
+    *g = H->m;
+}
+extern "C" void flat_metric(double r, double m, s5::Metric* g)
+{
+    LOCK; if (!scalar_ready()) { memset(g, 0xff, sizeof *g); return; }
+    Scratch* d = D;
+    dev_call([=] __device__ () { s5::flat_metric(r, m, &d->m); });
+    *g = H->m;
+}
+extern "C" void kerr_connection(double a, double r, double m, double G[4][4][4])
+{
+    LOCK; if (!scalar_ready()) { for (int i = 0; i < 64; i++) (&G[0][0][0])[i] = kNaN; return; }
+    Scratch* d = D;
+    dev_call([=] __device__ () { s5::Conn c; s5::kerr_connection(a, r, m, &c); s5::conn_to_array(&c, d->v); });
+    memcpy(G, H->v, 64 * sizeof(double));
+}
+extern "C" void flat_connection(double r, double m, double G[4][4][4])
+{
+    LOCK; if (!scalar_ready()) { for (int i = 0; i < 64; i++) (&G[0][0][0])[i] = kNaN; return; }
+    Scratch* d = D;
+    dev_call([=] __device__ () { s5::Conn c; s5::flat_connection(r, m, &c); s5::conn_to_array(&c, d->v); });
+    memcpy(G, H->v, 64 * sizeof(double));
+}
+/* generic contraction with a caller-supplied G[4][4][4] (all 40 upper-triangle terms, reference order sim5kerr.c:421-440) */
+extern "C" void Gamma(double G[4][4][4], double U[4], double V[4], double result[4])
+{
+    LOCK; if (!scalar_ready()) { result[0] = result[1] = result[2] = result[3] = kNaN; return; }
+    Scratch* d = D;
+    memcpy(H->v, G, 64 * sizeof(double));
+    memcpy(H->v + 64, U, 32); memcpy(H->v + 68, V, 32);
+    dev_call([=] __device__ () {
+        const double* g = d->v; const double* u = d->v + 64; const double* v = d->v + 68;
+        for (int i = 0; i < 4; i++) {
+            double acc = 0.0;
+            for (int j = 0; j < 4; j++) for (int k = j; k < 4; k++) acc -= 0.5 * g[i * 16 + j * 4 + k] * (u[j] * v[k] + u[k] * v[j]);
+            d->v[72 + i] = acc;
+        }
+    });
+    memcpy(result, H->v + 72, 32);
+}
+extern "C" double dotprod(double V1[4], double V2[4], s5::Metric* g)
+{
+    LOCK; if (!scalar_ready()) return kNaN;
+    Scratch* d = D;
+    memcpy(H->v, V1, 32); memcpy(H->v + 4, V2, 32);
+    int flat = (g == nullptr);
+    if (g) H->m = *g;
+    dev_call([=] __device__ () {
+        if (flat) d->v[8] = -d->v[0] * d->v[4] + d->v[1] * d->v[5] + d->v[2] * d->v[6] + d->v[3] * d->v[7];
+        else d->v[8] = s5::dotprod(d->v, d->v + 4, &d->m);
+    });
+    return H->v[8];
+}
+extern "C" void vector_norm_to(double V[4], double norm, s5::Metric* g)
+{
+    LOCK; if (!scalar_ready()) { V[0] = V[1] = V[2] = V[3] = kNaN; return; }
+    Scratch* d = D;
+    memcpy(H->v, V, 32); H->m = *g;
+    dev_call([=] __device__ () { s5::vector_norm_to(d->v, norm, &d->m); });
+    memcpy(V, H->v, 32);
+}
+extern "C" void tetrad_zamo(s5::Metric* g, s5::Tetrad* t)
+{
+    LOCK; if (!scalar_ready()) { memset(t, 0xff, sizeof *t); return; }
+    Scratch* d = D; H->m = *g;
+    dev_call([=] __device__ () { s5::tetrad_zamo(&d->m, &d->t); });
+    *t = H->t;
+}
+extern "C" void tetrad_azimuthal(s5::Metric* g, double Omega, s5::Tetrad* t)
+{
+    LOCK; if (!scalar_ready()) { memset(t, 0xff, sizeof *t); return; }
+    Scratch* d = D; H->m = *g;
+    dev_call([=] __device__ () { s5::tetrad_azimuthal(&d->m, Omega, &d->t); });
+    *t = H->t;
+}
+extern "C" void tetrad_surface(s5::Metric* g, double Omega, double V, double dhdr, s5::Tetrad* t)
+{
+    LOCK; if (!scalar_ready()) { memset(t, 0xff, sizeof *t); return; }
+    Scratch* d = D; H->m = *g;
+    dev_call([=] __device__ () { s5::tetrad_surface(&d->m, Omega, V, dhdr, &d->t); });
+    *t = H->t;
+}
+extern "C" void bl2on(double Vin[4], double Vout[4], s5::Tetrad* t)
+{
+    LOCK; if (!scalar_ready()) { Vout[0] = Vout[1] = Vout[2] = Vout[3] = kNaN; return; }
+    Scratch* d = D; memcpy(H->v, Vin, 32); H->t = *t;
+    dev_call([=] __device__ () { s5::bl2on(d->v, d->v + 4, &d->t); });
+    memcpy(Vout, H->v + 4, 32);
+}
+extern "C" void on2bl(double Vin[4], double Vout[4], s5::Tetrad* t)
+{
+    LOCK; if (!scalar_ready()) { Vout[0] = Vout[1] = Vout[2] = Vout[3] = kNaN; return; }
+    Scratch* d = D; memcpy(H->v, Vin, 32); H->t = *t;
+    dev_call([=] __device__ () { s5::on2bl(d->v, d->v + 4, &d->t); });
+    memcpy(Vout, H->v + 4, 32);
+}
+extern "C" double Omega_from_ell(double ell, s5::Metric* g)
+{
+    LOCK; if (!scalar_ready()) return kNaN;
+    Scratch* d = D; H->m = *g;
+    dev_call([=] __device__ () { d->v[0] = s5::Omega_from_ell(ell, &d->m); });
+    return H->v[0];
+}
+extern "C" double ell_from_Omega(double Omega, s5::Metric* g)
+{
+    LOCK; if (!scalar_ready()) return kNaN;
+    Scratch* d = D; H->m = *g;
+    dev_call([=] __device__ () { d->v[0] = s5::ell_from_Omega(Omega, &d->m); });
+    return H->v[0];
+}
+extern "C" void photon_momentum(double a, double r, double m, double l, double q, double r_sign, double m_sign, double k[4])
+{
+    LOCK; if (!scalar_ready()) { k[0] = k[1] = k[2] = k[3] = kNaN; return; }
+    Scratch* d = D;
+    dev_call([=] __device__ () { s5::photon_momentum(a, r, m, l, q, r_sign, m_sign, d->v); });
+    memcpy(k, H->v, 32);
+}
+extern "C" void photon_motion_constants(double a, double r, double m, double k[4], double* L, double* Q)
+{
+    LOCK; if (!scalar_ready()) { *L = *Q = kNaN; return; }
+    Scratch* d = D; memcpy(H->v, k, 32);
+    dev_call([=] __device__ () { s5::photon_motion_constants(a, r, m, d->v, &d->v[4], &d->v[5]); });
+    *L = H->v[4]; *Q = H->v[5];
+}
+extern "C" double photon_carter_const(double k[4], s5::Metric* g)
+{
+    LOCK; if (!scalar_ready()) return kNaN;
+    Scratch* d = D; memcpy(H->v, k, 32); H->m = *g;
+    dev_call([=] __device__ () { d->v[4] = s5::photon_carter_const(d->v, &d->m); });
+    return H->v[4];
+}
+extern "C" void fourvelocity_azimuthal(double Omega, s5::Metric* g, double U[4])
+{
+    LOCK; if (!scalar_ready()) { U[0] = U[1] = U[2] = U[3] = kNaN; return; }
+    Scratch* d = D; H->m = *g;
+    dev_call([=] __device__ () { s5::fourvelocity_azimuthal(Omega, &d->m, d->v); });
+    memcpy(U, H->v, 32);
+}
+
+/* ---- geodesics ----------------------------------------------------------------------------------- */
+extern "C" int geodesic_init_inf(double i, double a, double alpha, double beta, s5::Geodesic* g, int* error)
+{
+    LOCK; if (!scalar_ready()) { if (error) *error = -1; return 0; }
+    Scratch* d = D;
+    H->g = *g;
+    H->iv[1] = -1;
+    dev_call([=] __device__ () { d->iv[0] = s5::geodesic_init_inf(i, a, alpha, beta, &d->g, &d->iv[1]); });
+    *g = H->g;
+    if (error && H->iv[1] != -1) *error = H->iv[1];
+    return H->iv[0];
+}
+extern "C" int geodesic_init_src(double a, double r, double m, double k[4], int ppc, s5::Geodesic* g, int* error)
+{
+    LOCK; if (!scalar_ready()) { if (error) *error = -1; return 0; }
+    Scratch* d = D;
+    H->g = *g; memcpy(H->v, k, 32);
+    H->iv[1] = -1;
+    dev_call([=] __device__ () { d->iv[0] = s5::geodesic_init_src(a, r, m, d->v, ppc, &d->g, &d->iv[1]); });
+    *g = H->g;
+    if (error && H->iv[1] != -1) *error = H->iv[1];
+    return H->iv[0];
+}
+#define GEO_D(name, expr, ...) extern "C" double name(s5::Geodesic* g, __VA_ARGS__) { \
+    LOCK; if (!scalar_ready()) return kNaN; Scratch* d = D; H->g = *g; \
+    dev_call([=] __device__ () { d->v[0] = expr; }); return H->v[0]; }
+GEO_D(geodesic_P_int, s5::geodesic_P_int(&d->g, r, ppc), double r, int ppc)
+GEO_D(geodesic_position_rad, s5::geodesic_position_rad(&d->g, P), double P)
+GEO_D(geodesic_position_pol, s5::geodesic_position_pol(&d->g, P), double P)
+GEO_D(geodesic_position_pol_sign_k_theta, s5::geodesic_position_pol_sign_k_theta(&d->g, P), double P)
+GEO_D(geodesic_position_azm, s5::geodesic_position_azm(&d->g, r, m, P), double r, double m, double P)
+GEO_D(geodesic_dm_sign, s5::geodesic_dm_sign(&d->g, P), double P)
+GEO_D(geodesic_find_midplane_crossing, s5::geodesic_find_midplane_crossing(&d->g, order), int order)
+extern "C" void geodesic_position(s5::Geodesic*, double, double*) { /* empty in the reference too: sim5kerr-geod.c:268-285 */ }
+extern "C" void geodesic_momentum(s5::Geodesic* g, double P, double r, double m, double k[])
+{
+    LOCK; if (!scalar_ready()) { k[0] = k[1] = k[2] = k[3] = kNaN; return; }
+    Scratch* d = D; H->g = *g;
+    memcpy(H->v, k, 32);
+    dev_call([=] __device__ () { s5::geodesic_momentum(&d->g, P, r, m, d->v); });
+    memcpy(k, H->v, 32);
+}
+extern "C" void geodesic_follow(s5::Geodesic* g, double step, double* P, double* r, double* m, int* status)
+{
+    LOCK; if (!scalar_ready()) { if (status) *status = 0; *r = *m = kNaN; return; }
+    Scratch* d = D; H->g = *g;
+    H->v[0] = *P; H->v[1] = *r; H->v[2] = *m; H->iv[0] = status ? *status : 0;
+    dev_call([=] __device__ () { s5::geodesic_follow(&d->g, step, &d->v[0], &d->v[1], &d->v[2], &d->iv[0]); });
+    *P = H->v[0]; *r = H->v[1]; *m = H->v[2];
+    if (status) *status = H->iv[0];
+}
+
+/* ---- stepwise integrator ------------------------------------------------------------------------- */
+extern "C" void raytrace_prepare(double bh_spin, double x[4], double k[4], double precision_factor, int options, s5::RayData* rtd)
+{
+    LOCK; if (!scalar_ready()) { memset(rtd, 0xff, sizeof *rtd); return; }
+    Scratch* d = D; H->rtd = *rtd;
+    memcpy(H->v, x, 32); memcpy(H->v + 4, k, 32);
+    dev_call([=] __device__ () { s5::raytrace_prepare(bh_spin, d->v, d->v + 4, precision_factor, options, &d->rtd); });
+    *rtd = H->rtd;
+}
+extern "C" void raytrace(double x[4], double k[4], double* step, s5::RayData* rtd)
+{
+    LOCK; if (!scalar_ready()) { x[1] = kNaN; return; }
+    Scratch* d = D; H->rtd = *rtd;
+    memcpy(H->v, x, 32); memcpy(H->v + 4, k, 32); H->v[8] = *step;
+    dev_call([=] __device__ () { s5::raytrace(d->v, d->v + 4, &d->v[8], &d->rtd); });
+    memcpy(x, H->v, 32); memcpy(k, H->v + 4, 32); *step = H->v[8];
+    *rtd = H->rtd;
+}
+extern "C" double raytrace_error(double x[4], double k[4], s5::RayData* rtd)
+{
+    LOCK; if (!scalar_ready()) return kNaN;
+    Scratch* d = D; H->rtd = *rtd;
+    memcpy(H->v, x, 32); memcpy(H->v + 4, k, 32);
+    dev_call([=] __device__ () { d->v[8] = s5::raytrace_error(d->v, d->v + 4, &d->rtd); });
+    return H->v[8];
+}
+
+/* ---- polarization -------------------------------------------------------------------------------- */
+extern "C" void polarization_vector(double k[4], c_complex wp, s5::Metric* g, double f[4])
+{
+    LOCK; if (!scalar_ready()) { f[0] = f[1] = f[2] = f[3] = kNaN; return; }
+    Scratch* d = D; H->m = *g; memcpy(H->v, k, 32);
+    dev_call([=] __device__ () { s5::polarization_vector(d->v, s5::Cplx{wp.re, wp.im}, &d->m, d->v + 4); });
+    memcpy(f, H->v + 4, 32);
+}
+extern "C" c_complex polarization_constant(double k[4], double f[4], s5::Metric* g)
+{
+    LOCK; if (!scalar_ready()) return c_complex{kNaN, kNaN};
+    Scratch* d = D; H->m = *g; memcpy(H->v, k, 32); memcpy(H->v + 4, f, 32);
+    dev_call([=] __device__ () { s5::Cplx c = s5::polarization_constant(d->v, d->v + 4, &d->m); d->v[8] = c.re; d->v[9] = c.im; });
+    return c_complex{H->v[8], H->v[9]};
+}
+extern "C" c_complex polarization_constant_infinity(double a, double alpha, double beta, double incl)
+{
+    LOCK; if (!scalar_ready()) return c_complex{kNaN, kNaN};
+    Scratch* d = D;
+    dev_call([=] __device__ () { s5::Cplx c = s5::polarization_constant_infinity_s(a, alpha, beta, crm::cr_sin(incl)); d->v[8] = c.re; d->v[9] = c.im; });
+    return c_complex{H->v[8], H->v[9]};
+}
+extern "C" double polarization_angle_rotation(double a, double inc, double alpha, double beta, c_complex kappa)
+{
+    LOCK; if (!scalar_ready()) return kNaN;
+    Scratch* d = D;
+    dev_call([=] __device__ () { d->v[0] = s5::polarization_angle_rotation_s(a, crm::cr_sin(inc), alpha, beta, s5::Cplx{kappa.re, kappa.im}); });
+    return H->v[0];
+}
+
+/* ---- Novikov-Thorne flux (per-pixel part only) ----------------------------------------------------- */
+extern "C" int disk_nt_setup(double M, double a, double mdot_or_L, double alpha, int options)
+{
+    LOCK;
+    if (options != 0) { set_error("disk_nt_setup: only options=0 (mdot given) is on the GPU path"); return -1; }
+    sim5_image_params p;
+    memset(&p, 0, sizeof p);
+    p.nx = p.ny = 1; p.bh_spin = a; p.incl = 1.0; p.rmax = 1.0;
+    p.disk_mass = M; p.disk_mdot = mdot_or_L; p.disk_alpha = alpha;
+    g_ctx.disk_params = p;
+    g_ctx.disk_set = true;
+    return 0;
+}
+extern "C" double disk_nt_r_min(void)
+{
+    LOCK;
+    double a = g_ctx.disk_set ? (double)(float)g_ctx.disk_params.bh_spin : 0.0;
+    return s5_host_disk_nt_r_min(a);
+}
+extern "C" double disk_nt_flux(double r)
+{
+    LOCK; if (!scalar_ready()) return kNaN;
+    if (!g_ctx.disk_set) {
+        sim5_image_params p; memset(&p, 0, sizeof p);
+        p.nx = p.ny = 1; p.incl = 1.0; p.rmax = 1.0; p.disk_mass = 10.0; p.disk_mdot = 0.1; p.disk_alpha = 0.1;
+        g_ctx.disk_params = p; g_ctx.disk_set = true;
+    }
+    s5_fill_image_consts(&g_ctx.disk_params, g_ctx.h_consts);
+    if (!cuda_ok(cudaMemcpyAsync(g_ctx.d_consts, g_ctx.h_consts, sizeof(S5ImageConsts), cudaMemcpyHostToDevice, g_ctx.stream), "consts")) return kNaN;
+    Scratch* d = D;
+    const S5ImageConsts* dc = g_ctx.d_consts;
+    dev_call([=] __device__ () { d->v[0] = s5::disk_nt_flux(*dc, r); });
+    return H->v[0];
+}

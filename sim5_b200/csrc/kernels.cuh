@@ -1,0 +1,322 @@
+/*
+ * kernels.cuh -- the sm_100a kernels of the SIM5 photon hot path.
+ *
+ * Execution model (B200: 148 SMs, FP64 non-tensor pipe is the bound, HBM traffic is write-only and tiny):
+ *   - one ray per thread; persistent grid of (SM count x resident CTAs) CTAs;
+ *   - every WARP pulls tiles of 32 consecutive pixels of a row from one global atomic counter
+ *     (dynamic balance between the cheap outer image and the expensive shadow edge, no block syncs);
+ *   - per-image constants (S5ImageConsts, ~0.7 KB incl. the Novikov-Thorne and Chandrasekhar tables)
+ *     are staged in shared memory once per CTA;
+ *   - outputs are SoA planes; a warp stores 32 consecutive doubles per plane (one 256-byte
+ *     fully-coalesced transaction), no reads from HBM at all;
+ *   - the stepwise kernel keeps one live ray per lane and refills finished lanes from the queue
+ *     (ballot + one aggregated atomic per warp) so 300..8000-step rays do not idle their warp.
+ */
+#ifndef SIM5_KERNELS_CUH
+#define SIM5_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include "pixel.cuh"
+
+namespace s5 {
+
+struct DevOut {
+    double *r, *phi, *g, *flux, *chi, *delta, *mue, *intensity, *tau, *qerr;
+    int* steps;
+    unsigned char* status;
+    int base_row;                 /* plane index = (iy - base_row)*nx + ix */
+};
+
+struct DevStats {                 /* device-side counters, flushed once per CTA */
+    unsigned long long cls[32];
+    unsigned long long gtype[8];
+    unsigned long long steps;
+    unsigned long long rays;
+};
+
+#define S5_CTA_THREADS 128
+
+__device__ __forceinline__ void stage_consts(S5ImageConsts* dst, const S5ImageConsts* src)
+{
+    const int nwords = (int)(sizeof(S5ImageConsts) / sizeof(int));
+    const int* s = reinterpret_cast<const int*>(src);
+    int* d = reinterpret_cast<int*>(dst);
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) d[i] = s[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void store_pixel(const DevOut& out, unsigned outputs, size_t i, const PixelOut& o)
+{
+    if (outputs & SIM5_OUT_R)         out.r[i] = o.r;
+    if (outputs & SIM5_OUT_PHI)       out.phi[i] = o.phi;
+    if (outputs & SIM5_OUT_G)         out.g[i] = o.g;
+    if (outputs & SIM5_OUT_FLUX)      out.flux[i] = o.flux;
+    if (outputs & SIM5_OUT_CHI)       out.chi[i] = o.chi;
+    if (outputs & SIM5_OUT_DELTA)     out.delta[i] = o.delta;
+    if (outputs & SIM5_OUT_MUE)       out.mue[i] = o.mue;
+    if (outputs & SIM5_OUT_INTENSITY) out.intensity[i] = o.intensity;
+    if (outputs & SIM5_OUT_TAU)       out.tau[i] = o.tau;
+    if (outputs & SIM5_OUT_QERR)      out.qerr[i] = o.qerr;
+    if (outputs & SIM5_OUT_STEPS)     out.steps[i] = o.steps;
+    if (outputs & SIM5_OUT_STATUS)    out.status[i] = (unsigned char)o.status;
+}
+
+__device__ __forceinline__ void flush_stats(const unsigned int* s_cnt, unsigned long long s_steps, DevStats* gs)
+{
+    __syncthreads();
+    if (threadIdx.x < 32) { if (s_cnt[threadIdx.x]) atomicAdd(&gs->cls[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]); }
+    else if (threadIdx.x < 40) { if (s_cnt[threadIdx.x]) atomicAdd(&gs->gtype[threadIdx.x - 32], (unsigned long long)s_cnt[threadIdx.x]); }
+    (void)s_steps;
+}
+
+/* ------------------------------------------------------------------ */
+/* modes EQPLANE / POLARIZED : analytic geodesic per pixel             */
+/* ------------------------------------------------------------------ */
+__global__ void __launch_bounds__(S5_CTA_THREADS)
+k_trace_eqplane(const S5ImageConsts* __restrict__ gconsts, DevOut out, unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
+{
+    __shared__ S5ImageConsts c;
+    __shared__ unsigned int s_cnt[40];
+    if (threadIdx.x < 40) s_cnt[threadIdx.x] = 0;
+    stage_consts(&c, gconsts);
+
+    const int lane = threadIdx.x & 31;
+    const long long nx = c.nx;
+    const long long npix = (long long)(c.row_end - c.row_begin) * nx;
+    const long long ntiles = (npix + 31) >> 5;
+
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1ULL);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((long long)t >= ntiles) break;
+        long long p = ((long long)t << 5) + lane;
+        if (p < npix) {
+            int iy = c.row_begin + (int)(p / nx);
+            int ix = (int)(p - (long long)(iy - c.row_begin) * nx);
+            PixelOut o;
+            trace_eqplane_pixel(c, ix, iy, &o);
+            size_t i = (size_t)(iy - out.base_row) * (size_t)nx + (size_t)ix;
+            store_pixel(out, c.outputs, i, o);
+            atomicAdd(&s_cnt[o.status & 31], 1u);
+            atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);
+        }
+    }
+    flush_stats(s_cnt, 0, gstats);
+}
+
+/* ------------------------------------------------------------------ */
+/* mode STEPWISE : raytrace() stepping with warp-level lane refill     */
+/* ------------------------------------------------------------------ */
+#define S5_STEPS_PER_ROUND 16
+#define S5_REFILL_MIN 4
+
+__global__ void __launch_bounds__(S5_CTA_THREADS)
+k_trace_stepwise(const S5ImageConsts* __restrict__ gconsts, DevOut out, unsigned long long* __restrict__ ray_counter, DevStats* __restrict__ gstats)
+{
+    __shared__ S5ImageConsts c;
+    __shared__ unsigned int s_cnt[40];
+    __shared__ unsigned long long s_steps;
+    if (threadIdx.x < 40) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_steps = 0;
+    stage_consts(&c, gconsts);
+
+    const int lane = threadIdx.x & 31;
+    const long long nx = c.nx;
+    const long long npix = (long long)(c.row_end - c.row_begin) * nx;
+    const bool refill = !(c.flags & SIM5_FLAG_NO_REFILL);
+
+    StepRay s;
+    long long mypix = -1;
+    bool live = false;
+    bool drained = false;          /* queue exhausted (warp-uniform) */
+    unsigned long long my_steps = 0;
+
+    for (;;) {
+        unsigned idle = __ballot_sync(0xffffffffu, !live);
+        if (idle == 0xffffffffu && drained) break;
+        /* refill finished lanes: always when the whole warp is idle; otherwise once enough lanes wait */
+        bool do_fill = !drained && (idle == 0xffffffffu || (refill && __popc(idle) >= S5_REFILL_MIN));
+        if (do_fill) {
+            int nreq = __popc(idle);
+            unsigned long long base = 0;
+            int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(ray_counter, (unsigned long long)nreq);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if ((long long)base >= npix) drained = true;
+            if (!live) {
+                long long p = (long long)base + __popc(idle & ((1u << lane) - 1u));
+                if (p < npix) {
+                    int iy = c.row_begin + (int)(p / nx);
+                    int ix = (int)(p - (long long)(iy - c.row_begin) * nx);
+                    PixelOut o;
+                    mypix = p;
+                    if (stepwise_start(c, ix, iy, &s, &o)) {
+                        live = true;
+                    } else {
+                        size_t i = (size_t)(iy - out.base_row) * (size_t)nx + (size_t)ix;
+                        store_pixel(out, c.outputs, i, o);
+                        atomicAdd(&s_cnt[o.status & 31], 1u);
+                        atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);
+                    }
+                }
+            }
+            if ((long long)base + nreq >= npix) drained = true;
+        }
+        /* advance the live lanes */
+        #pragma unroll 1
+        for (int it = 0; it < S5_STEPS_PER_ROUND; it++) {
+            if (live) {
+                int cls = stepwise_step(c, &s);
+                if (cls) {
+                    PixelOut o;
+                    o.r = o.phi = o.g = o.flux = o.chi = o.delta = o.mue = 0.0;
+                    stepwise_finish(c, &s, cls, &o);
+                    int iy = c.row_begin + (int)(mypix / nx);
+                    int ix = (int)(mypix - (long long)(iy - c.row_begin) * nx);
+                    size_t i = (size_t)(iy - out.base_row) * (size_t)nx + (size_t)ix;
+                    store_pixel(out, c.outputs, i, o);
+                    atomicAdd(&s_cnt[o.status & 31], 1u);
+                    atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);
+                    my_steps += (unsigned long long)o.steps;
+                    live = false;
+                }
+            }
+            if (refill && !__any_sync(0xffffffffu, live)) break;
+        }
+    }
+    /* total step count */
+    for (int off = 16; off > 0; off >>= 1) my_steps += __shfl_down_sync(0xffffffffu, my_steps, off);
+    if (lane == 0 && my_steps) atomicAdd(&s_steps, my_steps);
+    flush_stats(s_cnt, 0, gstats);
+    if (threadIdx.x == 0 && s_steps) atomicAdd(&gstats->steps, s_steps);
+}
+
+/* ------------------------------------------------------------------ */
+/* mode HISTOGRAM : g-factor transfer function over a (spin, incl) lattice */
+/* ------------------------------------------------------------------ */
+__global__ void __launch_bounds__(S5_CTA_THREADS)
+k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice image */, int img_begin, int img_end,
+                  double* __restrict__ hist, unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
+{
+    __shared__ S5ImageConsts c;
+    __shared__ unsigned int s_cnt[40];
+    __shared__ int s_img;
+    if (threadIdx.x < 40) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_img = -1;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    /* all images share nx, ny */
+    const long long nx = gconsts[img_begin].nx;
+    const long long npix = (long long)gconsts[img_begin].ny * nx;
+    const long long tiles_per_img = (npix + 31) >> 5;
+    /* a CTA works on blocks of 4 consecutive tiles x 4 warps of ONE image so the staged constants stay valid */
+    const long long chunks_per_img = (tiles_per_img + 3) >> 2;
+    const long long nchunks = chunks_per_img * (long long)(img_end - img_begin);
+    __shared__ unsigned long long s_chunk;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_chunk = atomicAdd(tile_counter, 1ULL);
+        __syncthreads();
+        long long ch = (long long)s_chunk;
+        if (ch >= nchunks) break;
+        int img = img_begin + (int)(ch / chunks_per_img);
+        long long t = ((ch % chunks_per_img) << 2) + (threadIdx.x >> 5);
+        if (img != s_img) {
+            __syncthreads();
+            stage_consts(&c, gconsts + img);
+            if (threadIdx.x == 0) s_img = img;
+            __syncthreads();
+        }
+        long long p = (t << 5) + lane;
+        bool hit = false;
+        int bin = -1;
+        double w = 0.0;
+        if (t < tiles_per_img && p < npix) {
+            int iy = (int)(p / nx);
+            int ix = (int)(p - (long long)iy * nx);
+            PixelOut o;
+            trace_eqplane_pixel(c, ix, iy, &o);
+            atomicAdd(&s_cnt[o.status & 31], 1u);
+            atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);
+            unsigned cls = o.status & 31;
+            if (cls == SIM5_ST_HIT0 || cls == SIM5_ST_HIT1 || cls == SIM5_ST_HIT2) {
+                double tt = (o.g - c.g_min) / (c.g_max - c.g_min) * (double)c.n_bins;
+                if (tt >= 0.0 && tt < (double)c.n_bins) { hit = true; bin = (int)tt; w = o.flux * c.da * c.db; }
+            }
+        }
+        /* warp-aggregated accumulation: one atomic per distinct bin in the warp */
+        unsigned active = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            unsigned peers = __match_any_sync(active, bin);
+            int leader = __ffs(peers) - 1;
+            double sum = 0.0;
+            /* fixed lane order inside the group */
+            for (unsigned m = peers; m; m &= m - 1) {
+                int src = __ffs(m) - 1;
+                sum += __shfl_sync(peers, w, src);
+            }
+            if (lane == leader) atomicAdd(&hist[(size_t)img * c.n_bins + bin], sum);
+        }
+    }
+    flush_stats(s_cnt, 0, gstats);
+}
+
+/* ------------------------------------------------------------------ */
+/* FP64 DFMA-chain microbenchmark (roofline denominator)               */
+/* ------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.9999999, b = 1e-9;
+    #pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+        #pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = __fma_rn(a0, m, b); a1 = __fma_rn(a1, m, b); a2 = __fma_rn(a2, m, b); a3 = __fma_rn(a3, m, b);
+            a4 = __fma_rn(a4, m, b); a5 = __fma_rn(a5, m, b); a6 = __fma_rn(a6, m, b); a7 = __fma_rn(a7, m, b);
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;      /* keep the chains alive */
+}
+
+/* ------------------------------------------------------------------ */
+/* element-wise batch kernels (unit parity tests through the C-ABI)    */
+/* ------------------------------------------------------------------ */
+__global__ void k_batch_rf(long long n, const double* x, const double* y, const double* z, double* o)
+{ for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = rf(x[i], y[i], z[i]); }
+__global__ void k_batch_rd(long long n, const double* x, const double* y, const double* z, double* o)
+{ for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = rd(x[i], y[i], z[i]); }
+__global__ void k_batch_rc(long long n, const double* x, const double* y, double* o)
+{ for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = rc(x[i], y[i]); }
+__global__ void k_batch_rj(long long n, const double* x, const double* y, const double* z, const double* p, double* o)
+{ for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = rj(x[i], y[i], z[i], p[i]); }
+__global__ void k_batch_sncndn(long long n, const double* u, const double* m, double* sn, double* cn, double* dn)
+{ for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) jacobi_sncndn(u[i], m[i], &sn[i], &cn[i], &dn[i]); }
+__global__ void k_batch_libm(int op, long long n, const double* a, const double* b, double* o)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double v;
+        switch (op) {
+            case 0: v = crm::cr_sin(a[i]); break;
+            case 1: v = crm::cr_cos(a[i]); break;
+            case 2: v = crm::cr_log(a[i]); break;
+            case 3: v = crm::cr_atan2(a[i], b[i]); break;
+            case 4: v = crm::cr_acos(a[i]); break;
+            case 5: v = crm::cr_asin(a[i]); break;
+            case 6: v = crm::cr_atan(a[i]); break;
+            case 7: v = crm::cr_pow_third(a[i]); break;
+            case 8: v = crm::cr_pow_1p5(a[i]); break;
+            case 9: v = crm::cr_pow_4(a[i]); break;
+            case 10: v = exp(a[i]); break;
+            default: v = NAN;
+        }
+        o[i] = v;
+    }
+}
+
+} /* namespace s5 */
+#endif
