@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SIM5 photon hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, one process per GPU)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU implementation (host cores)
+
+Workload (BASELINE.json configs[1]): thin-disk image 4096x4096, a=0.998, i=75 deg, outputs r, phi, g,
+F*g^4 and the status byte; one STEP = one full image.  At N>1 the image rows are dealt to the ranks
+in interleaved 32-row blocks (sim5_b200/dist.py), every rank traces its rows, and the planes are gathered
+on rank 0 with NCCL at the end of the step (strong scaling: total work per step is fixed).
+
+Metric: geodesics (rays) per second.
+  value : device-resident -- planes stay in HBM (gathered to rank 0's HBM at N>1); CUDA events on the launch stream
+  e2e   : through the public host API (sim5_trace_image with pinned HOST planes): the timed region holds
+          the parameter upload and the device->host copy of every plane, every step
+Roofline: FP64 non-tensor pipe (no dense contraction, 44 B written and 0 B read per ray -> compute bound);
+  achieved = F_alg (16.8 kflop per ray with azimuth) * rays / kernel time,
+  peak = live DFMA-chain microbenchmark (MEASURED_PEAKS.json has no FP64 entry).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "geodesics_per_second"
+UNIT = "rays/s"
+F_ALG_PHI = 16.8e3        # flop per ray, (r, phi, g, F): SURVEY.md 8(d) non-redundant algorithm, / = 15, sqrt = 13 flop
+BYTES_PER_RAY = 4 * 8 + 1
+SAMPLE_N = 1024           # CPU sample: the same camera at 1024x1024 (1/16 of the rays of the 4096^2 image)
+
+
+def workload_params(abi, n=None):
+    p = abi.default_params(2)
+    if n:
+        p.nx = p.ny = n
+    return p
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu = gpu
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation (oracle/_ref, the unmodified sources + OpenMP pixel loop) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import harness as H
+    from sim5_b200 import abi
+    p = workload_params(abi, SAMPLE_N)
+    if H.have_ref():
+        kind, run = "reference", H.run_ref
+        cores = H.load_ref().ref_max_threads()
+    elif H.have_oracle():
+        kind, run = "port", H.run_oracle
+        cores = os.cpu_count()
+    else:
+        print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref/libsim5ref.so nor oracle/libsim5oracle.so is built"}))
+        return 0
+    for _ in range(args.warmup):
+        run(p)
+    t = 0.0
+    for _ in range(args.steps):
+        _, st, dt = run(p)
+        t += dt
+    rays = p.nx * p.ny * args.steps
+    v = rays / t
+    sample = "same camera (a=0.998, i=75deg, rmax=r_ms+20, r/phi/g/flux/status) at %dx%d = 1/16 of the rays per step" % (SAMPLE_N, SAMPLE_N)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_dict(args.gpus, 4096),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def config_dict(n_gpus, n):
+    return {"workload": "BASELINE configs[1]: Novikov-Thorne thin-disk image %dx%d, a=0.998, i=75deg, rmax=r_ms+20, "
+                        "outputs r/phi/g/F*g^4/status, crossing orders 0-1" % (n, n),
+            "rays_per_step": n * n, "parallelism": "rows interleaved over %d GPU(s) in 32-row blocks, NCCL gather to rank 0" % n_gpus,
+            "l2": "no input reads (rays are generated from the pixel index); %d MB of output planes per step > 126 MB L2" % (n * n * BYTES_PER_RAY // 1000000),
+            "e2e_note": "each rank copies its own rows to its own pinned host planes" if n_gpus > 1 else "pinned host planes"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    from sim5_b200 import abi, api, dist as sdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    api.init(local)
+    L = api.lib()
+    stream = torch.cuda.Stream(device=dev)      # a real (non-default) stream: the library launches on it, torch events time it
+    torch.cuda.set_stream(stream)
+    api.check(L.sim5_set_stream(C.c_void_p(stream.cuda_stream)), "sim5_set_stream")
+
+    n = args.size
+    p = workload_params(abi, n)
+    p.device = local
+    rows = sdist.apply_split(p, rank, world) if world > 1 else n
+    p.flags = abi.FLAG_DEVICE_PTRS | abi.FLAG_ASYNC
+    names = ("r", "phi", "g", "flux")
+    loc = {k: torch.empty((rows, n), dtype=torch.float64, device=dev) for k in names}
+    loc["status"] = torch.empty((rows, n), dtype=torch.uint8, device=dev)
+    out = abi.ImageOut()
+    for k, t in loc.items():
+        setattr(out, k, t.data_ptr())
+    gath = None
+    if world > 1 and rank == 0:
+        gath = {k: [torch.empty_like(t) for _ in range(world)] for k, t in loc.items()}
+    st = abi.TraceStats()
+    kev = []
+
+    def step(timed):
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        api.check(L.sim5_trace_image(C.byref(p), C.byref(out), C.byref(st)), "sim5_trace_image")
+        if timed:
+            e1.record()
+            kev.append((e0, e1))
+        if world > 1:
+            full = None
+            for k, t in loc.items():
+                dist.gather(t, gath[k] if rank == 0 else None, dst=0)
+                if rank == 0:
+                    full = sdist.assemble(gath[k], world)
+            return full
+        return None
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak_tf = api.fp64_peak_tflops(local, 8192) if rank == 0 else None
+    api.check(L.sim5_set_stream(C.c_void_p(stream.cuda_stream)), "sim5_set_stream")
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    fence()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    fence()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step(True)
+    ev1.record()
+    fence()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    kms = torch.tensor([sum(a.elapsed_time(b) for a, b in kev) / len(kev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    kernel_ms = float(kms.item())
+    rays_step = n * n
+    value = rays_step * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: public host API, pinned host planes, H2D of the parameters + D2H of every plane inside the timed region
+    api.check(L.sim5_set_stream(None), "sim5_set_stream")
+    ph = workload_params(abi, n)
+    ph.device = local
+    if world > 1:
+        sdist.apply_split(ph, rank, world)
+    hp = api.HostPlanes(ph, pinned=True)
+    for _ in range(2):
+        api.trace_image(ph, hp)
+    fence()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, hst = api.trace_image(ph, hp)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    e2e_s = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    fence()
+    clocks = sampler.stop() if sampler else None
+    e2e_value = rays_step * args.steps / float(e2e_s.item())
+    checksum = float(hp["g"].sum())
+
+    if rank == 0:
+        # CPU baseline beside it (N=1 only): the unmodified reference on the host cores, bounded sample
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            try:
+                import harness as H
+                ps = workload_params(abi, SAMPLE_N)
+                if H.have_ref():
+                    kind, run, cores = "reference", H.run_ref, H.load_ref().ref_max_threads()
+                else:
+                    kind, run, cores = "port", H.run_oracle, os.cpu_count()
+                run(ps)
+                _, _, dt = run(ps)
+                cpu = {"value": ps.nx * ps.ny / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                       "sample": "same camera at %dx%d (1/16 of the rays), all host threads, 1 timed pass after 1 warm-up" % (SAMPLE_N, SAMPLE_N)}
+            except Exception as e:  # the checker is optional for the benchmark itself
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
+        achieved = F_ALG_PHI * (rays_step / world) / (kernel_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+                traffic = json.load(fh).get("k_trace_eqplane_dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(world, n),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(abi.ImageParams),
+                    "d2h_bytes_per_step": (rays_step // world) * BYTES_PER_RAY, "checksum_g": checksum},
+            "gpu_launches": args.steps * world,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
+                         "peak_source": "live FP64 DFMA-chain microbenchmark (sim5_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry",
+                         "flop_per_ray": F_ALG_PHI, "kernel_ms": kernel_ms, "kernel": "k_trace_eqplane",
+                         "hbm_written_bytes_per_launch": (rays_step // world) * BYTES_PER_RAY},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=4096, help="image side (default: the BASELINE 4096)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -59,6 +59,8 @@ extern "C" {
 /* flags */
 #define SIM5_FLAG_DEVICE_PTRS   0x1  /* pointers in sim5_image_out are device pointers (no staging, no D2H) */
 #define SIM5_FLAG_NO_REFILL     0x2  /* debugging: disable warp-level lane refill / compaction */
+#define SIM5_FLAG_ASYNC         0x4  /* with DEVICE_PTRS: enqueue on the library stream (sim5_set_stream) and return without
+                                        synchronising; stats are not filled.  Pair with sim5_synchronize(). */
 
 /* ------------------------------------------------------------------ */
 /* per-pixel status byte                                               */
@@ -144,6 +146,11 @@ typedef struct sim5_image_params {
     double   incl_min_deg, incl_max_deg; /* i_k = min + (max-min)*k/(n_incl-1) degrees */
     double   g_min, g_max;       /* histogram range */
     double   rmax_offset;        /* rmax = r_ms(a_j) + rmax_offset */
+    /* multi-GPU interleaved row split: with split_count > 1 this call traces only the row blocks
+     * b = (iy - row_begin) / split_rows with b % split_count == split_index (one process per GPU, each with its
+     * own index).  Host planes keep full-image indexing; DEVICE planes are compact: local row
+     * lr = (b / split_count) * split_rows + (iy - row_begin) % split_rows, index lr*nx + ix. */
+    int32_t  split_count, split_index, split_rows, reserved2;
 } sim5_image_params;
 
 typedef struct sim5_image_out {
@@ -176,6 +183,8 @@ typedef struct sim5_trace_stats {
 
 /* lifecycle ------------------------------------------------------------- */
 int  sim5_gpu_init(int device);        /* create context/streams/scratch on `device`; idempotent */
+int  sim5_set_stream(void* cuda_stream); /* launch on the caller's cudaStream_t (e.g. torch's current stream); NULL = library stream */
+int  sim5_synchronize(void);            /* wait for everything enqueued by SIM5_FLAG_ASYNC calls */
 void sim5_gpu_shutdown(void);
 int  sim5_gpu_device_count(void);      /* 0 when no usable device */
 const char* sim5_last_error(void);

@@ -248,6 +248,7 @@ double ref_trace_image(const sim5_image_params* p, const sim5_image_out* out, in
     #pragma omp parallel for schedule(dynamic,4)
     for (iy = rb; iy < re; iy++) {
         int ix;
+        if (p->split_count > 1 && ((iy - rb) / (p->split_rows > 0 ? p->split_rows : 1)) % p->split_count != p->split_index) continue;
         for (ix = 0; ix < nx; ix++) {
             double alpha = (((double)(ix)+.5)/(double)(nx)-0.5)*2.0*rmax;
             double beta  = (((double)(iy)+.5)/(double)(ny)-0.5)*2.0*rmax * ((double)ny/(double)nx);

@@ -43,7 +43,7 @@ struct Context {
     bool warned = false;
     int device = -1;
     int sm_count = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     Scratch* h_scr = nullptr;
     Scratch* d_scr = nullptr;
@@ -106,7 +106,8 @@ int ensure_init(int device)
     }
     c.device = device;
     c.sm_count = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    c.stream = c.own_stream;
     CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c.ev0)); CK(cudaEventCreate(&c.ev1)); CK(cudaEventCreate(&c.ev2)); CK(cudaEventCreate(&c.ev3));
     CK(cudaHostAlloc((void**)&c.h_scr, sizeof(Scratch), cudaHostAllocMapped));
@@ -258,8 +259,24 @@ extern "C" void sim5_gpu_shutdown(void)
     for (int i = 0; i < 8; i++) { if (c.batch[i]) cudaFree(c.batch[i]); c.batch[i] = nullptr; c.batch_bytes[i] = 0; }
     cudaFreeHost(c.h_scr); cudaFreeHost(c.h_consts); cudaFree(c.d_consts); cudaFree(c.d_counter); cudaFree(c.d_stats); cudaFreeHost(c.h_stats);
     cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1); cudaEventDestroy(c.ev2); cudaEventDestroy(c.ev3);
-    cudaStreamDestroy(c.stream); cudaStreamDestroy(c.copy_stream);
+    cudaStreamDestroy(c.own_stream); cudaStreamDestroy(c.copy_stream);
     c.ready = false;
+}
+
+extern "C" int sim5_set_stream(void* cuda_stream)
+{
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    int rc = ensure_init(-1);
+    if (rc) return rc;
+    g_ctx.stream = cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.own_stream;
+    return SIM5_OK;
+}
+extern "C" int sim5_synchronize(void)
+{
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (!g_ctx.ready) return SIM5_OK;
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    return SIM5_OK;
 }
 
 extern "C" int sim5_gpu_device_count(void)
@@ -351,11 +368,19 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     for (int i = 0; i < 12; i++)
         if ((p->outputs & kPlaneInfo[i].bit) && !host_plane(out, i)) { set_error("selected output plane is NULL"); return SIM5_ERR_NO_OUTPUT; }
 
-    size_t npix = (size_t)(re - rb) * (size_t)p->nx;
+    int split = p->split_count > 1 ? p->split_count : 1;
+    int srows = p->split_rows > 0 ? p->split_rows : 1;
+    if (split > 1) {
+        if (p->split_index < 0 || p->split_index >= split) { set_error("bad split_index"); return SIM5_ERR_BAD_PARAM; }
+        if ((re - rb) % (split * srows) != 0) { set_error("row range must be a multiple of split_count*split_rows"); return SIM5_ERR_BAD_PARAM; }
+    }
+    int nrows_local = (re - rb) / split;
+    size_t npix = (size_t)nrows_local * (size_t)p->nx;
     bool devptr = (p->flags & SIM5_FLAG_DEVICE_PTRS) != 0;
+    bool async = devptr && (p->flags & SIM5_FLAG_ASYNC);
     DevOut d;
     memset(&d, 0, sizeof d);
-    d.base_row = devptr ? 0 : rb;
+    d.compact = (!devptr || split > 1) ? 1 : 0;
     for (int i = 0; i < 12; i++) {
         if (!(p->outputs & kPlaneInfo[i].bit)) continue;
         if (devptr) { set_dev_plane(&d, i, host_plane(out, i)); continue; }
@@ -364,9 +389,9 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         set_dev_plane(&d, i, c.planes[i].p);
     }
 
-    s5_fill_image_consts(p, c.h_consts);
+    S5ImageConsts consts;                  /* travels by value as a kernel parameter: no H2D copy, async-safe */
+    s5_fill_image_consts(p, &consts);
     CK(cudaEventRecord(c.ev0, c.stream));
-    CK(cudaMemcpyAsync(c.d_consts, c.h_consts, sizeof(S5ImageConsts), cudaMemcpyHostToDevice, c.stream));
     CK(cudaMemsetAsync(c.d_counter, 0, sizeof(unsigned long long), c.stream));
     CK(cudaMemsetAsync(c.d_stats, 0, sizeof(DevStats), c.stream));
     int grid = 0;
@@ -374,19 +399,29 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     if (npix > 0) {
         if (p->mode == SIM5_MODE_STEPWISE) {
             grid = persistent_grid(s5::k_trace_stepwise, S5_CTA_THREADS);
-            s5::k_trace_stepwise<<<grid, S5_CTA_THREADS, 0, c.stream>>>(c.d_consts, d, c.d_counter, c.d_stats);
+            s5::k_trace_stepwise<<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d, c.d_counter, c.d_stats);
         } else {
             grid = persistent_grid(s5::k_trace_eqplane, S5_CTA_THREADS);
-            s5::k_trace_eqplane<<<grid, S5_CTA_THREADS, 0, c.stream>>>(c.d_consts, d, c.d_counter, c.d_stats);
+            s5::k_trace_eqplane<<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d, c.d_counter, c.d_stats);
         }
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(c.ev2, c.stream));
+    if (async) return SIM5_OK;
     if (!devptr && npix > 0) {
         for (int i = 0; i < 12; i++) {
             if (!(p->outputs & kPlaneInfo[i].bit)) continue;
-            char* dst = (char*)host_plane(out, i) + (size_t)rb * p->nx * kPlaneInfo[i].elem;
-            CK(cudaMemcpyAsync(dst, c.planes[i].p, npix * kPlaneInfo[i].elem, cudaMemcpyDeviceToHost, c.stream));
+            size_t es = kPlaneInfo[i].elem;
+            if (split == 1) {
+                char* dst = (char*)host_plane(out, i) + (size_t)rb * p->nx * es;
+                CK(cudaMemcpyAsync(dst, c.planes[i].p, npix * es, cudaMemcpyDeviceToHost, c.stream));
+            } else {
+                size_t blk = (size_t)srows * p->nx * es;
+                for (int b = 0; b < nrows_local / srows; b++) {
+                    int iy0 = rb + (b * split + p->split_index) * srows;
+                    CK(cudaMemcpyAsync((char*)host_plane(out, i) + (size_t)iy0 * p->nx * es, (char*)c.planes[i].p + (size_t)b * blk, blk, cudaMemcpyDeviceToHost, c.stream));
+                }
+            }
         }
     }
     CK(cudaMemcpyAsync(c.h_stats, c.d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c.stream));

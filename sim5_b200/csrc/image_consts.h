@@ -22,6 +22,7 @@ struct S5ImageConsts {
     double rmin_emit;    /* r_ms(a) unless overridden, disk-image.c:41,83 */
     double r_bh;
     int nx, ny, row_begin, row_end;
+    int nrows_local, split_count, split_index, split_rows;   /* rows this call traces and how they map to image rows */
     int max_order, mode;
     unsigned outputs, flags;
     /* Novikov-Thorne flux, sim5disk-nt.c:109-146 with the float statics of :27-32 */
@@ -64,6 +65,15 @@ static inline double s5_host_disk_nt_r_min(double a)
     return r0 + 1e-3;
 }
 
+/* image row of local row lr (contiguous when split_count == 1) */
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline int s5_local_to_image_row(const S5ImageConsts* c, int lr)
+{
+    return c->row_begin + ((lr / c->split_rows) * c->split_count + c->split_index) * c->split_rows + lr % c->split_rows;
+}
+
 static inline void s5_fill_image_consts(const sim5_image_params* p, S5ImageConsts* c)
 {
     memset(c, 0, sizeof(*c));
@@ -77,6 +87,10 @@ static inline void s5_fill_image_consts(const sim5_image_params* p, S5ImageConst
     c->nx = p->nx; c->ny = p->ny;
     c->row_begin = p->row_begin; c->row_end = p->row_end;
     if (c->row_begin == 0 && c->row_end == 0) c->row_end = p->ny;
+    c->split_count = p->split_count > 1 ? p->split_count : 1;
+    c->split_index = p->split_count > 1 ? p->split_index : 0;
+    c->split_rows  = p->split_rows > 0 ? p->split_rows : 1;
+    c->nrows_local = (c->row_end - c->row_begin) / c->split_count;
     c->max_order = p->max_order;
     c->mode = p->mode;
     c->outputs = p->outputs;

@@ -6,7 +6,8 @@
  *   - every WARP pulls tiles of 32 consecutive pixels of a row from one global atomic counter
  *     (dynamic balance between the cheap outer image and the expensive shadow edge, no block syncs);
  *   - per-image constants (S5ImageConsts, ~0.7 KB incl. the Novikov-Thorne and Chandrasekhar tables)
- *     are staged in shared memory once per CTA;
+ *     travel as a __grid_constant__ kernel parameter and are staged in shared memory once per CTA
+ *     (the table lookups are lane-divergent, which shared memory serves without serialisation);
  *   - outputs are SoA planes; a warp stores 32 consecutive doubles per plane (one 256-byte
  *     fully-coalesced transaction), no reads from HBM at all;
  *   - the stepwise kernel keeps one live ray per lane and refills finished lanes from the queue
@@ -24,7 +25,7 @@ struct DevOut {
     double *r, *phi, *g, *flux, *chi, *delta, *mue, *intensity, *tau, *qerr;
     int* steps;
     unsigned char* status;
-    int base_row;                 /* plane index = (iy - base_row)*nx + ix */
+    int compact;                  /* 1: plane index = local_row*nx + ix ; 0: full-image index iy*nx + ix */
 };
 
 struct DevStats {                 /* device-side counters, flushed once per CTA */
@@ -73,16 +74,16 @@ __device__ __forceinline__ void flush_stats(const unsigned int* s_cnt, unsigned 
 /* modes EQPLANE / POLARIZED : analytic geodesic per pixel             */
 /* ------------------------------------------------------------------ */
 __global__ void __launch_bounds__(S5_CTA_THREADS)
-k_trace_eqplane(const S5ImageConsts* __restrict__ gconsts, DevOut out, unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
+k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
 {
     __shared__ S5ImageConsts c;
     __shared__ unsigned int s_cnt[40];
     if (threadIdx.x < 40) s_cnt[threadIdx.x] = 0;
-    stage_consts(&c, gconsts);
+    stage_consts(&c, &gconsts);
 
     const int lane = threadIdx.x & 31;
     const long long nx = c.nx;
-    const long long npix = (long long)(c.row_end - c.row_begin) * nx;
+    const long long npix = (long long)c.nrows_local * nx;
     const long long ntiles = (npix + 31) >> 5;
 
     for (;;) {
@@ -92,11 +93,12 @@ k_trace_eqplane(const S5ImageConsts* __restrict__ gconsts, DevOut out, unsigned 
         if ((long long)t >= ntiles) break;
         long long p = ((long long)t << 5) + lane;
         if (p < npix) {
-            int iy = c.row_begin + (int)(p / nx);
-            int ix = (int)(p - (long long)(iy - c.row_begin) * nx);
+            int lr = (int)(p / nx);
+            int ix = (int)(p - (long long)lr * nx);
+            int iy = s5_local_to_image_row(&c, lr);
             PixelOut o;
             trace_eqplane_pixel(c, ix, iy, &o);
-            size_t i = (size_t)(iy - out.base_row) * (size_t)nx + (size_t)ix;
+            size_t i = out.compact ? (size_t)p : (size_t)iy * (size_t)nx + (size_t)ix;
             store_pixel(out, c.outputs, i, o);
             atomicAdd(&s_cnt[o.status & 31], 1u);
             atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);
@@ -112,18 +114,18 @@ k_trace_eqplane(const S5ImageConsts* __restrict__ gconsts, DevOut out, unsigned 
 #define S5_REFILL_MIN 4
 
 __global__ void __launch_bounds__(S5_CTA_THREADS)
-k_trace_stepwise(const S5ImageConsts* __restrict__ gconsts, DevOut out, unsigned long long* __restrict__ ray_counter, DevStats* __restrict__ gstats)
+k_trace_stepwise(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigned long long* __restrict__ ray_counter, DevStats* __restrict__ gstats)
 {
     __shared__ S5ImageConsts c;
     __shared__ unsigned int s_cnt[40];
     __shared__ unsigned long long s_steps;
     if (threadIdx.x < 40) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_steps = 0;
-    stage_consts(&c, gconsts);
+    stage_consts(&c, &gconsts);
 
     const int lane = threadIdx.x & 31;
     const long long nx = c.nx;
-    const long long npix = (long long)(c.row_end - c.row_begin) * nx;
+    const long long npix = (long long)c.nrows_local * nx;
     const bool refill = !(c.flags & SIM5_FLAG_NO_REFILL);
 
     StepRay s;
@@ -147,14 +149,15 @@ k_trace_stepwise(const S5ImageConsts* __restrict__ gconsts, DevOut out, unsigned
             if (!live) {
                 long long p = (long long)base + __popc(idle & ((1u << lane) - 1u));
                 if (p < npix) {
-                    int iy = c.row_begin + (int)(p / nx);
-                    int ix = (int)(p - (long long)(iy - c.row_begin) * nx);
+                    int lr = (int)(p / nx);
+                    int ix = (int)(p - (long long)lr * nx);
+                    int iy = s5_local_to_image_row(&c, lr);
                     PixelOut o;
                     mypix = p;
                     if (stepwise_start(c, ix, iy, &s, &o)) {
                         live = true;
                     } else {
-                        size_t i = (size_t)(iy - out.base_row) * (size_t)nx + (size_t)ix;
+                        size_t i = out.compact ? (size_t)p : (size_t)iy * (size_t)nx + (size_t)ix;
                         store_pixel(out, c.outputs, i, o);
                         atomicAdd(&s_cnt[o.status & 31], 1u);
                         atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);
@@ -172,9 +175,10 @@ k_trace_stepwise(const S5ImageConsts* __restrict__ gconsts, DevOut out, unsigned
                     PixelOut o;
                     o.r = o.phi = o.g = o.flux = o.chi = o.delta = o.mue = 0.0;
                     stepwise_finish(c, &s, cls, &o);
-                    int iy = c.row_begin + (int)(mypix / nx);
-                    int ix = (int)(mypix - (long long)(iy - c.row_begin) * nx);
-                    size_t i = (size_t)(iy - out.base_row) * (size_t)nx + (size_t)ix;
+                    int lr = (int)(mypix / nx);
+                    int ix = (int)(mypix - (long long)lr * nx);
+                    int iy = s5_local_to_image_row(&c, lr);
+                    size_t i = out.compact ? (size_t)mypix : (size_t)iy * (size_t)nx + (size_t)ix;
                     store_pixel(out, c.outputs, i, o);
                     atomicAdd(&s_cnt[o.status & 31], 1u);
                     atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);

@@ -137,3 +137,61 @@ def err_summary(x, ref, floor=0.0):
         return {"max": 0.0, "p999": 0.0, "exact": 1.0, "n": 0}
     return {"max": float(e.max()), "p999": float(np.quantile(e, 0.999)), "exact": float(np.mean(e == 0.0)),
             "n": int(e.size)}
+
+
+# tolerances of BASELINE.json's north_star: bit-exact classification / termination flags;
+# relative error <= 1e-9 on r, phi, g and <= 1e-7 on the polarization angle and flux.
+TOL = {"r": 1e-9, "phi": 1e-9, "g": 1e-9, "flux": 1e-7, "chi": 1e-7, "delta": 1e-7, "mue": 1e-9,
+       "intensity": 1e-7, "tau": 1e-7, "qerr": None}
+FLOOR = {"phi": 1.0, "chi": 1.0}          # |dphi| / max(|phi|, 1): phi ~ 1e-5 on the alpha ~ 0 column
+
+
+def assert_image_parity(got, ref, label="", tol=TOL):
+    """got/ref: dicts of flat arrays (Planes.arrays or npz).  Returns the per-plane error summaries."""
+    report = {}
+    if "status" in ref:
+        bad = int(np.sum(np.asarray(got["status"]) != np.asarray(ref["status"])))
+        assert bad == 0, "%s: status byte differs on %d pixels" % (label, bad)
+    if "steps" in ref:
+        bad = int(np.sum(np.asarray(got["steps"]) != np.asarray(ref["steps"])))
+        assert bad == 0, "%s: step count differs on %d rays" % (label, bad)
+    for k in ref:
+        if k in ("status", "steps", "class_count", "gtype_count") or k not in got:
+            continue
+        t = tol.get(k)
+        s = err_summary(got[k], ref[k], FLOOR.get(k, 0.0))
+        report[k] = s
+        if t is not None:
+            assert s["max"] <= t, "%s: %s max rel err %.3e > %.1e (p99.9 %.3e)" % (label, k, s["max"], t, s["p999"])
+    return report
+
+
+def load_hostsim():
+    if "hostsim" not in _libs:
+        lib = C.CDLL(os.path.join(ROOT, "tests", "_build", "libhostsim.so"))
+        lib.hs_trace_image.restype = C.c_double
+        lib.hs_trace_image.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(abi.ImageOut), C.c_int]
+        _libs["hostsim"] = lib
+    return _libs["hostsim"]
+
+
+def run_hostsim(p, nthreads=0):
+    pl = Planes(p)
+    dt = load_hostsim().hs_trace_image(C.byref(p), C.byref(pl.out), nthreads)
+    return pl, None, dt
+
+
+def golden(name):
+    return np.load(os.path.join(ROOT, "tests", "golden", name))
+
+
+GOLDEN_IMAGES = (  # (file, cfg, nx, ny, extra output bits)
+    ("image_cfg1_64.npz", 1, 64, 64, 0), ("image_cfg2_64.npz", 2, 64, 64, 0), ("image_cfg2_50x37.npz", 2, 50, 37, 0),
+    ("image_cfg3_64.npz", 3, 64, 64, abi.OUT_MUE), ("image_cfg4_16.npz", 4, 16, 16, abi.OUT_QERR),
+)
+
+
+def golden_params(cfg, nx, ny, extra):
+    p = abi.default_params(cfg, nx, ny)
+    p.outputs |= extra
+    return p

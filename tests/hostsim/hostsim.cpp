@@ -58,7 +58,8 @@ double hs_trace_image(const sim5_image_params* p, const sim5_image_out* out, int
     if (nthreads > 0) omp_set_num_threads(nthreads);
     double t0 = omp_get_wtime();
     #pragma omp parallel for schedule(dynamic, 4)
-    for (int iy = c.row_begin; iy < c.row_end; iy++) {
+    for (int lr = 0; lr < c.nrows_local; lr++) {
+        int iy = s5_local_to_image_row(&c, lr);
         for (int ix = 0; ix < c.nx; ix++) {
             PixelOut o;
             if (c.mode == SIM5_MODE_STEPWISE) {

@@ -1,0 +1,104 @@
+"""C-ABI surface: the library loads, exports every symbol the headers declare, struct layouts match the
+reference's (geodesic 240 B, raytrace_data 144 B) and the ctypes mirror.  No compute calls."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from sim5_b200 import abi, api  # noqa: E402
+
+
+def _declared_functions(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    src = re.sub(r"#[^\n]*(\\\n[^\n]*)*", "", src)
+    names = set()
+    for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}()]*\)\s*;", src):
+        names.add(m.group(1))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    L = api.lib()
+    declared = _declared_functions("sim5_b200.h") | _declared_functions("sim5lib.h")
+    assert len(declared) > 90
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, "declared in include/*.h but not exported: %s" % missing
+
+
+def test_struct_layouts_match_c(tmp_path):
+    src = tmp_path / "sizes.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "sim5lib.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(geodesic), sizeof(raytrace_data), sizeof(sim5metric), sizeof(sim5tetrad),
+           sizeof(sim5_image_params), sizeof(sim5_image_out), sizeof(sim5_trace_stats));
+    printf("%zu %zu %zu %zu %zu %zu\n", offsetof(geodesic, r1), offsetof(geodesic, nrr), offsetof(geodesic, m2p),
+           offsetof(geodesic, Rpc), offsetof(geodesic, k), offsetof(geodesic, p));
+    printf("%zu %zu %zu %zu\n", offsetof(raytrace_data, WP), offsetof(raytrace_data, dk), offsetof(raytrace_data, kt), offsetof(raytrace_data, error));
+    return 0;
+}
+''')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=gnu11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-lm"])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    sizes = [int(x) for x in out[0].split()]
+    assert sizes[:4] == [240, 144, 64, 192]                     # SURVEY.md 8a [probe] numbers of the reference structs
+    assert sizes[4] == C.sizeof(abi.ImageParams)
+    assert sizes[5] == C.sizeof(abi.ImageOut)
+    assert sizes[6] == C.sizeof(abi.TraceStats)
+    assert [int(x) for x in out[1].split()] == [56, 120, 128, 176, 200, 232]
+    assert [int(x) for x in out[2].split()] == [40, 64, 128, 136]
+
+
+def test_default_params_agree_with_python_presets():
+    L = api.lib()
+    for cfg in range(1, 6):
+        q = abi.ImageParams()
+        assert L.sim5_default_params(cfg, C.byref(q)) == 0
+        p = abi.default_params(cfg)
+        for name, _ in abi.ImageParams._fields_:
+            assert getattr(p, name) == getattr(q, name), (cfg, name, getattr(p, name), getattr(q, name))
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU every entry must FAIL (no silent CPU path); with a GPU this test is a no-op."""
+    L = api.lib()
+    if L.sim5_gpu_device_count() > 0:
+        pytest.skip("GPU present")
+    p = abi.default_params(1, 8)
+    planes = api.HostPlanes(p, pinned=False)
+    st = abi.TraceStats()
+    rc = L.sim5_trace_image(C.byref(p), C.byref(planes.out), C.byref(st))
+    assert rc == abi.ERR_NO_DEVICE
+    assert b"no CPU path" in L.sim5_last_error()
+    L.rf.restype = C.c_double
+    L.rf.argtypes = [C.c_double] * 3
+    v = L.rf(0.0, 1.0, 1.0)
+    assert v != v                                                # NaN, not pi/2
+    with pytest.raises(api.Sim5Error):
+        api.init(0)
+
+
+def test_product_does_not_reference_oracle():
+    """The product tree must not import, link or execute anything under oracle/ or tests/."""
+    bad = []
+    for base, _, files in os.walk(os.path.join(ROOT, "sim5_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                # code references only (comments may cite the checkers): includes, imports, dlopen/CDLL, link flags
+                for line in txt.splitlines():
+                    code = re.sub(r"/\*.*?\*/|//.*$|#(?!include).*$", "", line) if not f.endswith(".py") else line.split("#")[0]
+                    if re.search(r"(#include|import|dlopen|CDLL|-l|\.so).*(oracle|sim5ref|hostsim)", code):
+                        bad.append((os.path.join(base, f), line.strip()))
+    assert not bad, bad
+    out = subprocess.check_output(["ldd", api.LIB_PATH], text=True)
+    assert "sim5ref" not in out and "oracle" not in out and "hostsim" not in out

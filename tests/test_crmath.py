@@ -1,0 +1,88 @@
+"""The double-double device libm (sim5_b200/csrc/crmath.cuh), exercised through its host instantiation:
+(1) against the exact value from mpmath -- it must be the correctly rounded result essentially always;
+(2) against glibc (what the reference calls) on the committed vectors -- never more than 1 ulp apart and
+    equal in > 99.5 % of calls (glibc itself is not correctly rounded in ~0.1 %)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+
+ROOT = H.ROOT
+OPS = {"sin": 0, "cos": 1, "log": 2, "atan2": 3, "acos": 4, "asin": 5, "atan": 6, "pow_third": 7, "pow_1p5": 8, "pow_4": 9}
+
+
+@pytest.fixture(scope="module")
+def hs():
+    return C.CDLL(os.path.join(ROOT, "tests", "_build", "libhostsim.so"))
+
+
+def _call(hs, op, a, b=None):
+    b = np.zeros_like(a) if b is None else b
+    return H.batch_call(hs, "hs_batch_libm", [a, b], extra=(C.c_int(OPS[op]),))
+
+
+def test_against_glibc_vectors(hs):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "libm_glibc.npz"))
+    for op in OPS:
+        a = g[op + "_in"]
+        mine = _call(hs, op, a, g["atan2_x"] if op == "atan2" else None)
+        ref = g[op + "_glibc"]
+        ulp = np.abs(mine - ref) / np.spacing(np.abs(ref))
+        assert np.nanmax(ulp) <= 1.0, op
+        assert np.mean(mine == ref) > 0.995, (op, float(np.mean(mine == ref)))
+
+
+def test_correctly_rounded_against_mpmath(hs):
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 200
+    rng = np.random.default_rng(7)
+    n = 1500
+    cases = {
+        "sin": (rng.uniform(-7, 7, n), mp.sin), "cos": (rng.uniform(-7, 7, n), mp.cos),
+        "log": (np.exp(rng.uniform(-10, 10, n)), mp.log), "acos": (rng.uniform(-1, 1, n), mp.acos),
+        "asin": (rng.uniform(-1, 1, n), mp.asin), "atan": (rng.normal(size=n) * 3, mp.atan),
+        "pow_third": (np.exp(rng.uniform(-20, 40, n)), lambda x: mp.power(x, mp.mpf(1. / 3.))),
+        "pow_1p5": (np.exp(rng.uniform(-2, 8, n)), lambda x: mp.power(x, mp.mpf(1.5))),
+        "pow_4": (rng.uniform(0, 2, n), lambda x: x ** 4),
+    }
+    for op, (a, f) in cases.items():
+        mine = _call(hs, op, a)
+        exact = np.array([float(f(mp.mpf(float(x)))) for x in a])
+        assert np.mean(mine == exact) >= 0.999, (op, float(np.mean(mine == exact)))
+    y = rng.normal(size=n); x = rng.normal(size=n)
+    mine = _call(hs, "atan2", y, x)
+    exact = np.array([float(mp.atan2(mp.mpf(float(a)), mp.mpf(float(b)))) for a, b in zip(y, x)])
+    assert np.mean(mine == exact) >= 0.999
+
+
+def test_special_values(hs):
+    inf = np.inf
+    assert list(_call(hs, "sin", np.array([0.0, 1e-300]))) == [0.0, 1e-300]
+    assert _call(hs, "cos", np.array([0.0]))[0] == 1.0
+    assert _call(hs, "log", np.array([1.0]))[0] == 0.0
+    assert _call(hs, "log", np.array([0.0]))[0] == -inf
+    assert np.isnan(_call(hs, "log", np.array([-1.0]))[0])
+    assert _call(hs, "acos", np.array([1.0]))[0] == 0.0
+    assert _call(hs, "acos", np.array([-1.0]))[0] == np.pi
+    assert _call(hs, "acos", np.array([0.0]))[0] == np.pi / 2
+    assert np.isnan(_call(hs, "acos", np.array([1.5]))[0])
+    assert _call(hs, "atan2", np.array([0.0]), np.array([-1.0]))[0] == np.pi
+    assert _call(hs, "atan2", np.array([1.0]), np.array([0.0]))[0] == np.pi / 2
+    assert _call(hs, "pow_third", np.array([0.0, 8.0, 27.0])).tolist()[0] == 0.0
+    assert _call(hs, "pow_4", np.array([-2.0]))[0] == 16.0
+
+
+def test_x87_mu_roots_match_reference_structs(hs):
+    """geodesic_priv_T_roots uses x87 long double on the CPU (sim5kerr-geod.c:1125-1131); the emulation must
+    reproduce m2m and m2p of the reference's geodesic structs bit for bit."""
+    from tools_golden import geodesic_struct_dtype
+    g = np.load(os.path.join(ROOT, "tests", "golden", "geodesic_init_inf.npz"))
+    gd = g["g"].copy().view(geodesic_struct_dtype()).reshape(-1)
+    ok = g["ok"] == 1
+    a = gd["a"][ok]; l = gd["l"][ok]; q = gd["q"][ok]
+    m2m, m2p = H.batch_call(hs, "hs_mu_roots", [q, l * l, a * a], nout=2)
+    assert np.array_equal(m2m, gd["m2m"][ok])
+    assert np.array_equal(m2p, gd["m2p"][ok])

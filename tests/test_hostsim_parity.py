@@ -1,0 +1,116 @@
+"""CPU-side parity of the KERNEL MATH: the device headers (sim5_b200/csrc/*.cuh) instantiated on the host
+(tests/hostsim -- test-only, bit-identical arithmetic to the sm_100a build) against
+  (1) the committed golden fixtures produced by the unmodified reference, and
+  (2) the unmodified reference itself where oracle/_ref is built.
+This is what lets the build box (no GPU) vouch for the kernels before GPU time is spent; the GPU tests
+(test_gpu_parity.py) repeat the comparison through the C-ABI on the device."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+from sim5_b200 import abi
+from tools_golden import geodesic_struct_dtype
+
+
+@pytest.mark.parametrize("fname,cfg,nx,ny,extra", H.GOLDEN_IMAGES)
+def test_images_against_golden(fname, cfg, nx, ny, extra):
+    p = H.golden_params(cfg, nx, ny, extra)
+    got, _, _ = H.run_hostsim(p)
+    rep = H.assert_image_parity(got.arrays, H.golden(fname), label=fname)
+    assert rep
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("cfg,n", [(1, 160), (2, 160), (3, 128), (4, 24)])
+def test_images_against_reference(cfg, n):
+    p = abi.default_params(cfg, n)
+    got, _, _ = H.run_hostsim(p)
+    ref, st, _ = H.run_ref(p)
+    H.assert_image_parity(got.arrays, ref.arrays, label="cfg%d %d^2" % (cfg, n))
+    # every class the config is supposed to exercise is present
+    if cfg in (1, 2, 3):
+        assert st.class_count[abi.ST_HIT0] > 0 and st.class_count[abi.ST_MISS] > 0 and st.class_count[abi.ST_NOCROSS0] > 0
+        assert st.gtype_count[abi.GT_RR] > 0 and st.gtype_count[abi.GT_RC] > 0
+    else:
+        assert st.class_count[abi.ST_HORIZON] > 0 and st.class_count[abi.ST_ESCAPE] > 0
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built")
+def test_edge_cases_against_reference():
+    """Error classes and odd shapes: out-of-range spin and inclination (init errors 12, 11), zero spin
+    (clamped to 1e-4), near-polar and near-equatorial observers, order-2 crossings, 1-pixel rows, row ranges."""
+    cases = []
+    p = abi.default_params(1, 24); p.bh_spin = 1.5; cases.append(("spin>1", p))
+    p = abi.default_params(1, 24); p.incl = 1.6; cases.append(("incl>pi/2", p))
+    p = abi.default_params(1, 24); p.bh_spin = 0.0; p.rmax = 14.0; cases.append(("a=0", p))
+    p = abi.default_params(2, 24); p.incl = abi.deg2rad(1.0); cases.append(("i=1deg", p))
+    p = abi.default_params(2, 24); p.incl = abi.deg2rad(89.0); cases.append(("i=89deg", p))
+    p = abi.default_params(2, 33, 17); p.max_order = 2; cases.append(("order2 ragged", p))
+    p = abi.default_params(1, 1, 1); cases.append(("1x1", p))
+    p = abi.default_params(2, 40); p.row_begin, p.row_end = 13, 29; cases.append(("rows 13..29", p))
+    p = abi.default_params(1, 31, 64); p.r_emit_min = 3.0; cases.append(("r_emit_min", p))
+    for label, p in cases:
+        got, _, _ = H.run_hostsim(p)
+        ref, _, _ = H.run_ref(p)
+        H.assert_image_parity(got.arrays, ref.arrays, label=label)
+
+
+def test_geodesic_structs_against_golden():
+    """geodesic_init_inf through the scalar-API device function (inclination via the double-double sincos):
+    every field of the 240-byte struct against the reference's, plus the first crossing and its radius."""
+    hs = H.load_hostsim()
+    hs.hs_geodesic_init_inf.restype = C.c_int
+    hs.hs_geodesic_init_inf.argtypes = [C.c_double] * 4 + [C.c_void_p, C.POINTER(C.c_int)]
+    g = H.golden("geodesic_init_inf.npz")
+    dt = geodesic_struct_dtype()
+    ref = g["g"].copy().view(dt).reshape(-1)
+    n = len(ref)
+    exact = {k: 0 for k in ("l", "q", "m2p", "m2m", "mm", "mK", "rp", "Rpc", "Tpp", "Tip")}
+    nok = 0
+    for i in range(n):
+        buf = (C.c_char * 240)()
+        e = C.c_int(0)
+        ok = hs.hs_geodesic_init_inf(g["incl"][i], g["spin"][i], g["alpha"][i], g["beta"][i], buf, C.byref(e))
+        assert ok == g["ok"][i] and e.value == g["err"][i], i
+        if not ok:
+            continue
+        nok += 1
+        mine = np.frombuffer(buf, dtype=dt, count=1)[0]
+        assert mine["nrr"] == ref["nrr"][i] and mine["type"] == ref["type"][i]
+        for k in exact:
+            a, b = float(mine[k]), float(ref[k][i])
+            assert abs(a - b) <= 1e-9 * max(abs(b), 1e-300), (i, k, a, b)
+            exact[k] += (a == b)
+    assert nok > 1000
+    # cos(i) and sin(i) come from our sincos here, so l, q (and everything downstream) may differ by an ulp in
+    # the ~0.1 % of inclinations where glibc's sincos is not correctly rounded; the x87-emulated roots are
+    # exact whenever their inputs are
+    for k, v in exact.items():
+        assert v >= 0.98 * nok, (k, v, nok)
+
+
+def test_histogram_against_golden():
+    """cfg 5 shrunk (3 spins x 2 inclinations x 32 bins, 48^2 rays each): per-image eq-plane traces binned on the host
+    exactly as the kernel does (weight F*g^4*da*db)."""
+    hs = H.load_hostsim()
+    p = abi.default_params(5, 48)
+    p.n_spin, p.n_incl, p.n_bins = 3, 2, 32
+    ref = H.golden("hist_cfg5_3x2x32_48.npz")["hist"].reshape(3, 2, 32)
+    for js in range(3):
+        for ki in range(2):
+            q = abi.default_params(2, 48)
+            q.outputs = abi.OUT_G | abi.OUT_FLUX | abi.OUT_STATUS
+            q.bh_spin = max(p.spin_max * js / (p.n_spin - 1), 1e-4)
+            q.incl = abi.deg2rad(p.incl_min_deg + (p.incl_max_deg - p.incl_min_deg) * ki / (p.n_incl - 1))
+            q.rmax = abi.r_ms(q.bh_spin) + p.rmax_offset
+            got, _, _ = H.run_hostsim(q)
+            hit = (got["status"] & 31) <= 1
+            t = (got["g"] - p.g_min) / (p.g_max - p.g_min) * p.n_bins
+            sel = hit & (t >= 0) & (t < p.n_bins)
+            da = 2.0 * q.rmax / q.nx
+            db = 2.0 * q.rmax * (q.ny / q.nx) / q.ny
+            h = np.bincount(t[sel].astype(int), weights=got["flux"][sel] * da * db, minlength=p.n_bins)
+            assert np.allclose(h, ref[js, ki], rtol=1e-9, atol=0.0)
