@@ -59,6 +59,7 @@ extern "C" {
 /* flags */
 #define SIM5_FLAG_DEVICE_PTRS   0x1  /* pointers in sim5_image_out are device pointers (no staging, no D2H) */
 #define SIM5_FLAG_NO_REFILL     0x2  /* debugging: disable warp-level lane refill / compaction */
+#define SIM5_FLAG_SINGLE_PASS    0x8  /* A/B testing: compute the azimuth inside the tracing kernel instead of the queued second phase */
 #define SIM5_FLAG_ASYNC         0x4  /* with DEVICE_PTRS: enqueue on the library stream (sim5_set_stream) and return without
                                         synchronising; stats are not filled.  Pair with sim5_synchronize(). */
 
@@ -207,6 +208,10 @@ int  sim5_trace_image(const sim5_image_params* p, const sim5_image_out* out, sim
 /* FP64 DFMA-chain microbenchmark: returns measured TFLOP/s (2 flop per DFMA) of the device, <0 on error.
  * This is the roofline denominator for the compute-bound FP64 path (MEASURED_PEAKS.json has no FP64 entry). */
 double sim5_fp64_peak_tflops(int device, int iters);
+
+/* development aid: kernel-only time in ms of `reps` calls per thread of one device routine over n threads
+ * (which: 0 rf, 1 rj, 2 rc, 3 sncndn, 4 sincos, 5 log, 6 atan2, 7 pow(.,1/3), 8 four divisions, 9 four sqrt, 10 complete rj) */
+double sim5_micro_bench(int which, int64_t n, int reps);
 
 /* batched element-wise access to the device functions (parity tests call these through the C-ABI).
  * Each mirrors one reference function; n elements, SoA arrays. */

@@ -12,7 +12,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsim5b200.so")
+LIB_PATH = os.environ.get("SIM5_B200_LIB") or os.path.join(_HERE, "libsim5b200.so")   # env override: kernel-variant A/B runs only
 
 _lib = None
 

@@ -21,6 +21,7 @@
 
 using s5::DevOut;
 using s5::DevStats;
+using s5::AzQueue;
 
 /* ------------------------------------------------------------------ */
 /* context                                                             */
@@ -55,6 +56,7 @@ struct Context {
     DevStats* h_stats = nullptr;          /* pinned */
     Plane planes[12];
     Plane hist;
+    Plane azq_f, azq_key;                 /* azimuth work-item queue (phase A -> phase B) */
     void* batch[8] = {nullptr};
     size_t batch_bytes[8] = {0};
     std::string last_error;
@@ -115,7 +117,7 @@ int ensure_init(int device)
     c.consts_cap = 1;
     CK(cudaHostAlloc((void**)&c.h_consts, sizeof(S5ImageConsts), cudaHostAllocDefault));
     CK(cudaMalloc((void**)&c.d_consts, sizeof(S5ImageConsts)));
-    CK(cudaMalloc((void**)&c.d_counter, sizeof(unsigned long long)));
+    CK(cudaMalloc((void**)&c.d_counter, 8 * sizeof(unsigned long long)));   /* [0..2] tile counters, [4..5] queue counts */
     CK(cudaMalloc((void**)&c.d_stats, sizeof(DevStats)));
     CK(cudaHostAlloc((void**)&c.h_stats, sizeof(DevStats), cudaHostAllocDefault));
     /* the stepper keeps ~100 doubles of live state per thread and calls non-inlined Carlson routines */
@@ -256,6 +258,8 @@ extern "C" void sim5_gpu_shutdown(void)
     cudaStreamSynchronize(c.stream);
     for (auto& pl : c.planes) { if (pl.p) cudaFree(pl.p); pl = Plane(); }
     if (c.hist.p) cudaFree(c.hist.p); c.hist = Plane();
+    if (c.azq_f.p) cudaFree(c.azq_f.p); c.azq_f = Plane();
+    if (c.azq_key.p) cudaFree(c.azq_key.p); c.azq_key = Plane();
     for (int i = 0; i < 8; i++) { if (c.batch[i]) cudaFree(c.batch[i]); c.batch[i] = nullptr; c.batch_bytes[i] = 0; }
     cudaFreeHost(c.h_scr); cudaFreeHost(c.h_consts); cudaFree(c.d_consts); cudaFree(c.d_counter); cudaFree(c.d_stats); cudaFreeHost(c.h_stats);
     cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1); cudaEventDestroy(c.ev2); cudaEventDestroy(c.ev3);
@@ -391,19 +395,41 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
 
     S5ImageConsts consts;                  /* travels by value as a kernel parameter: no H2D copy, async-safe */
     s5_fill_image_consts(p, &consts);
+    /* two-phase azimuth: phase A queues the disk hits, phase B integrates phi per geodesic type */
+    AzQueue q;
+    memset(&q, 0, sizeof q);
+    bool two_phase = (p->mode != SIM5_MODE_STEPWISE) && (p->outputs & SIM5_OUT_PHI) && !(p->flags & SIM5_FLAG_SINGLE_PASS) && npix > 0;
+    if (two_phase) {
+        rc = reserve(c.azq_f, npix * S5_AZ_NFIELDS * sizeof(double)); if (rc) return rc;
+        rc = reserve(c.azq_key, npix * sizeof(unsigned long long)); if (rc) return rc;
+        q.f = (double*)c.azq_f.p; q.key = (unsigned long long*)c.azq_key.p; q.count = c.d_counter + 4; q.cap = (long long)npix;
+    }
     CK(cudaEventRecord(c.ev0, c.stream));
-    CK(cudaMemsetAsync(c.d_counter, 0, sizeof(unsigned long long), c.stream));
+    CK(cudaMemsetAsync(c.d_counter, 0, 8 * sizeof(unsigned long long), c.stream));
     CK(cudaMemsetAsync(c.d_stats, 0, sizeof(DevStats), c.stream));
-    int grid = 0;
+    int grid = 0, launches = 0;
     CK(cudaEventRecord(c.ev1, c.stream));
     if (npix > 0) {
         if (p->mode == SIM5_MODE_STEPWISE) {
             grid = persistent_grid(s5::k_trace_stepwise, S5_CTA_THREADS);
             s5::k_trace_stepwise<<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d, c.d_counter, c.d_stats);
         } else {
-            grid = persistent_grid(s5::k_trace_eqplane, S5_CTA_THREADS);
-            s5::k_trace_eqplane<<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d, c.d_counter, c.d_stats);
+            if (two_phase) {
+                grid = persistent_grid(s5::k_trace_eqplane<true>, S5_CTA_THREADS);
+                s5::k_trace_eqplane<true><<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d, q, c.d_counter, c.d_stats);
+            } else {
+                grid = persistent_grid(s5::k_trace_eqplane<false>, S5_CTA_THREADS);
+                s5::k_trace_eqplane<false><<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d, q, c.d_counter, c.d_stats);
+            }
+            if (two_phase) {
+                int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_CTA_THREADS);
+                int g_rc = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RC>, S5_CTA_THREADS);
+                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_CTA_THREADS, 0, c.stream>>>(consts, q, d.phi, c.d_counter + 1);
+                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_CTA_THREADS, 0, c.stream>>>(consts, q, d.phi, c.d_counter + 2);
+                launches += 2;
+            }
         }
+        launches += 1;
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(c.ev2, c.stream));
@@ -436,7 +462,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         float ms = 0;
         cudaEventElapsedTime(&ms, c.ev1, c.ev2); stats->kernel_ms = ms;
         cudaEventElapsedTime(&ms, c.ev0, c.ev3); stats->total_ms = ms;
-        stats->kernel_launches = npix > 0 ? 1 : 0;
+        stats->kernel_launches = launches;
         stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = S5_CTA_THREADS;
     }
     return SIM5_OK;
@@ -464,6 +490,26 @@ extern "C" double sim5_fp64_peak_tflops(int device, int iters)
         double flops = (double)grid * 256.0 * (double)iters * 64.0 * 2.0;
         double tf = flops / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
+    }
+    return best;
+}
+
+/* kernel-only time (ms) of `reps` calls per thread of one device routine over n threads; <0 on error */
+extern "C" double sim5_micro_bench(int which, int64_t n, int reps)
+{
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (ensure_init(-1) != SIM5_OK) return -1.0;
+    Context& c = g_ctx;
+    n = (n + 127) / 128 * 128;
+    if (reserve(c.planes[0], (size_t)n * sizeof(double)) != SIM5_OK) return -1.0;
+    float best = 1e30f;
+    for (int it = 0; it < 3; it++) {
+        cudaEventRecord(c.ev0, c.stream);
+        s5::k_micro<<<(unsigned)(n / 128), 128, 0, c.stream>>>(which, reps, (double*)c.planes[0].p);
+        cudaEventRecord(c.ev1, c.stream);
+        if (!cuda_ok(cudaStreamSynchronize(c.stream), "micro bench")) return -1.0;
+        float ms = 0; cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+        if (ms < best) best = ms;
     }
     return best;
 }

@@ -33,6 +33,13 @@
 #define S5_NOINL __attribute__((noinline))
 #endif
 #define S5_CONST static constexpr
+/* mid-size routines (a few hundred instructions, several call sites): inlining them multiplies the kernel's code size
+ * and the instruction cache starts missing (ncu: stall_no_inst); S5_MID lets the build choose */
+#if defined(S5_MID_NOINLINE)
+#define S5_MID S5_NOINL
+#else
+#define S5_MID S5_INL
+#endif
 
 namespace crm {
 
@@ -458,7 +465,7 @@ S5_HD S5_INL double x87_to_double(dd v) { return add_(v.h, v.l); }
 
 /* The T-integral roots exactly as the CPU reference computes them (sim5kerr-geod.c:1124-1131):
  *   long double qla = q + l2 - a2;  X = sqrt(sqr(qla)+4.*q*a2) + qla;  m2m = X/(a2+a2);  m2p = (q+q)/X */
-S5_HD S5_INL void x87_mu_roots(double q, double l2, double a2, double* m2m, double* m2p)
+S5_HD S5_MID void x87_mu_roots(double q, double l2, double a2, double* m2m, double* m2p)
 {
     double qla = add_(add_(q, l2), -a2);
     dd sq = round_to_64(two_prod(qla, qla));            /* fmul in extended precision */

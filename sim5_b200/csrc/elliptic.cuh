@@ -160,14 +160,14 @@ S5_HD S5_INL double elliptic_k(double m)
 }
 
 /* F(phi,m) from sin(phi) and from cos(phi).  sim5elliptic.c:273-284, 254-271 */
-S5_HD S5_INL double elliptic_f_sin(double s, double m)
+S5_HD S5_MID double elliptic_f_sin(double s, double m)
 {
     if (m == 1.0) m = 0.99999999;
     if (s == 0.0) return 0.0;
     double s2 = sq(s);
     return s * rf(1. - s2, 1.0 - s2 * m, 1.0);
 }
-S5_HD S5_INL double elliptic_f_cos(double c, double m)
+S5_HD S5_MID double elliptic_f_cos(double c, double m)
 {
     if (m == 1.0) m = 0.99999999;
     if (c == 1.0) return 0.0;
@@ -221,7 +221,7 @@ S5_HD S5_INL double elliptic_e_sin(double s, double m)
 }
 
 /* complete Pi(n,m).  sim5elliptic.c:365-378 */
-S5_HD S5_INL double elliptic_pi_complete(double n, double m)
+S5_HD S5_MID double elliptic_pi_complete(double n, double m)
 {
     if (isinf(n)) return 0.0;
     if (m == 1.0) m = 0.99999999;
@@ -230,7 +230,7 @@ S5_HD S5_INL double elliptic_pi_complete(double n, double m)
     return rf(0.0, q, 1.0) + n * rj(0.0, q, 1.0, 1.0 - n) / 3.0;
 }
 /* Pi(phi,n,m) from cos(phi).  sim5elliptic.c:425-450 */
-S5_HD S5_INL double elliptic_pi_cos(double c, double n, double m)
+S5_HD S5_MID double elliptic_pi_cos(double c, double n, double m)
 {
     if (isinf(n)) return 0.0;
     if (c == 1.0) return 0.0;
@@ -247,6 +247,39 @@ S5_HD S5_INL double elliptic_pi_cos(double c, double n, double m)
     double q = 1.0 - (1.0 - c2) * m;
     return base + ((base == 0.0) ? (+1) : (-1)) * s * (rf(c2, q, 1.0) - ns2 * rj(c2, q, 1.0, 1.0 + ns2) / 3.0);
 }
+/* elliptic_pi_cos for several characteristics n at one (cos_phi, m): the R_F term rf(c^2, 1-(1-c^2)m, 1) does not
+ * depend on n, so it is evaluated once (or taken from a caller that already has it).  Same bits as elliptic_pi_cos. */
+struct PiShare { double c, m, c2, s, q, rfv; bool fast; };
+S5_HD S5_MID PiShare pi_share(double c, double m)
+{
+    PiShare sh;
+    sh.c = c; sh.m = m;
+    sh.fast = (c > 0.0) && (c != 1.0) && (m != 1.0);
+    sh.c2 = sq(c);
+    sh.s = sqrt(1.0 - sh.c2);
+    sh.q = 1.0 - (1.0 - sh.c2) * m;
+    sh.rfv = sh.fast ? rf(sh.c2, sh.q, 1.0) : 0.0;
+    return sh;
+}
+S5_HD S5_INL PiShare pi_share_with(double c, double m, double rfv)      /* rfv == rf(c^2, 1-(1-c^2)m, 1) already known */
+{
+    PiShare sh;
+    sh.c = c; sh.m = m;
+    sh.fast = (c > 0.0) && (c != 1.0) && (m != 1.0);
+    sh.c2 = sq(c);
+    sh.s = sqrt(1.0 - sh.c2);
+    sh.q = 1.0 - (1.0 - sh.c2) * m;
+    sh.rfv = rfv;
+    return sh;
+}
+S5_HD S5_MID double pi_cos_shared(const PiShare& sh, double n)
+{
+    if (!sh.fast) return elliptic_pi_cos(sh.c, n, sh.m);
+    if (isinf(n)) return 0.0;
+    double ns2 = -n * (1.0 - sh.c2);
+    return 0.0 + (+1) * sh.s * (sh.rfv - ns2 * rj(sh.c2, sh.q, 1.0, 1.0 + ns2) / 3.0);
+}
+
 /* Pi(phi,n,m) from sin(phi).  sim5elliptic.c:453-474 */
 S5_HD S5_INL double elliptic_pi_sin(double s, double n, double m)
 {
@@ -262,14 +295,17 @@ S5_HD S5_INL double elliptic_pi_sin(double s, double n, double m)
 }
 
 /* inverse Jacobi functions.  sim5elliptic.c:480-486, 492-514, 522-528 */
-S5_HD S5_INL double jacobi_isn(double z, double m)
+S5_HD S5_MID double jacobi_isn(double z, double m)
 {
     if (fabs(m - 0.0) < 1e-8) return cr_asin(z);
     if (fabs(m - 1.0) < 1e-8) return cr_log(sqrt((1. + z) / (1. - z)));
     return z * rf(1.0 - z * z, 1.0 - m * z * z, 1.0);
 }
-S5_HD S5_INL double jacobi_icn(double z, double m)
+/* jacobi_icn that also hands out its Carlson value rf(z^2, 1-m(1-z^2), 1) (rfv, valid when *have) so that
+ * callers needing the same R_F again (elliptic_pi_cos with the same modulus and cosine) can share it */
+S5_HD S5_MID double jacobi_icn_ex(double z, double m, double* rfv, double* z_used, double* m_used, bool* have)
 {
+    *have = false;
     if ((z > +1.0) && (z < +1.0 + 1e-8)) z = +1.0;
     if ((z < -1.0) && (z > -1.0 - 1e-8)) z = -1.0;
     if ((m > +1.0) && (m < +1.0 + 1e-8)) m = 1.0;
@@ -280,8 +316,15 @@ S5_HD S5_INL double jacobi_icn(double z, double m)
     if (m == 0.0) return cr_acos(z);
     if (m == 1.0) return cr_log((1. + sqrt(1. - z)) / z);
 
-    double v = sqrt(1. - z * z) * rf(z * z, 1.0 - m * (1. - z * z), 1.0);
+    double f = rf(z * z, 1.0 - m * (1. - z * z), 1.0);
+    *rfv = f; *z_used = z; *m_used = m; *have = true;
+    double v = sqrt(1. - z * z) * f;
     return (z > 0.0) ? v : 2. / sqrt(1. - m) * elliptic_f_sin(-z, m / (m - 1.)) + v;
+}
+S5_HD S5_INL double jacobi_icn(double z, double m)
+{
+    double f, zu, mu; bool have;
+    return jacobi_icn_ex(z, m, &f, &zu, &mu, &have);
 }
 S5_HD S5_INL double jacobi_itn(double z, double m)
 {
@@ -394,7 +437,7 @@ S5_HD S5_INL void catan_axis(double re, double im, double* ore, double* oim)
 }
 
 /* int du/(1+a cn u), B&F 341.03 / 361.54.  sim5elliptic.c:755-792 (complex arithmetic spelled out) */
-S5_HD S5_INL double integral_R1(double a, double u, double m)
+S5_HD S5_MID double integral_R1(double a, double u, double m)
 {
     double a2 = sq(a);
     double n = a2 / (a2 - 1.);
@@ -441,7 +484,7 @@ S5_HD S5_INL double integral_R_rp_re_inf(double a, double b, double c, double d,
     return -2.0 / sqrt((a - c) * (b - d)) / (p - a) * (integral_Z1(c2, a2, u1, m2) - integral_Z1_at0(c2, a2));
 }
 /* int_X1^inf dx/((x-p) sqrt((x-a)(x-b)(x-c)(x-c*))), c = u+iv, B&F 260.04.  sim5elliptic.c:1081-1112 */
-S5_HD S5_INL double integral_R_rp_cc2_inf(double a, double b, double cre, double cim, double p, double X1)
+S5_HD S5_MID double integral_R_rp_cc2_inf(double a, double b, double cre, double cim, double p, double X1)
 {
     double u = cre;
     double v2 = sq(cim);
@@ -458,7 +501,7 @@ S5_HD S5_INL double integral_R_rp_cc2_inf(double a, double b, double cre, double
     return (B - A) * g / (B * a + b * A - p * A - p * B) * (t0 + t1);
 }
 /* int_X^b dx/((p-x^2) sqrt((a^2+x^2)(b^2-x^2))), B&F 213.02.  sim5elliptic.c:1142-1159 */
-S5_HD S5_INL double integral_T_mp(double a2, double b2, double p, double X)
+S5_HD S5_MID double integral_T_mp(double a2, double b2, double p, double X)
 {
     double m = b2 / (a2 + b2);
     double n = b2 / (b2 - p);

@@ -62,7 +62,7 @@ S5_HD S5_INL int ensure_range(double* v, double lo, double hi, double acc)
 }
 
 /* roots of R(r), geodesic class, pericentre and R-integral to the pericentre.  sim5kerr-geod.c:985-1104 */
-S5_HD S5_INL int geodesic_R_roots(Geodesic* g, double r0, int* error)
+S5_HD S5_MID int geodesic_R_roots(Geodesic* g, double r0, int* error, double* isn_inf = nullptr)
 {
     double a = g->a, l = g->l, q = g->q;
     double a2 = sq(a), l2 = sq(l);
@@ -139,7 +139,11 @@ S5_HD S5_INL int geodesic_R_roots(Geodesic* g, double r0, int* error)
             r1 = g->r1.re; r2 = g->r2.re; r3 = g->r3.re; r4 = g->r4.re;
             mm = ((r2 - r3) * (r1 - r4)) / ((r2 - r4) * (r1 - r3));
             g->rp = r1;
-            g->Rpc = 2. / sqrt((r1 - r3) * (r2 - r4)) * jacobi_isn(sqrt((r2 - r4) / (r1 - r4)), mm);
+            {
+                double u = jacobi_isn(sqrt((r2 - r4) / (r1 - r4)), mm);
+                if (isn_inf) *isn_inf = u;          /* == the u1 of integral_R_rp_re_inf, sim5elliptic.c:1039-1040 */
+                g->Rpc = 2. / sqrt((r1 - r3) * (r2 - r4)) * u;
+            }
             break;
         case GEOD_TYPE_RR_BH:
             r1 = g->r1.re; r2 = g->r2.re; r3 = g->r3.re; r4 = g->r4.re;
@@ -170,7 +174,7 @@ S5_HD S5_INL int geodesic_R_roots(Geodesic* g, double r0, int* error)
 }
 
 /* roots of Theta(mu).  sim5kerr-geod.c:1109-1184 (CPU branch: extended-precision m2m, m2p) */
-S5_HD S5_INL int geodesic_T_roots(Geodesic* g, double m, int* error)
+S5_HD S5_MID int geodesic_T_roots(Geodesic* g, double m, int* error)
 {
     double a = g->a, l = g->l, q = g->q;
     double a2 = sq(a), l2 = sq(l);
@@ -234,7 +238,7 @@ S5_HD S5_INL int geodesic_init_inf(double i, double a, double alpha, double beta
 }
 
 /* r -> P.  sim5kerr-geod.c:178-263 */
-S5_HD S5_INL double geodesic_P_int(const Geodesic* g, double r, int ppc)
+S5_HD S5_MID double geodesic_P_int(const Geodesic* g, double r, int ppc)
 {
     double r1, r2, r3, r4, u, v, mm, R, A, B;
     if (r == g->rp) return g->Rpc;
@@ -272,7 +276,7 @@ S5_HD S5_INL double geodesic_P_int(const Geodesic* g, double r, int ppc)
 }
 
 /* P -> r.  sim5kerr-geod.c:290-357 */
-S5_HD S5_INL double geodesic_position_rad(const Geodesic* g, double P)
+S5_HD S5_MID double geodesic_position_rad(const Geodesic* g, double P)
 {
     if ((P <= 0.0) || (P >= 2. * g->Rpc)) return NAN;
     if (P == g->Rpc) return g->rp;

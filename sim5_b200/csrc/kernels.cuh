@@ -35,7 +35,25 @@ struct DevStats {                 /* device-side counters, flushed once per CTA 
     unsigned long long rays;
 };
 
+/* queue of azimuth work items between phase A (k_trace_eqplane) and phase B (k_azimuth): SoA, RR items from the
+ * front, RC items from the back of the same arrays, so each phase-B launch sees one geodesic type only */
+struct AzQueue {
+    double* f;                    /* [S5_AZ_NFIELDS][cap] */
+    unsigned long long* key;      /* [cap]: bits 0..47 output index, bits 48..51 nrr, bit 56 rf_ok */
+    unsigned long long* count;    /* [0] RR items, [1] RC items */
+    long long cap;                /* 0: no queue -> the azimuth is computed inline by phase A */
+};
+
 #define S5_CTA_THREADS 128
+#ifndef S5_MIN_CTAS_EQ
+#define S5_MIN_CTAS_EQ 1          /* resident CTAs per SM the eq-plane kernel is compiled for (register cap = 65536/(128*n)) */
+#endif
+#ifndef S5_MIN_CTAS_STEP
+#define S5_MIN_CTAS_STEP 1
+#endif
+#ifndef S5_MIN_CTAS_AZ
+#define S5_MIN_CTAS_AZ 1
+#endif
 
 __device__ __forceinline__ void stage_consts(S5ImageConsts* dst, const S5ImageConsts* src)
 {
@@ -73,8 +91,9 @@ __device__ __forceinline__ void flush_stats(const unsigned int* s_cnt, unsigned 
 /* ------------------------------------------------------------------ */
 /* modes EQPLANE / POLARIZED : analytic geodesic per pixel             */
 /* ------------------------------------------------------------------ */
-__global__ void __launch_bounds__(S5_CTA_THREADS)
-k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
+template <bool DEFER>
+__global__ void __launch_bounds__(S5_CTA_THREADS, S5_MIN_CTAS_EQ)
+k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQueue q, unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
 {
     __shared__ S5ImageConsts c;
     __shared__ unsigned int s_cnt[40];
@@ -92,19 +111,88 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsig
         t = __shfl_sync(0xffffffffu, t, 0);
         if ((long long)t >= ntiles) break;
         long long p = ((long long)t << 5) + lane;
+        AzIn z;
+        bool deferred = false;
+        size_t i = 0;
         if (p < npix) {
             int lr = (int)(p / nx);
             int ix = (int)(p - (long long)lr * nx);
             int iy = s5_local_to_image_row(&c, lr);
             PixelOut o;
-            trace_eqplane_pixel(c, ix, iy, &o);
-            size_t i = out.compact ? (size_t)p : (size_t)iy * (size_t)nx + (size_t)ix;
+            deferred = trace_eqplane_pixel_t<DEFER>(c, ix, iy, &o, &z);
+            i = out.compact ? (size_t)p : (size_t)iy * (size_t)nx + (size_t)ix;
             store_pixel(out, c.outputs, i, o);
             atomicAdd(&s_cnt[o.status & 31], 1u);
             atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);
         }
+        if (DEFER) {
+            /* hand the azimuth of this tile's hits to phase B: one aggregated atomic per warp and geodesic type */
+            bool is_rr = deferred && z.type == GEOD_TYPE_RR;
+            bool is_rc = deferred && z.type == GEOD_TYPE_RC;
+            unsigned m_rr = __ballot_sync(0xffffffffu, is_rr);
+            unsigned m_rc = __ballot_sync(0xffffffffu, is_rc);
+            long long slot = -1;
+            if (m_rr) {
+                int leader = __ffs(m_rr) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(&q.count[0], (unsigned long long)__popc(m_rr));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (is_rr) slot = (long long)base + __popc(m_rr & ((1u << lane) - 1u));
+            }
+            if (m_rc) {
+                int leader = __ffs(m_rc) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(&q.count[1], (unsigned long long)__popc(m_rc));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (is_rc) slot = q.cap - 1 - ((long long)base + __popc(m_rc & ((1u << lane) - 1u)));
+            }
+            if (slot >= 0) {
+                double* f = q.f + slot;
+                const long long cap = q.cap;
+                f[0 * cap] = z.e0;  f[1 * cap] = z.e1;  f[2 * cap] = z.e2;   f[3 * cap] = z.e3;
+                f[4 * cap] = z.l;   f[5 * cap] = z.m2m; f[6 * cap] = z.m2p;  f[7 * cap] = z.mm;
+                f[8 * cap] = z.Tpp; f[9 * cap] = z.Tip; f[10 * cap] = z.Rpc; f[11 * cap] = z.beta;
+                f[12 * cap] = z.K_mm; f[13 * cap] = z.rf_u; f[14 * cap] = z.isn_inf; f[15 * cap] = z.r; f[16 * cap] = z.P;
+                q.key[slot] = (unsigned long long)i | ((unsigned long long)(z.nrr & 15) << 48) | ((unsigned long long)(z.rf_ok ? 1 : 0) << 56);
+            }
+        }
     }
     flush_stats(s_cnt, 0, gstats);
+}
+
+/* phase B: azimuth of the queued disk hits of ONE geodesic type (TYPE = GEOD_TYPE_RR or GEOD_TYPE_RC) */
+template <int TYPE>
+__global__ void __launch_bounds__(S5_CTA_THREADS, S5_MIN_CTAS_AZ)
+k_azimuth(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double* __restrict__ phi, unsigned long long* __restrict__ tile_counter)
+{
+    const int lane = threadIdx.x & 31;
+    const long long count = (long long)q.count[TYPE == GEOD_TYPE_RR ? 0 : 1];
+    const long long ntiles = (count + 31) >> 5;
+    const long long cap = q.cap;
+    const double a_eff = fmax(1e-4, gconsts.a);
+    const double cos_i = gconsts.cos_i;
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1ULL);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((long long)t >= ntiles) break;
+        long long it = ((long long)t << 5) + lane;
+        if (it < count) {
+            long long slot = (TYPE == GEOD_TYPE_RR) ? it : cap - 1 - it;
+            const double* f = q.f + slot;
+            AzIn z;
+            z.e0 = f[0 * cap];  z.e1 = f[1 * cap];  z.e2 = f[2 * cap];   z.e3 = f[3 * cap];
+            z.l = f[4 * cap];   z.m2m = f[5 * cap]; z.m2p = f[6 * cap];  z.mm = f[7 * cap];
+            z.Tpp = f[8 * cap]; z.Tip = f[9 * cap]; z.Rpc = f[10 * cap]; z.beta = f[11 * cap];
+            z.K_mm = f[12 * cap]; z.rf_u = f[13 * cap]; z.isn_inf = f[14 * cap]; z.r = f[15 * cap]; z.P = f[16 * cap];
+            unsigned long long key = q.key[slot];
+            z.a = a_eff; z.cos_i = cos_i;
+            z.type = TYPE;
+            z.nrr = (int)((key >> 48) & 15);
+            z.rf_ok = ((key >> 56) & 1) != 0;
+            phi[key & 0xffffffffffffULL] = azimuth_from(z);
+        }
+    }
 }
 
 /* ------------------------------------------------------------------ */
@@ -113,7 +201,7 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsig
 #define S5_STEPS_PER_ROUND 16
 #define S5_REFILL_MIN 4
 
-__global__ void __launch_bounds__(S5_CTA_THREADS)
+__global__ void __launch_bounds__(S5_CTA_THREADS, S5_MIN_CTAS_STEP)
 k_trace_stepwise(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigned long long* __restrict__ ray_counter, DevStats* __restrict__ gstats)
 {
     __shared__ S5ImageConsts c;
@@ -199,7 +287,7 @@ k_trace_stepwise(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsi
 /* ------------------------------------------------------------------ */
 /* mode HISTOGRAM : g-factor transfer function over a (spin, incl) lattice */
 /* ------------------------------------------------------------------ */
-__global__ void __launch_bounds__(S5_CTA_THREADS)
+__global__ void __launch_bounds__(S5_CTA_THREADS, S5_MIN_CTAS_EQ)
 k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice image */, int img_begin, int img_end,
                   double* __restrict__ hist, unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
 {
@@ -285,6 +373,36 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
     }
     double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 12345.678) out[0] = s;      /* keep the chains alive */
+}
+
+/* micro-benchmark of one device routine in isolation (arguments generated in registers, one store per thread):
+ * the ceiling a routine reaches without the rest of the pixel pipeline around it */
+__global__ void __launch_bounds__(128) k_micro(int which, int reps, double* out)
+{
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    /* cheap per-thread arguments in the ranges the azimuth path uses */
+    double u = (double)((i * 2654435761ULL) & 0xfffff) * (1.0 / 1048576.0);      /* [0,1) */
+    double v = (double)((i * 40503ULL + 12345ULL) & 0xfffff) * (1.0 / 1048576.0);
+    double c2 = 0.05 + 0.9 * u, m = 0.1 + 0.8 * v;
+    double acc = 0.0;
+    for (int r = 0; r < reps; r++) {
+        double q = 1.0 - (1.0 - c2) * m;
+        switch (which) {
+            case 0: acc += rf(c2, q, 1.0); break;
+            case 1: acc += rj(c2, q, 1.0, 1.0 + 0.7 * (1.0 - c2)); break;
+            case 2: acc += rc(c2, q); break;
+            case 3: { double sn, cn, dn; jacobi_sncndn(1.5 * u, m, &sn, &cn, &dn); acc += sn + cn + dn; break; }
+            case 4: { double sn, cn; crm::cr_sincos(3.0 * u, &sn, &cn); acc += sn + cn; break; }
+            case 5: acc += crm::cr_log(0.5 + 4.0 * u); break;
+            case 6: acc += crm::cr_atan2(u - 0.5, v - 0.3); break;
+            case 7: acc += crm::cr_pow_third(0.1 + 100.0 * u); break;
+            case 8: acc += (1.0 + u) / (1.0 + v) + (2.0 + u) / (3.0 + v) + (0.5 + v) / (1.5 + u) + (4.0 + v) / (1.1 + u); break;   /* 4 independent divisions */
+            case 9: acc += sqrt(1.0 + u) + sqrt(2.0 + v) + sqrt(0.5 + u) + sqrt(3.0 + v); break;                                   /* 4 independent square roots */
+            case 10: acc += rj(0.0, 1.0 - m, 1.0, 1.0 + 0.3 * u); break;
+        }
+        c2 += 1e-6; m += 1e-7; u += 1e-6; v += 1e-6;
+    }
+    out[i] = acc;
 }
 
 /* ------------------------------------------------------------------ */

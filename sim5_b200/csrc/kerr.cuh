@@ -64,7 +64,7 @@ struct Conn {
     double g301, g302, g313, g323;
 };
 /* sim5kerr.c:232-316 */
-S5_HD S5_INL void kerr_connection(double a, double r, double m, Conn* G)
+S5_HD S5_MID void kerr_connection(double a, double r, double m, Conn* G)
 {
     double rS = 2.0 * r;
     double s = sqrt(1. - m * m);
@@ -259,7 +259,7 @@ S5_HD S5_INL double Omega_from_ell(double ell, const Metric* g) { return -(g->g0
 /* sim5kerr.c:1114-1124 */
 S5_HD S5_INL double ell_from_Omega(double Omega, const Metric* g) { return -(g->g03 + g->g33 * Omega) / (g->g00 + g->g03 * Omega); }
 /* sim5kerr.c:1127-1141 */
-S5_HD S5_INL double gfactorK(double r, double a, double l)
+S5_HD S5_MID double gfactorK(double r, double a, double l)
 {
     double Om = 1. / (a + crm::cr_pow_1p5(r));
     return sqrt(1. - 2. / r * sq(1. - a * Om) - (r * r + a * a) * sq(Om)) / (1. - Om * l);

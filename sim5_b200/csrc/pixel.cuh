@@ -46,7 +46,7 @@ S5_HD S5_INL void pixel_impact(const S5ImageConsts& c, int ix, int iy, double* a
 }
 
 /* Page-Thorne flux with the per-image pieces hoisted.  sim5disk-nt.c:109-146 */
-S5_HD S5_INL double disk_nt_flux(const S5ImageConsts& c, double r)
+S5_HD S5_MID double disk_nt_flux(const S5ImageConsts& c, double r)
 {
     if (r <= c.nt_rms) return 0.0;
     double x = sqrt(r);
@@ -69,9 +69,19 @@ S5_HD S5_INL double chandra_delta(const double* tab, double mue)
     return tab[i0] + (tab[i0 + 1] - tab[i0]) * w;
 }
 
-/* geodesic_init_inf with the two T-integrals' Carlson values kept for the crossings.
- * Same results as geodesic_init_inf_sc (geod.cuh); K_mm = K(mm), icn_u = cn^-1(cos_i/sqrt(m2p), mm). */
-S5_HD S5_INL int init_inf_cached(const S5ImageConsts& c, double alpha, double beta, Geodesic* g, int* error, double* K_mm, double* icn_u)
+/* per-ray values that the reference recomputes several times (identical inputs -> identical bits) */
+struct RayCache {
+    double K_mm;        /* K(mm) = rf(0, 1-mm, 1): Tpp, every crossing order, complete Pi in the azimuth */
+    double icn_u;       /* cn^-1(cos_i/sqrt(m2p), mm): Tip and every crossing order */
+    double rf_u;        /* the R_F inside icn_u; equals the R_F of elliptic_pi_cos(cos_i/sqrt(m2p), ., mm) */
+    double rf_u_z, rf_u_m;
+    double isn_inf;     /* sn^-1 at r = infinity (RR rays): Rpc and both integral_R_rp_re_inf calls */
+    bool have_rf_u;
+};
+
+/* geodesic_init_inf with the T-integrals' Carlson values kept for the crossings and the azimuth.
+ * Same results as geodesic_init_inf_sc (geod.cuh). */
+S5_HD S5_INL int init_inf_cached(const S5ImageConsts& c, double alpha, double beta, Geodesic* g, int* error, RayCache* k)
 {
     double a = c.a, i = c.incl;
     if ((a < 0.0) || (a > 1. - 1e-6)) { *error = GD_ERROR_SPIN_RANGE; return 0; }
@@ -85,34 +95,166 @@ S5_HD S5_INL int init_inf_cached(const S5ImageConsts& c, double alpha, double be
     g->l = -alpha * c.sin_i;
     g->q = sq(beta) + sq(c.cos_i) * (sq(alpha) - sq(a));
     if (g->q == 0.0) { *error = GD_ERROR_Q_RANGE; return 0; }
-    if (!geodesic_R_roots(g, 1.7976931348623157e308, error)) return 0;
+    k->isn_inf = 0.0;
+    if (!geodesic_R_roots(g, 1.7976931348623157e308, error, &k->isn_inf)) return 0;
     if (!geodesic_T_roots(g, g->cos_i, error)) return 0;
     /* theta_int(0) == mK*K(mm): jacobi_icn(0/sqrt(m2p), mm) takes its z == 0 exit (0 <= mm < 1 here) */
-    *K_mm = elliptic_k(g->mm);
-    *icn_u = jacobi_icn(g->cos_i / sqrt(g->m2p), g->mm);
-    g->Tpp = 2. * (g->mK * (*K_mm));
-    g->Tip = g->mK * (*icn_u);
+    k->K_mm = elliptic_k(g->mm);
+    k->icn_u = jacobi_icn_ex(g->cos_i / sqrt(g->m2p), g->mm, &k->rf_u, &k->rf_u_z, &k->rf_u_m, &k->have_rf_u);
+    g->Tpp = 2. * (g->mK * k->K_mm);
+    g->Tip = g->mK * k->icn_u;
     *error = GD_OK;
     return 1;
 }
 /* geodesic_find_midplane_crossing on the cached values.  sim5kerr-geod.c:845-885 */
-S5_HD S5_INL double crossing_cached(const Geodesic* g, int order, double K_mm, double icn_u)
+S5_HD S5_INL double crossing_cached(const Geodesic* g, int order, const RayCache& k)
 {
     if (g->q <= 0.0) return NAN;
     double u = g->cos_i / sqrt(g->m2p);
     double u0 = u;
     if (!ensure_range(&u, -1.0, +1.0, 1e-4)) return NAN;
-    double icn = (u == u0) ? icn_u : jacobi_icn(u, g->mm);
+    double icn = (u == u0) ? k.icn_u : jacobi_icn(u, g->mm);
     double pos;
-    if (g->beta > 0.0)      pos = g->mK * ((2. * (double)order + 1.) * K_mm + icn);
-    else if (g->beta < 0.0) pos = g->mK * ((2. * (double)order + 1.) * K_mm - icn);
-    else                    pos = g->mK * ((2. * (double)order + 1.) * K_mm);
+    if (g->beta > 0.0)      pos = g->mK * ((2. * (double)order + 1.) * k.K_mm + icn);
+    else if (g->beta < 0.0) pos = g->mK * ((2. * (double)order + 1.) * k.K_mm - icn);
+    else                    pos = g->mK * ((2. * (double)order + 1.) * k.K_mm);
     if (pos > 2. * g->Rpc) pos = NAN;
     return pos;
 }
 
+/* Everything the azimuth of an equatorial disk hit needs from its geodesic (17 doubles + flags).  The image
+ * kernels run the azimuth as a SECOND PHASE over a queue of these items (kernels.cuh): phase A (roots, crossing,
+ * radius, g, flux) and phase B (3 rf + 6 rj + 2 sncndn) each fit the instruction cache and run at higher
+ * occupancy than one fused kernel, and phase B is free of RR/RC divergence. */
+struct AzIn {
+    double e0, e1, e2, e3;      /* RR: r1..r4 (real) ; RC: r1, r2, Re r3, Im r3 */
+    double l, m2m, m2p, mm, Tpp, Tip, Rpc, beta;
+    double K_mm, rf_u, isn_inf;
+    double r, P;
+    double a, cos_i;            /* per-image: the clamped spin g->a and cos(i) */
+    int type, nrr;
+    bool rf_ok;                 /* rf_u is the R_F of elliptic_pi_cos(cos_i/sqrt(m2p), ., m2p/(m2m+m2p)) */
+};
+#define S5_AZ_NFIELDS 17
+
+S5_HD S5_INL void az_make(const Geodesic* g, const RayCache& k, double r, double P, AzIn* z)
+{
+    if (g->type == GEOD_TYPE_RR) { z->e0 = g->r1.re; z->e1 = g->r2.re; z->e2 = g->r3.re; z->e3 = g->r4.re; }
+    else                          { z->e0 = g->r1.re; z->e1 = g->r2.re; z->e2 = g->r3.re; z->e3 = g->r3.im; }
+    z->l = g->l; z->m2m = g->m2m; z->m2p = g->m2p; z->mm = g->mm; z->Tpp = g->Tpp; z->Tip = g->Tip; z->Rpc = g->Rpc; z->beta = g->beta;
+    z->K_mm = k.K_mm; z->rf_u = k.rf_u; z->isn_inf = k.isn_inf;
+    z->r = r; z->P = P; z->a = g->a; z->cos_i = g->cos_i;
+    z->type = g->type; z->nrr = g->nrr;
+    double tm = g->m2p / (g->m2m + g->m2p);
+    z->rf_ok = k.have_rf_u && (k.rf_u_z == g->cos_i / sqrt(g->m2p)) && (k.rf_u_m == tm);
+}
+
+/* geodesic_position_azm(g, r, m = 0, P) for an equatorial hit, without the reference's repeated Carlson calls
+ * (sim5kerr-geod.c:462-555 -> sim5elliptic.c:1017-1044, 676-690, 425-450, 1142-1159):
+ *   - both poles (r+, r-) share sn^-1, sn/cn/dn and the R_F term of Pi at each of the two limits (infinity, r);
+ *   - sn^-1 at infinity is the value already behind Rpc; integral_Z1(u=0) is a signed zero;
+ *   - K(mm) and the R_F behind Tip serve the polar integrals; phi_mp(m=0) is the same call as phi_pp/2.
+ * 3 rf + 6 rj + 2 sncndn instead of ~14 rf + 7 rj + 4 sncndn (reference: ~33 rf incl. its argument checks), same bits. */
+S5_HD S5_MID double azimuth_from(const AzIn& z)
+{
+    double phi = 0.0;
+    int ppc = (z.nrr > 0) && (z.P > z.Rpc);
+    double a2 = sq(z.a);
+    double rp = 1. + sqrt(1. - a2);
+    double rm = 1. - sqrt(1. - a2);
+    double A, B;
+    const double r = z.r;
+
+    if (z.type == GEOD_TYPE_RR) {
+        double a = z.e0, b = z.e1, c = z.e2, d = z.e3;
+        double m2 = ((b - c) * (a - d)) / ((a - c) * (b - d));
+        double pre = -2.0 / sqrt((a - c) * (b - d));
+        double aa2 = (a - d) / (b - d);
+        double sn_, dn_, cn_inf, cn_r;
+        double u_inf = z.isn_inf;
+        jacobi_sncndn(u_inf, m2, &sn_, &cn_inf, &dn_);
+        PiShare sh_inf = pi_share(cn_inf, m2);
+        double u_r = jacobi_isn(sqrt(((b - d) * (r - a)) / ((a - d) * (r - b))), m2);
+        jacobi_sncndn(u_r, m2, &sn_, &cn_r, &dn_);
+        PiShare sh_r = pi_share(cn_r, m2);
+        {
+            double p = rp;
+            double c2 = ((p - b) * (a - d)) / ((p - a) * (b - d));
+            double z0 = integral_Z1_at0(c2, aa2);
+            double Rinf = pre / (p - a) * (1. / c2 * ((c2 - aa2) * pi_cos_shared(sh_inf, c2) + aa2 * u_inf) - z0);
+            double Rr   = pre / (p - a) * (1. / c2 * ((c2 - aa2) * pi_cos_shared(sh_r, c2) + aa2 * u_r) - z0);
+            A = Rinf + (ppc ? +1 : -1) * Rr;
+        }
+        {
+            double p = rm;
+            double c2 = ((p - b) * (a - d)) / ((p - a) * (b - d));
+            double z0 = integral_Z1_at0(c2, aa2);
+            double Rinf = pre / (p - a) * (1. / c2 * ((c2 - aa2) * pi_cos_shared(sh_inf, c2) + aa2 * u_inf) - z0);
+            double Rr   = pre / (p - a) * (1. / c2 * ((c2 - aa2) * pi_cos_shared(sh_r, c2) + aa2 * u_r) - z0);
+            B = Rinf + (ppc ? +1 : -1) * Rr;
+        }
+        phi += 1. / sqrt(1. - a2) * (A * (z.a * rp - z.l * a2 / 2.) - B * (z.a * rm - z.l * a2 / 2.));
+    } else if (z.type == GEOD_TYPE_RC) {
+        A = integral_R_rp_cc2_inf(z.e0, z.e1, z.e2, z.e3, rp, r);
+        B = integral_R_rp_cc2_inf(z.e0, z.e1, z.e2, z.e3, rm, r);
+        phi += 1. / sqrt(1. - a2) * (A * (z.a * rp - z.l * a2 / 2.) - B * (z.a * rm - z.l * a2 / 2.));
+    } else {
+        return NAN;
+    }
+
+    /* polar part: integral_T_mp(m2m, m2p, 1.0, X) for X = 0 (twice) and X = cos_i */
+    double tm = z.m2p / (z.m2m + z.m2p);
+    double tn = z.m2p / (z.m2p - 1.0);
+    double tpre = 1. / sqrt(z.m2m + z.m2p) / (1.0 - z.m2p);
+    double comp;                                     /* elliptic_pi_cos(0, n, m) -> elliptic_pi_complete(n, m) */
+    if (isinf(tn)) {
+        comp = 0.0;
+    } else {
+        double mc = (tm == 1.0) ? 0.99999999 : tm;
+        double nc = (tn == 1.0) ? 0.99999999 : tn;
+        double q = 1.0 - mc;
+        double rfK = (tm == z.mm && tm != 1.0) ? z.K_mm : rf(0.0, q, 1.0);
+        comp = rfK + nc * rj(0.0, q, 1.0, 1.0 - nc) / 3.0;
+    }
+    double T0 = tpre * comp;
+    double phi_pp = 2.0 * z.l / z.a * T0;
+    double phi_mp = z.l / z.a * T0;
+    double phi_ip;
+    if (z.cos_i >= 0.0) {
+        double cu = z.cos_i / sqrt(z.m2p);
+        PiShare sh = z.rf_ok ? pi_share_with(cu, tm, z.rf_u) : pi_share(cu, tm);
+        double v = (cu == 0.0 && !isinf(tn)) ? comp : pi_cos_shared(sh, tn);
+        phi_ip = z.l / z.a * (tpre * v);
+    } else {
+        phi_ip = z.l / z.a * integral_T_mp(z.m2m, z.m2p, 1.0, z.cos_i);
+    }
+
+    double T;
+    double sign_dm = (z.beta >= 0.0) ? +1.0 : -1.0;
+    if (sign_dm > 0.0) {
+        T = -(z.Tpp - z.Tip);
+        phi -= phi_pp - phi_ip;
+    } else {
+        T = -z.Tip;
+        phi -= phi_ip;
+    }
+    if (z.P >= T + z.Tpp) {
+        T += z.Tpp;
+        phi += phi_pp;
+        sign_dm = -sign_dm;
+    }
+    phi += (sign_dm < 0) ? phi_mp : phi_pp - phi_mp;
+    return phi;
+}
+S5_HD S5_INL double azimuth_equatorial(const Geodesic* g, const RayCache& k, double r, double P)
+{
+    AzIn z;
+    az_make(g, k, r, P, &z);
+    return azimuth_from(z);
+}
+
 /* emission-side quantities of the polarized mode for a disk hit at (r, m=0), position parameter P */
-S5_HD S5_INL void polarized_hit(const S5ImageConsts& c, const Geodesic* gd, double r, double P, PixelOut* o)
+S5_HD S5_MID void polarized_hit(const S5ImageConsts& c, const Geodesic* gd, double r, double P, PixelOut* o)
 {
     double a = c.a;
     double k[4], U[4], N[4], kl[4], fl[4], f[4];
@@ -141,7 +283,10 @@ S5_HD S5_INL void polarized_hit(const S5ImageConsts& c, const Geodesic* gd, doub
 }
 
 /* modes EQPLANE and POLARIZED */
-S5_HD S5_INL void trace_eqplane_pixel(const S5ImageConsts& c, int ix, int iy, PixelOut* o)
+/* DEFER: when the azimuth is requested, a hit fills *defer (returns true) instead of computing phi here
+ * (the instantiation then carries no azimuth code at all) */
+template <bool DEFER>
+S5_HD S5_INL bool trace_eqplane_pixel_t(const S5ImageConsts& c, int ix, int iy, PixelOut* o, AzIn* defer)
 {
     double alpha, beta;
     pixel_impact(c, ix, iy, &alpha, &beta);
@@ -150,25 +295,33 @@ S5_HD S5_INL void trace_eqplane_pixel(const S5ImageConsts& c, int ix, int iy, Pi
 
     Geodesic gd;
     int error = 0;
-    double K_mm = 0.0, icn_u = 0.0;
+    RayCache k;
     gd.type = -1;
-    if (!init_inf_cached(c, alpha, beta, &gd, &error, &K_mm, &icn_u)) {
+    if (!init_inf_cached(c, alpha, beta, &gd, &error, &k)) {
         int gt = (error == GD_ERROR_TYPE_RR_DOUBLE) ? gtype_code(gd.type) : SIM5_GT_NONE;
         o->status = (unsigned)((SIM5_ST_INITERR + error) | (gt << 5));
-        return;
+        return false;
     }
     unsigned gt = (unsigned)gtype_code(gd.type) << 5;
     for (int order = 0; order <= c.max_order; order++) {
-        double P = crossing_cached(&gd, order, K_mm, icn_u);
+        double P = crossing_cached(&gd, order, k);
         if (isnan(P)) {
             o->status = (order == 0 ? SIM5_ST_NOCROSS0 : order == 1 ? SIM5_ST_NOCROSS1 : SIM5_ST_NOCROSS2) | gt;
-            return;
+            return false;
         }
         double r = geodesic_position_rad(&gd, P);
         if (r >= c.rmin_emit) {
+            bool deferred = false;
             o->status = (order == 0 ? SIM5_ST_HIT0 : order == 1 ? SIM5_ST_HIT1 : SIM5_ST_HIT2) | gt;
             o->r = r;
-            if (c.outputs & SIM5_OUT_PHI) o->phi = geodesic_position_azm(&gd, r, 0.0, P);
+            if (c.outputs & SIM5_OUT_PHI) {
+                if (DEFER) {
+                    if (gd.type == GEOD_TYPE_RR || gd.type == GEOD_TYPE_RC) { az_make(&gd, k, r, P, defer); deferred = true; }
+                    else o->phi = NAN;               /* geodesic_position_azm returns NaN for the other types */
+                } else {
+                    o->phi = azimuth_equatorial(&gd, k, r, P);
+                }
+            }
             if (c.mode == SIM5_MODE_POLARIZED) {
                 polarized_hit(c, &gd, r, P, o);
             } else {
@@ -177,10 +330,15 @@ S5_HD S5_INL void trace_eqplane_pixel(const S5ImageConsts& c, int ix, int iy, Pi
                 o->g = g;
                 o->flux = f * crm::cr_pow_4(g);
             }
-            return;
+            return deferred;
         }
     }
     o->status = SIM5_ST_MISS | gt;
+    return false;
+}
+S5_HD S5_INL void trace_eqplane_pixel(const S5ImageConsts& c, int ix, int iy, PixelOut* o)
+{
+    trace_eqplane_pixel_t<false>(c, ix, iy, o, nullptr);
 }
 
 /* mode STEPWISE: raytrace() through the harness torus (SURVEY.md 8d cfg 4; oracle/ref_driver.c pixel_stepwise) */

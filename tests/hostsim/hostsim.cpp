@@ -51,6 +51,35 @@ int hs_geodesic_init_inf(double i, double a, double alpha, double beta, void* g,
     return geodesic_init_inf(i, a, alpha, beta, (Geodesic*)g, error);
 }
 
+// fused azimuth (pixel.cuh azimuth_equatorial) vs the call-for-call port of geodesic_position_azm (geod.cuh) on every
+// hit pixel of an image: returns the number of pixels where the two differ in any bit (must be 0)
+long hs_azimuth_mismatches(const sim5_image_params* p)
+{
+    S5ImageConsts c;
+    s5_fill_image_consts(p, &c);
+    long bad = 0;
+    #pragma omp parallel for schedule(dynamic, 4) reduction(+:bad)
+    for (int iy = 0; iy < c.ny; iy++) {
+        for (int ix = 0; ix < c.nx; ix++) {
+            double alpha, beta;
+            pixel_impact(c, ix, iy, &alpha, &beta);
+            Geodesic gd; int err = 0; RayCache k;
+            if (!init_inf_cached(c, alpha, beta, &gd, &err, &k)) continue;
+            for (int order = 0; order <= 1; order++) {
+                double P = crossing_cached(&gd, order, k);
+                if (isnan(P)) break;
+                double r = geodesic_position_rad(&gd, P);
+                if (!(r >= c.rmin_emit)) continue;
+                double a = azimuth_equatorial(&gd, k, r, P);
+                double b = geodesic_position_azm(&gd, r, 0.0, P);
+                if (memcmp(&a, &b, 8) != 0 && !(a != a && b != b)) bad++;
+                break;
+            }
+        }
+    }
+    return bad;
+}
+
 double hs_trace_image(const sim5_image_params* p, const sim5_image_out* out, int nthreads)
 {
     S5ImageConsts c;

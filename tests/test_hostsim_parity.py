@@ -114,3 +114,16 @@ def test_histogram_against_golden():
             db = 2.0 * q.rmax * (q.ny / q.nx) / q.ny
             h = np.bincount(t[sel].astype(int), weights=got["flux"][sel] * da * db, minlength=p.n_bins)
             assert np.allclose(h, ref[js, ki], rtol=1e-9, atol=0.0)
+
+
+def test_fused_azimuth_equals_call_for_call_port():
+    """The kernels' azimuth (3 rf + 6 rj + 2 sncndn per ray) must equal, bit for bit, the call-for-call port of
+    geodesic_position_azm (~27 rf + 7 rj + 8 sncndn) that the golden/reference comparisons pin."""
+    hs = H.load_hostsim()
+    hs.hs_azimuth_mismatches.restype = C.c_long
+    hs.hs_azimuth_mismatches.argtypes = [C.POINTER(abi.ImageParams)]
+    for cfg, n in ((2, 192), (3, 128), (1, 128)):
+        p = abi.default_params(cfg, n)
+        assert hs.hs_azimuth_mismatches(C.byref(p)) == 0
+    p = abi.default_params(2, 96); p.incl = abi.deg2rad(20.0); p.bh_spin = 0.3
+    assert hs.hs_azimuth_mismatches(C.byref(p)) == 0

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""A/B timing of kernel build variants (sim5_b200/variants/*.so): kernel ms of the main workloads + a golden check."""
+import glob, os, subprocess, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD = r'''
+import os, sys, json
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import numpy as np
+import harness as H
+from sim5_b200 import abi, api
+api.init(0)
+res = {}
+p = abi.default_params(2, 64); got, _ = api.trace_image(p)
+try:
+    H.assert_image_parity(got.arrays, H.golden("image_cfg2_64.npz"), "golden"); res["golden"] = "ok"
+except AssertionError as e:
+    res["golden"] = str(e)
+def t(p, reps=3):
+    planes = api.HostPlanes(p)
+    best = 1e30
+    for _ in range(reps):
+        _, st = api.trace_image(p, planes); best = min(best, st.kernel_ms)
+    return best, st
+p = abi.default_params(2); ms, st = t(p); res["cfg2_phi_ms"] = round(ms,3); res["cfg2_phi_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
+p = abi.default_params(2); p.outputs = abi.OUT_R|abi.OUT_G|abi.OUT_FLUX|abi.OUT_STATUS; ms, st = t(p); res["cfg2_nophi_ms"] = round(ms,3); res["cfg2_nophi_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
+p = abi.default_params(3); ms, st = t(p); res["cfg3_ms"] = round(ms,3); res["cfg3_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
+p = abi.default_params(4, 512); ms, st = t(p, 1); res["cfg4_512_ms"] = round(ms,2); res["cfg4_steps_s"] = "%%.3e" %% (st.total_steps/ms*1e3)
+if os.environ.get("SWEEP_NOREFILL"):
+    p.flags = abi.FLAG_NO_REFILL; ms, st = t(p, 1); res["cfg4_512_norefill_ms"] = round(ms,2)
+print(json.dumps(res))
+''' % (ROOT, ROOT)
+libs = sorted(glob.glob(os.path.join(ROOT, "sim5_b200", "variants", "*.so"))) or [os.path.join(ROOT, "sim5_b200", "libsim5b200.so")]
+for lib in libs:
+    env = dict(os.environ, SIM5_B200_LIB=lib)
+    r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
+    line = r.stdout.strip().split("\n")[-1] if r.stdout.strip() else r.stderr[-400:]
+    print(os.path.basename(lib), line, flush=True)
