@@ -46,13 +46,13 @@ struct AzQueue {
 
 #define S5_CTA_THREADS 128
 #ifndef S5_MIN_CTAS_EQ
-#define S5_MIN_CTAS_EQ 1          /* resident CTAs per SM the eq-plane kernel is compiled for (register cap = 65536/(128*n)) */
+#define S5_MIN_CTAS_EQ 4          /* resident CTAs per SM the eq-plane kernel is compiled for (register cap = 65536/(128*n)); r01c sweep: 4 is the knee */
 #endif
 #ifndef S5_MIN_CTAS_STEP
 #define S5_MIN_CTAS_STEP 1
 #endif
 #ifndef S5_MIN_CTAS_AZ
-#define S5_MIN_CTAS_AZ 1
+#define S5_MIN_CTAS_AZ 4
 #endif
 
 __device__ __forceinline__ void stage_consts(S5ImageConsts* dst, const S5ImageConsts* src)

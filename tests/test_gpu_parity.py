@@ -27,7 +27,7 @@ def test_images_against_golden(gpu_api, fname, cfg, nx, ny, extra):
     if "class_count" in g:
         assert list(st.class_count) == list(g["class_count"])
         assert list(st.gtype_count) == list(g["gtype_count"])
-    assert st.kernel_launches == 1 and st.rays == nx * ny
+    assert st.kernel_launches >= 1 and st.rays == nx * ny
 
 
 @pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref did not travel")
