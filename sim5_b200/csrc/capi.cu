@@ -422,10 +422,10 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                 s5::k_trace_eqplane<false><<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d, q, c.d_counter, c.d_stats);
             }
             if (two_phase) {
-                int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_CTA_THREADS);
-                int g_rc = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RC>, S5_CTA_THREADS);
-                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_CTA_THREADS, 0, c.stream>>>(consts, q, d.phi, c.d_counter + 1);
-                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_CTA_THREADS, 0, c.stream>>>(consts, q, d.phi, c.d_counter + 2);
+                int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_AZ_THREADS);
+                int g_rc = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RC>, S5_AZ_THREADS);
+                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(consts, q, d.phi, c.d_counter + 1);
+                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(consts, q, d.phi, c.d_counter + 2);
                 launches += 2;
             }
         }

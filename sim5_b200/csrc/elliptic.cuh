@@ -12,6 +12,7 @@
 #define SIM5_ELLIPTIC_CUH
 
 #include "crmath.cuh"
+#include "fastfp.cuh"
 
 namespace s5 {
 
@@ -27,8 +28,9 @@ S5_HD S5_INL double max3(double a, double b, double c) { return fmax(fmax(a, b),
 
 #define S5_CARLSON_TOL 0.0003
 
+/* ---- plain-operator versions: the reference spelling with `/` and sqrt(); the fallback of the fast versions below ---- */
 /* R_F(x,y,z), duplication theorem with the 5th-order series tail.  sim5elliptic.c:18-52 */
-S5_HD S5_NOINL double rf(double x, double y, double z)
+S5_HD S5_NOINL double rf_plain(double x, double y, double z)
 {
     constexpr double THIRD = 1.0 / 3.0;
     constexpr double K1 = 1.0 / 24.0, K2 = 0.1, K3 = 3.0 / 44.0, K4 = 1.0 / 14.0;
@@ -75,7 +77,7 @@ S5_HD S5_NOINL double rd(double x, double y, double z)
 }
 
 /* R_C(x,y), Cauchy principal value for y < 0.  sim5elliptic.c:104-137 */
-S5_HD S5_NOINL double rc(double x, double y)
+S5_HD S5_NOINL double rc_plain(double x, double y)
 {
     constexpr double THIRD = 1.0 / 3.0, K1 = 0.3, K2 = 1.0 / 7.0, K3 = 0.375, K4 = 9.0 / 22.0;
     double pre, mu, s;
@@ -99,7 +101,7 @@ S5_HD S5_NOINL double rc(double x, double y)
 
 /* R_J(x,y,z,p), principal value for p < 0; returns 0 on out-of-range arguments like the reference.
  * sim5elliptic.c:144-206 */
-S5_HD S5_NOINL double rj(double x, double y, double z, double p)
+S5_HD S5_NOINL double rj_plain(double x, double y, double z, double p)
 {
     constexpr double K1 = 3.0 / 14.0, K2 = 1.0 / 3.0, K3 = 3.0 / 22.0, K4 = 3.0 / 26.0,
                      K5 = 0.75 * K3, K6 = 1.5 * K4, K7 = 0.5 * K2, K8 = K3 + K3;
@@ -121,7 +123,7 @@ S5_HD S5_NOINL double rj(double x, double y, double z, double p)
         pt = yt + cb;
         double rho = xt * zt / yt;
         double tau = p * pt / yt;
-        rcx = rc(rho, tau);
+        rcx = rc_plain(rho, tau);
     }
     double mu, dx, dy, dz, dp;
     do {
@@ -129,7 +131,7 @@ S5_HD S5_NOINL double rj(double x, double y, double z, double p)
         double lam = sx * (sy + sz) + sy * sz;
         double al = sq(pt * (sx + sy + sz) + sx * sy * sz);
         double be = pt * sq(pt + lam);
-        acc += w * rc(al, be);
+        acc += w * rc_plain(al, be);
         w = 0.25 * w;
         xt = 0.25 * (xt + lam);
         yt = 0.25 * (yt + lam);
@@ -148,9 +150,273 @@ S5_HD S5_NOINL double rj(double x, double y, double z, double p)
     double ee = eb + 2.0 * dp * (ea - ec);
     double res = 3.0 * acc + w * (1.0 + ed * (-K1 + K5 * ed - K6 * ee) + eb * (K7 + dp * (-K8 + dp * K4))
         + dp * ea * (K2 - dp * K3) - K2 * dp * ec) / (mu * sqrt(mu));
-    if (p <= 0.0) res = ca * (cb * res + 3.0 * (rcx - rf(xt, yt, zt)));
+    if (p <= 0.0) res = ca * (cb * res + 3.0 * (rcx - rf_plain(xt, yt, zt)));
     return res;
 }
+
+
+/* ---- fast versions (what the kernels call): the same arithmetic, operation for operation, on the branch-free
+ * division / square root of fastfp.cuh; quotients by a common divisor share one refined reciprocal.
+ *
+ * Domain: the fast bodies run only when every argument is zero-or-within [2^-100, 2^100) (R_C: [2^-320, 2^320)), which
+ * the entry test establishes with one integer compare per argument.  Inside that domain every operand of every
+ * sqrt/division of the duplication loops is a positive normal number far from the exponent limits (the iterates stay
+ * between min and max of the arguments; numerators mu-x are exact zeros or >= one ulp of a number >= 2^-322), so the
+ * unchecked primitives are exact replacements of the operators.  Anything else (negative p aside, which has its own
+ * prologue) takes the plain version.  tests: test_gpu_parity.py::test_carlson_fast_vs_plain. ---- */
+#if defined(S5_NO_FASTFP)
+S5_HD S5_INL double rf(double x, double y, double z) { return rf_plain(x, y, z); }
+S5_HD S5_INL double rc(double x, double y) { return rc_plain(x, y); }
+S5_HD S5_INL double rj(double x, double y, double z, double p) { return rj_plain(x, y, z, p); }
+#else
+S5_HD S5_INL bool above_tol(double d) { return fabs(d) > S5_CARLSON_TOL; }
+#define S5_EXP_MID 100          /* exponent window of the fast R_F / R_J bodies */
+#define S5_EXP_WIDE 320         /* ... of R_C (it receives squares and cubes of R_J's iterates) */
+
+/* R_F body: x zero-or-mid, y and z mid */
+S5_HD S5_INL double rf_core(double x, double y, double z)
+{
+    constexpr double THIRD = 1.0 / 3.0;
+    constexpr double K1 = 1.0 / 24.0, K2 = 0.1, K3 = 3.0 / 44.0, K4 = 1.0 / 14.0;
+    double mu, dx, dy, dz;
+    double sx = ff::fsqrt0_nc(x), sy = ff::fsqrt_nc(y), sz = ff::fsqrt_nc(z);
+    for (;;) {
+        double lam = sx * (sy + sz) + sy * sz;
+        x = 0.25 * (x + lam);
+        y = 0.25 * (y + lam);
+        z = 0.25 * (z + lam);
+        mu = THIRD * (x + y + z);
+        ff::Rcp rmu = ff::rcp_of(mu);
+        dx = ff::fdiv_nc(mu - x, rmu);
+        dy = ff::fdiv_nc(mu - y, rmu);
+        dz = ff::fdiv_nc(mu - z, rmu);
+        if (!(above_tol(dx) || above_tol(dy) || above_tol(dz))) break;     /* == !(max3(|dx|,|dy|,|dz|) > tol) */
+        sx = ff::fsqrt_nc(x); sy = ff::fsqrt_nc(y); sz = ff::fsqrt_nc(z);
+    }
+    double e2 = dx * dy - dz * dz;
+    double e3 = dx * dy * dz;
+    return ff::fdiv_nc(1.0 + (K1 * e2 - K2 - K3 * e3) * e2 + K4 * e3, ff::fsqrt_nc(mu));
+}
+S5_HD S5_INL bool rf_fast_domain(double x, double y, double z)
+{
+    return ff::zero_or_pos_within<S5_EXP_MID>(x) && ff::pos_within<S5_EXP_MID>(y) && ff::pos_within<S5_EXP_MID>(z);
+}
+S5_HD S5_NOINL double rf(double x, double y, double z)
+{
+    if (!rf_fast_domain(x, y, z)) return rf_plain(x, y, z);
+    return rf_core(x, y, z);
+}
+
+/* R_C body for y > 0: x zero-or-wide, y wide.  sx_known > 0: the caller knows sqrt(x) exactly
+ * (x = RN(v*v) => sqrt(x) = |v| for every binary64 v whose square is a normal number) */
+S5_HD S5_INL double rc_pos_core(double x, double y, double sx_known = 0.0)
+{
+    constexpr double THIRD = 1.0 / 3.0, K1 = 0.3, K2 = 1.0 / 7.0, K3 = 0.375, K4 = 9.0 / 22.0;
+    double mu, s;
+    double sx = (sx_known > 0.0) ? sx_known : ff::fsqrt0_nc(x);
+    double sy = ff::fsqrt_nc(y);
+    for (;;) {
+        double lam = 2.0 * sx * sy + y;
+        x = 0.25 * (x + lam);
+        y = 0.25 * (y + lam);
+        mu = THIRD * (x + y + y);
+        s = ff::fdiv_nc(y - mu, mu);
+        if (!above_tol(s)) break;
+        sx = ff::fsqrt_nc(x); sy = ff::fsqrt_nc(y);
+    }
+    return ff::fdiv_nc(1.0 * (1.0 + s * s * (K1 + s * (K2 + s * (K3 + s * K4)))), ff::fsqrt_nc(mu));
+}
+/* R_C body for y < 0 (Cauchy principal value): x zero-or-wide, -y wide */
+S5_HD S5_INL double rc_neg_core(double x, double y)
+{
+    constexpr double THIRD = 1.0 / 3.0, K1 = 0.3, K2 = 1.0 / 7.0, K3 = 0.375, K4 = 9.0 / 22.0;
+    double mu, s;
+    double xs = x - y;
+    double sx = ff::fsqrt_nc(xs);
+    double pre = ff::fdiv_nc(ff::fsqrt0_nc(x), sx);
+    x = xs;
+    y = -y;
+    double sy = ff::fsqrt_nc(y);
+    for (;;) {
+        double lam = 2.0 * sx * sy + y;
+        x = 0.25 * (x + lam);
+        y = 0.25 * (y + lam);
+        mu = THIRD * (x + y + y);
+        s = ff::fdiv_nc(y - mu, mu);
+        if (!above_tol(s)) break;
+        sx = ff::fsqrt_nc(x); sy = ff::fsqrt_nc(y);
+    }
+    return ff::fdiv_nc(pre * (1.0 + s * s * (K1 + s * (K2 + s * (K3 + s * K4)))), ff::fsqrt_nc(mu));
+}
+S5_HD S5_NOINL double rc(double x, double y)
+{
+    if (ff::zero_or_pos_within<S5_EXP_WIDE>(x)) {
+        if (ff::pos_within<S5_EXP_WIDE>(y)) return rc_pos_core(x, y);
+        if (ff::pos_within<S5_EXP_WIDE>(-y)) return rc_neg_core(x, y);
+    }
+    return rc_plain(x, y);
+}
+
+/* tail of R_J after convergence.  sim5elliptic.c:197-203 */
+S5_HD S5_INL double rj_tail(double acc, double w, double mu, double dx, double dy, double dz, double dp)
+{
+    constexpr double K1 = 3.0 / 14.0, K2 = 1.0 / 3.0, K3 = 3.0 / 22.0, K4 = 3.0 / 26.0,
+                     K5 = 0.75 * K3, K6 = 1.5 * K4, K7 = 0.5 * K2, K8 = K3 + K3;
+    double ea = dx * (dy + dz) + dy * dz;
+    double eb = dx * dy * dz;
+    double ec = dp * dp;
+    double ed = ea - 3.0 * ec;
+    double ee = eb + 2.0 * dp * (ea - ec);
+    return 3.0 * acc + ff::fdiv_nc(w * (1.0 + ed * (-K1 + K5 * ed - K6 * ee) + eb * (K7 + dp * (-K8 + dp * K4))
+        + dp * ea * (K2 - dp * K3) - K2 * dp * ec), mu * ff::fsqrt_nc(mu));
+}
+
+/* R_F(x,y,z) (if WANT_RF) and R_J(x,y,z,p_k), k < NJ, over ONE duplication sequence: sqrt(x), sqrt(y), sqrt(z), lambda,
+ * the sums and the x,y,z updates do not depend on p, so the elliptic_pi_cos pairs of the azimuth (both poles r+ and r-
+ * at the same amplitude, plus the R_F of the same amplitude) pay for them once.  Each function keeps its own
+ * convergence test and leaves the loop at the iteration the stand-alone routine would.  x zero-or-mid; y, z, p_k mid. */
+template <int NJ, bool WANT_RF>
+S5_HD S5_INL void rfj_shared_core(double x, double y, double z, const double* p, double* rf_out, double* rj_out)
+{
+    constexpr double THIRD = 1.0 / 3.0;
+    constexpr double F1 = 1.0 / 24.0, F2 = 0.1, F3 = 3.0 / 44.0, F4 = 1.0 / 14.0;
+    double pt[NJ], acc[NJ];
+    bool jdone[NJ];
+    #pragma unroll
+    for (int k = 0; k < NJ; k++) { pt[k] = p[k]; acc[k] = 0.0; jdone[k] = false; }
+    bool fdone = !WANT_RF;
+    double w = 1.0;
+    double sx = ff::fsqrt0_nc(x), sy = ff::fsqrt_nc(y), sz = ff::fsqrt_nc(z);
+    for (;;) {
+        double lam = sx * (sy + sz) + sy * sz;
+        double ssum = sx + sy + sz;
+        double sprod = sx * sy * sz;
+        #pragma unroll
+        for (int k = 0; k < NJ; k++) {
+            if (!jdone[k]) {
+                double v = pt[k] * ssum + sprod;
+                double al = sq(v);
+                double be = pt[k] * sq(pt[k] + lam);
+                acc[k] += w * rc_pos_core(al, be, fabs(v));
+                pt[k] = 0.25 * (pt[k] + lam);
+            }
+        }
+        w = 0.25 * w;
+        x = 0.25 * (x + lam);
+        y = 0.25 * (y + lam);
+        z = 0.25 * (z + lam);
+        double s3 = x + y + z;
+        if (WANT_RF && !fdone) {
+            double mu = THIRD * s3;
+            ff::Rcp rmu = ff::rcp_of(mu);
+            double dx = ff::fdiv_nc(mu - x, rmu), dy = ff::fdiv_nc(mu - y, rmu), dz = ff::fdiv_nc(mu - z, rmu);
+            if (!(above_tol(dx) || above_tol(dy) || above_tol(dz))) {
+                double e2 = dx * dy - dz * dz;
+                double e3 = dx * dy * dz;
+                *rf_out = ff::fdiv_nc(1.0 + (F1 * e2 - F2 - F3 * e3) * e2 + F4 * e3, ff::fsqrt_nc(mu));
+                fdone = true;
+            }
+        }
+        bool all = fdone;
+        #pragma unroll
+        for (int k = 0; k < NJ; k++) {
+            if (!jdone[k]) {
+                double mu = 0.2 * (s3 + pt[k] + pt[k]);
+                ff::Rcp rmu = ff::rcp_of(mu);
+                double dx = ff::fdiv_nc(mu - x, rmu), dy = ff::fdiv_nc(mu - y, rmu), dz = ff::fdiv_nc(mu - z, rmu), dp = ff::fdiv_nc(mu - pt[k], rmu);
+                if (!(above_tol(dx) || above_tol(dy) || above_tol(dz) || above_tol(dp))) {
+                    rj_out[k] = rj_tail(acc[k], w, mu, dx, dy, dz, dp);
+                    jdone[k] = true;
+                }
+            }
+            all = all && jdone[k];
+        }
+        if (all) break;
+        sx = ff::fsqrt_nc(x); sy = ff::fsqrt_nc(y); sz = ff::fsqrt_nc(z);
+    }
+}
+
+S5_HD S5_INL bool rj_args_bad(double x, double y, double z, double p)
+{
+    /* pow(5.0*DBL_MIN,1./3.) and 0.3*pow(0.1*DBL_MAX,1./3.) */
+    const double LO = 0x1.13c484138708ep-340, HI = 0x1.674da50c1a606p+338;
+    return (fmin(fmin(x, y), z) < 0.0) || (fmin(fmin(x + y, x + z), fmin(y + z, fabs(p))) < LO) ||
+           (fmax(fmax(x, y), fmax(z, fabs(p))) > HI);
+}
+/* R_J, p < 0 (principal value): the prologue/epilogue of sim5elliptic.c:166-177, 204 around the shared body */
+S5_HD S5_INL double rj_neg_core(double x, double y, double z, double p)
+{
+    double xt = fmin(fmin(x, y), z);
+    double zt = fmax(fmax(x, y), z);
+    double yt = x + y + z - xt - zt;
+    double ca = ff::fdiv_nc(1.0, yt - p);
+    double cb = ca * (zt - yt) * (yt - xt);
+    double pt = yt + cb;
+    ff::Rcp ryt = ff::rcp_of(yt);
+    double rho = ff::fdiv_nc(xt * zt, ryt);
+    double tau = ff::fdiv_nc(p * pt, ryt);
+    double rcx = rc_neg_core(rho, tau);
+    /* body: identical to the p > 0 loop; the final x,y,z are also needed for the R_F term */
+    constexpr double THIRD = 1.0 / 3.0;
+    (void)THIRD;
+    double acc = 0.0, w = 1.0, mu, dx, dy, dz, dp;
+    double sx = ff::fsqrt0_nc(xt), sy = ff::fsqrt_nc(yt), sz = ff::fsqrt_nc(zt);
+    for (;;) {
+        double lam = sx * (sy + sz) + sy * sz;
+        double v = pt * (sx + sy + sz) + sx * sy * sz;
+        double al = sq(v);
+        double be = pt * sq(pt + lam);
+        acc += w * rc_pos_core(al, be, fabs(v));
+        w = 0.25 * w;
+        xt = 0.25 * (xt + lam);
+        yt = 0.25 * (yt + lam);
+        zt = 0.25 * (zt + lam);
+        pt = 0.25 * (pt + lam);
+        mu = 0.2 * (xt + yt + zt + pt + pt);
+        ff::Rcp rmu = ff::rcp_of(mu);
+        dx = ff::fdiv_nc(mu - xt, rmu); dy = ff::fdiv_nc(mu - yt, rmu); dz = ff::fdiv_nc(mu - zt, rmu); dp = ff::fdiv_nc(mu - pt, rmu);
+        if (!(above_tol(dx) || above_tol(dy) || above_tol(dz) || above_tol(dp))) break;
+        sx = ff::fsqrt_nc(xt); sy = ff::fsqrt_nc(yt); sz = ff::fsqrt_nc(zt);
+    }
+    double res = rj_tail(acc, w, mu, dx, dy, dz, dp);
+    return ca * (cb * res + 3.0 * (rcx - rf_core(xt, yt, zt)));
+}
+S5_HD S5_INL bool rj_fast_domain(double x, double y, double z, double p)
+{
+    return ff::zero_or_pos_within<S5_EXP_MID>(x) && ff::pos_within<S5_EXP_MID>(y) && ff::pos_within<S5_EXP_MID>(z) && ff::pos_within<S5_EXP_MID>(p);
+}
+S5_HD S5_NOINL double rj(double x, double y, double z, double p)
+{
+    if (rj_fast_domain(x, y, z, p)) {             /* implies the reference's argument test passes */
+        double v;
+        rfj_shared_core<1, false>(x, y, z, &p, nullptr, &v);
+        return v;
+    }
+    if (rj_args_bad(x, y, z, p)) return 0.0;
+    /* p < 0 with x,y,z,|p| in range and the sorted middle/largest strictly positive and distinct from a zero smallest */
+    if (p < 0.0 && ff::pos_within<S5_EXP_MID>(-p) && ff::zero_or_pos_within<S5_EXP_MID>(x) && ff::zero_or_pos_within<S5_EXP_MID>(y) && ff::zero_or_pos_within<S5_EXP_MID>(z)
+        && ((x > 0.0) + (y > 0.0) + (z > 0.0) >= 2)) {
+        double xt = fmin(fmin(x, y), z), zt = fmax(fmax(x, y), z);
+        double yt = x + y + z - xt - zt;
+        double pt = yt + ff::fdiv_nc(1.0, yt - p) * (zt - yt) * (yt - xt);
+        if (ff::pos_within<S5_EXP_MID>(yt) && ff::pos_within<S5_EXP_MID>(pt)) return rj_neg_core(x, y, z, p);
+    }
+    return rj_plain(x, y, z, p);
+}
+/* R_F(x,y,z), R_J(x,y,z,p1), R_J(x,y,z,p2) -- bit-identical to the three stand-alone calls */
+S5_HD S5_NOINL void rf_rj2(double x, double y, double z, double p1, double p2, double* f, double* j1, double* j2)
+{
+    if (rj_fast_domain(x, y, z, p1) && ff::pos_within<S5_EXP_MID>(p2)) {
+        double p[2] = {p1, p2}, j[2];
+        rfj_shared_core<2, true>(x, y, z, p, f, j);
+        *j1 = j[0]; *j2 = j[1];
+        return;
+    }
+    *f = rf(x, y, z);
+    *j1 = rj(x, y, z, p1);
+    *j2 = rj(x, y, z, p2);
+}
+#endif
 
 /* K(m).  sim5elliptic.c:217-225 */
 S5_HD S5_INL double elliptic_k(double m)
@@ -278,6 +544,26 @@ S5_HD S5_MID double pi_cos_shared(const PiShare& sh, double n)
     if (isinf(n)) return 0.0;
     double ns2 = -n * (1.0 - sh.c2);
     return 0.0 + (+1) * sh.s * (sh.rfv - ns2 * rj(sh.c2, sh.q, 1.0, 1.0 + ns2) / 3.0);
+}
+
+/* elliptic_pi_cos(c, n1, m) and elliptic_pi_cos(c, n2, m): one amplitude, two characteristics (the two poles r+ and r- of
+ * the azimuth integrand).  The R_F term and the x,y,z duplication sequence of both R_J are shared (rf_rj2). */
+S5_HD S5_MID void pi_cos_pair(double c, double m, double n1, double n2, double* P1, double* P2)
+{
+    bool fast = (c > 0.0) && (c != 1.0) && (m != 1.0) && !isinf(n1) && !isinf(n2);
+    if (!fast) { *P1 = elliptic_pi_cos(c, n1, m); *P2 = elliptic_pi_cos(c, n2, m); return; }
+    double c2 = sq(c);
+    double s = sqrt(1.0 - c2);
+    double q = 1.0 - (1.0 - c2) * m;
+    double ns1 = -n1 * (1.0 - c2), ns2 = -n2 * (1.0 - c2);
+    double f, j1, j2;
+#if defined(S5_NO_FASTFP)
+    f = rf(c2, q, 1.0); j1 = rj(c2, q, 1.0, 1.0 + ns1); j2 = rj(c2, q, 1.0, 1.0 + ns2);
+#else
+    rf_rj2(c2, q, 1.0, 1.0 + ns1, 1.0 + ns2, &f, &j1, &j2);
+#endif
+    *P1 = 0.0 + (+1) * s * (f - ns1 * j1 / 3.0);
+    *P2 = 0.0 + (+1) * s * (f - ns2 * j2 / 3.0);
 }
 
 /* Pi(phi,n,m) from sin(phi).  sim5elliptic.c:453-474 */

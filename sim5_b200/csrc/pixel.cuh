@@ -155,7 +155,15 @@ S5_HD S5_INL void az_make(const Geodesic* g, const RayCache& k, double r, double
  *   - sn^-1 at infinity is the value already behind Rpc; integral_Z1(u=0) is a signed zero;
  *   - K(mm) and the R_F behind Tip serve the polar integrals; phi_mp(m=0) is the same call as phi_pp/2.
  * 3 rf + 6 rj + 2 sncndn instead of ~14 rf + 7 rj + 4 sncndn (reference: ~33 rf incl. its argument checks), same bits. */
-S5_HD S5_MID double azimuth_from(const AzIn& z)
+#if defined(__CUDA_ARCH__)
+#define S5_STAGE_SYNC() do { if (SYNC) __syncthreads(); } while (0)
+#else
+#define S5_STAGE_SYNC() do { } while (0)
+#endif
+/* SYNC: the caller is a CTA whose threads ALL run this routine on items of ONE geodesic type; the barriers between
+ * the stages keep its warps inside the same routine (the same instruction-cache lines) at the same time */
+template <bool SYNC>
+S5_HD S5_MID double azimuth_from_t(const AzIn& z)
 {
     double phi = 0.0;
     int ppc = (z.nrr > 0) && (z.P > z.Rpc);
@@ -173,24 +181,31 @@ S5_HD S5_MID double azimuth_from(const AzIn& z)
         double sn_, dn_, cn_inf, cn_r;
         double u_inf = z.isn_inf;
         jacobi_sncndn(u_inf, m2, &sn_, &cn_inf, &dn_);
-        PiShare sh_inf = pi_share(cn_inf, m2);
         double u_r = jacobi_isn(sqrt(((b - d) * (r - a)) / ((a - d) * (r - b))), m2);
+        S5_STAGE_SYNC();
         jacobi_sncndn(u_r, m2, &sn_, &cn_r, &dn_);
-        PiShare sh_r = pi_share(cn_r, m2);
+        double c2p = ((rp - b) * (a - d)) / ((rp - a) * (b - d));
+        double c2m = ((rm - b) * (a - d)) / ((rm - a) * (b - d));
+        double Pinf_p, Pinf_m, Pr_p, Pr_m;
+        S5_STAGE_SYNC();
+        pi_cos_pair(cn_inf, m2, c2p, c2m, &Pinf_p, &Pinf_m);
+        S5_STAGE_SYNC();
+        pi_cos_pair(cn_r, m2, c2p, c2m, &Pr_p, &Pr_m);
+        S5_STAGE_SYNC();
         {
             double p = rp;
-            double c2 = ((p - b) * (a - d)) / ((p - a) * (b - d));
+            double c2 = c2p;
             double z0 = integral_Z1_at0(c2, aa2);
-            double Rinf = pre / (p - a) * (1. / c2 * ((c2 - aa2) * pi_cos_shared(sh_inf, c2) + aa2 * u_inf) - z0);
-            double Rr   = pre / (p - a) * (1. / c2 * ((c2 - aa2) * pi_cos_shared(sh_r, c2) + aa2 * u_r) - z0);
+            double Rinf = pre / (p - a) * (1. / c2 * ((c2 - aa2) * Pinf_p + aa2 * u_inf) - z0);
+            double Rr   = pre / (p - a) * (1. / c2 * ((c2 - aa2) * Pr_p + aa2 * u_r) - z0);
             A = Rinf + (ppc ? +1 : -1) * Rr;
         }
         {
             double p = rm;
-            double c2 = ((p - b) * (a - d)) / ((p - a) * (b - d));
+            double c2 = c2m;
             double z0 = integral_Z1_at0(c2, aa2);
-            double Rinf = pre / (p - a) * (1. / c2 * ((c2 - aa2) * pi_cos_shared(sh_inf, c2) + aa2 * u_inf) - z0);
-            double Rr   = pre / (p - a) * (1. / c2 * ((c2 - aa2) * pi_cos_shared(sh_r, c2) + aa2 * u_r) - z0);
+            double Rinf = pre / (p - a) * (1. / c2 * ((c2 - aa2) * Pinf_m + aa2 * u_inf) - z0);
+            double Rr   = pre / (p - a) * (1. / c2 * ((c2 - aa2) * Pr_m + aa2 * u_r) - z0);
             B = Rinf + (ppc ? +1 : -1) * Rr;
         }
         phi += 1. / sqrt(1. - a2) * (A * (z.a * rp - z.l * a2 / 2.) - B * (z.a * rm - z.l * a2 / 2.));
@@ -216,6 +231,7 @@ S5_HD S5_MID double azimuth_from(const AzIn& z)
         double rfK = (tm == z.mm && tm != 1.0) ? z.K_mm : rf(0.0, q, 1.0);
         comp = rfK + nc * rj(0.0, q, 1.0, 1.0 - nc) / 3.0;
     }
+    S5_STAGE_SYNC();
     double T0 = tpre * comp;
     double phi_pp = 2.0 * z.l / z.a * T0;
     double phi_mp = z.l / z.a * T0;
@@ -246,6 +262,7 @@ S5_HD S5_MID double azimuth_from(const AzIn& z)
     phi += (sign_dm < 0) ? phi_mp : phi_pp - phi_mp;
     return phi;
 }
+S5_HD S5_INL double azimuth_from(const AzIn& z) { return azimuth_from_t<false>(z); }
 S5_HD S5_INL double azimuth_equatorial(const Geodesic* g, const RayCache& k, double r, double P)
 {
     AzIn z;
