@@ -28,6 +28,24 @@ S5_HD S5_INL double max3(double a, double b, double c) { return fmax(fmax(a, b),
 
 #define S5_CARLSON_TOL 0.0003
 
+/* Carlson series constants as a constant-bank table: a 64-bit literal costs two UMOV per use in SASS (the kernels are
+ * instruction-issue bound), a c[bank][offset] operand costs nothing.  Same values as the literals of the plain versions. */
+#define S5_KC_INIT { 1.0 / 3.0, 0.0003, 0.2, \
+    1.0 / 24.0, 0.1, 3.0 / 44.0, 1.0 / 14.0, \
+    0.3, 1.0 / 7.0, 0.375, 9.0 / 22.0, \
+    3.0 / 14.0, 1.0 / 3.0, 3.0 / 22.0, 3.0 / 26.0, 0.75 * (3.0 / 22.0), 1.5 * (3.0 / 26.0), 0.5 * (1.0 / 3.0), (3.0 / 22.0) + (3.0 / 22.0) }
+enum { KC_THIRD = 0, KC_TOL, KC_FIFTH, KC_F1, KC_F2, KC_F3, KC_F4, KC_C1, KC_C2, KC_C3, KC_C4,
+       KC_J1, KC_J2, KC_J3, KC_J4, KC_J5, KC_J6, KC_J7, KC_J8, KC_COUNT };
+static const double s5_kc_host[KC_COUNT] = S5_KC_INIT;
+#if defined(__CUDACC__)
+static __constant__ double s5_kc_dev[KC_COUNT] = S5_KC_INIT;
+#endif
+#if defined(__CUDA_ARCH__)
+#define S5KC(i) s5_kc_dev[i]
+#else
+#define S5KC(i) s5_kc_host[i]
+#endif
+
 /* ---- plain-operator versions: the reference spelling with `/` and sqrt(); the fallback of the fast versions below ---- */
 /* R_F(x,y,z), duplication theorem with the 5th-order series tail.  sim5elliptic.c:18-52 */
 S5_HD S5_NOINL double rf_plain(double x, double y, double z)
@@ -169,15 +187,15 @@ S5_HD S5_INL double rf(double x, double y, double z) { return rf_plain(x, y, z);
 S5_HD S5_INL double rc(double x, double y) { return rc_plain(x, y); }
 S5_HD S5_INL double rj(double x, double y, double z, double p) { return rj_plain(x, y, z, p); }
 #else
-S5_HD S5_INL bool above_tol(double d) { return fabs(d) > S5_CARLSON_TOL; }
+S5_HD S5_INL bool above_tol(double d) { return fabs(d) > S5KC(KC_TOL); }
 #define S5_EXP_MID 100          /* exponent window of the fast R_F / R_J bodies */
 #define S5_EXP_WIDE 320         /* ... of R_C (it receives squares and cubes of R_J's iterates) */
 
 /* R_F body: x zero-or-mid, y and z mid */
 S5_HD S5_INL double rf_core(double x, double y, double z)
 {
-    constexpr double THIRD = 1.0 / 3.0;
-    constexpr double K1 = 1.0 / 24.0, K2 = 0.1, K3 = 3.0 / 44.0, K4 = 1.0 / 14.0;
+    const double THIRD = S5KC(KC_THIRD);
+    const double K1 = S5KC(KC_F1), K2 = S5KC(KC_F2), K3 = S5KC(KC_F3), K4 = S5KC(KC_F4);
     double mu, dx, dy, dz;
     double sx = ff::fsqrt0_nc(x), sy = ff::fsqrt_nc(y), sz = ff::fsqrt_nc(z);
     for (;;) {
@@ -207,13 +225,12 @@ S5_HD S5_NOINL double rf(double x, double y, double z)
     return rf_core(x, y, z);
 }
 
-/* R_C body for y > 0: x zero-or-wide, y wide.  sx_known > 0: the caller knows sqrt(x) exactly
+/* R_C body for y > 0: x zero-or-wide, y wide; sx = sqrt(x) comes from the caller, who may know it exactly
  * (x = RN(v*v) => sqrt(x) = |v| for every binary64 v whose square is a normal number) */
-S5_HD S5_INL double rc_pos_core(double x, double y, double sx_known = 0.0)
+S5_HD S5_INL double rc_pos_core(double x, double y, double sx)
 {
-    constexpr double THIRD = 1.0 / 3.0, K1 = 0.3, K2 = 1.0 / 7.0, K3 = 0.375, K4 = 9.0 / 22.0;
+    const double THIRD = S5KC(KC_THIRD), K1 = S5KC(KC_C1), K2 = S5KC(KC_C2), K3 = S5KC(KC_C3), K4 = S5KC(KC_C4);
     double mu, s;
-    double sx = (sx_known > 0.0) ? sx_known : ff::fsqrt0_nc(x);
     double sy = ff::fsqrt_nc(y);
     for (;;) {
         double lam = 2.0 * sx * sy + y;
@@ -224,12 +241,12 @@ S5_HD S5_INL double rc_pos_core(double x, double y, double sx_known = 0.0)
         if (!above_tol(s)) break;
         sx = ff::fsqrt_nc(x); sy = ff::fsqrt_nc(y);
     }
-    return ff::fdiv_nc(1.0 * (1.0 + s * s * (K1 + s * (K2 + s * (K3 + s * K4)))), ff::fsqrt_nc(mu));
+    return ff::fdiv_nc(1.0 + s * s * (K1 + s * (K2 + s * (K3 + s * K4))), ff::fsqrt_nc(mu));      /* pre == 1: 1.0 * v == v */
 }
 /* R_C body for y < 0 (Cauchy principal value): x zero-or-wide, -y wide */
 S5_HD S5_INL double rc_neg_core(double x, double y)
 {
-    constexpr double THIRD = 1.0 / 3.0, K1 = 0.3, K2 = 1.0 / 7.0, K3 = 0.375, K4 = 9.0 / 22.0;
+    const double THIRD = S5KC(KC_THIRD), K1 = S5KC(KC_C1), K2 = S5KC(KC_C2), K3 = S5KC(KC_C3), K4 = S5KC(KC_C4);
     double mu, s;
     double xs = x - y;
     double sx = ff::fsqrt_nc(xs);
@@ -251,7 +268,7 @@ S5_HD S5_INL double rc_neg_core(double x, double y)
 S5_HD S5_NOINL double rc(double x, double y)
 {
     if (ff::zero_or_pos_within<S5_EXP_WIDE>(x)) {
-        if (ff::pos_within<S5_EXP_WIDE>(y)) return rc_pos_core(x, y);
+        if (ff::pos_within<S5_EXP_WIDE>(y)) return rc_pos_core(x, y, ff::fsqrt0_nc(x));
         if (ff::pos_within<S5_EXP_WIDE>(-y)) return rc_neg_core(x, y);
     }
     return rc_plain(x, y);
@@ -260,8 +277,8 @@ S5_HD S5_NOINL double rc(double x, double y)
 /* tail of R_J after convergence.  sim5elliptic.c:197-203 */
 S5_HD S5_INL double rj_tail(double acc, double w, double mu, double dx, double dy, double dz, double dp)
 {
-    constexpr double K1 = 3.0 / 14.0, K2 = 1.0 / 3.0, K3 = 3.0 / 22.0, K4 = 3.0 / 26.0,
-                     K5 = 0.75 * K3, K6 = 1.5 * K4, K7 = 0.5 * K2, K8 = K3 + K3;
+    const double K1 = S5KC(KC_J1), K2 = S5KC(KC_J2), K3 = S5KC(KC_J3), K4 = S5KC(KC_J4),
+                 K5 = S5KC(KC_J5), K6 = S5KC(KC_J6), K7 = S5KC(KC_J7), K8 = S5KC(KC_J8);
     double ea = dx * (dy + dz) + dy * dz;
     double eb = dx * dy * dz;
     double ec = dp * dp;
@@ -278,8 +295,8 @@ S5_HD S5_INL double rj_tail(double acc, double w, double mu, double dx, double d
 template <int NJ, bool WANT_RF>
 S5_HD S5_INL void rfj_shared_core(double x, double y, double z, const double* p, double* rf_out, double* rj_out)
 {
-    constexpr double THIRD = 1.0 / 3.0;
-    constexpr double F1 = 1.0 / 24.0, F2 = 0.1, F3 = 3.0 / 44.0, F4 = 1.0 / 14.0;
+    const double THIRD = S5KC(KC_THIRD);
+    const double F1 = S5KC(KC_F1), F2 = S5KC(KC_F2), F3 = S5KC(KC_F3), F4 = S5KC(KC_F4);
     double pt[NJ], acc[NJ];
     bool jdone[NJ];
     #pragma unroll
@@ -291,9 +308,10 @@ S5_HD S5_INL void rfj_shared_core(double x, double y, double z, const double* p,
         double lam = sx * (sy + sz) + sy * sz;
         double ssum = sx + sy + sz;
         double sprod = sx * sy * sz;
+        constexpr bool SOLO = (NJ == 1) && !WANT_RF;      /* one function: it leaves the loop when it converges, no flags needed */
         #pragma unroll
         for (int k = 0; k < NJ; k++) {
-            if (!jdone[k]) {
+            if (SOLO || !jdone[k]) {
                 double v = pt[k] * ssum + sprod;
                 double al = sq(v);
                 double be = pt[k] * sq(pt[k] + lam);
@@ -320,8 +338,8 @@ S5_HD S5_INL void rfj_shared_core(double x, double y, double z, const double* p,
         bool all = fdone;
         #pragma unroll
         for (int k = 0; k < NJ; k++) {
-            if (!jdone[k]) {
-                double mu = 0.2 * (s3 + pt[k] + pt[k]);
+            if (SOLO || !jdone[k]) {
+                double mu = S5KC(KC_FIFTH) * (s3 + pt[k] + pt[k]);
                 ff::Rcp rmu = ff::rcp_of(mu);
                 double dx = ff::fdiv_nc(mu - x, rmu), dy = ff::fdiv_nc(mu - y, rmu), dz = ff::fdiv_nc(mu - z, rmu), dp = ff::fdiv_nc(mu - pt[k], rmu);
                 if (!(above_tol(dx) || above_tol(dy) || above_tol(dz) || above_tol(dp))) {
@@ -372,7 +390,7 @@ S5_HD S5_INL double rj_neg_core(double x, double y, double z, double p)
         yt = 0.25 * (yt + lam);
         zt = 0.25 * (zt + lam);
         pt = 0.25 * (pt + lam);
-        mu = 0.2 * (xt + yt + zt + pt + pt);
+        mu = S5KC(KC_FIFTH) * (xt + yt + zt + pt + pt);
         ff::Rcp rmu = ff::rcp_of(mu);
         dx = ff::fdiv_nc(mu - xt, rmu); dy = ff::fdiv_nc(mu - yt, rmu); dz = ff::fdiv_nc(mu - zt, rmu); dp = ff::fdiv_nc(mu - pt, rmu);
         if (!(above_tol(dx) || above_tol(dy) || above_tol(dz) || above_tol(dp))) break;
