@@ -33,6 +33,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "geodesics_per_second"
 UNIT = "rays/s"
 F_ALG_PHI = 16.8e3        # flop per ray, (r, phi, g, F): SURVEY.md 8(d) non-redundant algorithm, / = 15, sqrt = 13 flop
+F_ALG_TRACE = 3.7e3       # of which phase A (roots, crossing, r, g, F): 3 rf + 1 sncndn + roots + glue, per ray
+F_ALG_AZ_RR = 13.1e3      # and phase B per RR disk hit: 3 rf + 6 rj + 2 sncndn + glue
 BYTES_PER_RAY = 4 * 8 + 1
 SAMPLE_N = 1024           # CPU sample: the same camera at 1024x1024 (1/16 of the rays of the 4096^2 image)
 
@@ -166,6 +168,9 @@ def run_ours(args):
         gath = {k: [torch.empty_like(t) for _ in range(world)] for k, t in loc.items()}
     st = abi.TraceStats()
     kev = []
+    phase_ms = [0.0, 0.0, 0.0]      # summed device time of k_trace_eqplane, k_azimuth<RR>, k_azimuth<RC> over the timed steps
+    phase_items = [0, 0]            # RR / RC disk hits integrated by the azimuth kernels (per step)
+    launches = [0]
 
     def step(timed):
         if timed:
@@ -175,6 +180,12 @@ def run_ours(args):
         if timed:
             e1.record()
             kev.append((e0, e1))
+            # per-kernel CUDA events recorded by the library on the launch stream, read back inside the timed region
+            pm, items = api.last_phase_ms()
+            for i, v in enumerate(pm):
+                phase_ms[i] += v
+            phase_items[0], phase_items[1] = items
+            launches[0] += len(pm)
         if world > 1:
             full = None
             for k, t in loc.items():
@@ -256,11 +267,21 @@ def run_ours(args):
                        "sample": "same camera at %dx%d (1/16 of the rays), all host threads, 1 timed pass after 1 warm-up" % (SAMPLE_N, SAMPLE_N)}
             except Exception as e:  # the checker is optional for the benchmark itself
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
-        achieved = F_ALG_PHI * (rays_step / world) / (kernel_ms * 1e-3) / 1e12
+        achieved_step = F_ALG_PHI * (rays_step / world) / (kernel_ms * 1e-3) / 1e12
+        ph = [v / args.steps for v in phase_ms]
+        dom = max(range(3), key=lambda i: ph[i])
+        knames = ("k_trace_eqplane<DEFER>", "k_azimuth<RR>", "k_azimuth<RC>")
+        if dom == 1:
+            units, per_unit, what = phase_items[0], F_ALG_AZ_RR, "RR disk hits"
+        elif dom == 0:
+            units, per_unit, what = rays_step // world, F_ALG_TRACE, "rays"
+        else:
+            units, per_unit, what = phase_items[1], F_ALG_AZ_RR, "RC disk hits"
+        achieved = per_unit * units / (ph[dom] * 1e-3) / 1e12 if ph[dom] > 0 else None
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-                traffic = json.load(fh).get("k_trace_eqplane_dram_bytes_per_launch")
+                traffic = json.load(fh).get(knames[dom])
         except Exception:
             pass
         line = {
@@ -269,11 +290,14 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic", "config": config_dict(world, n),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(abi.ImageParams),
                     "d2h_bytes_per_step": (rays_step // world) * BYTES_PER_RAY, "checksum_g": checksum},
-            "gpu_launches": args.steps * world,
+            "gpu_launches": launches[0] * world,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
+                         "frac": achieved / peak_tf if (peak_tf and achieved) else None, "traffic": traffic,
                          "peak_source": "live FP64 DFMA-chain microbenchmark (sim5_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry",
-                         "flop_per_ray": F_ALG_PHI, "kernel_ms": kernel_ms, "kernel": "k_trace_eqplane",
+                         "kernel": knames[dom], "kernel_ms": ph[dom], "units_per_launch": units, "unit_kind": what, "flop_per_unit": per_unit,
+                         "kernels_ms": dict(zip(knames, ph)), "azimuth_items": {"rr": phase_items[0], "rc": phase_items[1]},
+                         "step": {"achieved": achieved_step, "frac": achieved_step / peak_tf if peak_tf else None,
+                                  "flop_per_ray": F_ALG_PHI, "kernels_ms_total": kernel_ms},
                          "hbm_written_bytes_per_launch": (rays_step // world) * BYTES_PER_RAY},
             "cpu_baseline": cpu,
             "clocks": clocks,

@@ -205,6 +205,12 @@ int  sim5_default_params(int cfg, sim5_image_params* p);
 /* THE batched entry: replaces the per-pixel loop of disk-image.c:53-105 */
 int  sim5_trace_image(const sim5_image_params* p, const sim5_image_out* out, sim5_trace_stats* stats);
 
+/* device time in ms of each kernel of the most recent sim5_trace_image call (CUDA events on the launch stream; waits for
+ * the call to finish, so it also works after SIM5_FLAG_ASYNC): ms[0] trace kernel (phase A), ms[1] azimuth of the RR
+ * geodesics, ms[2] azimuth of the RC geodesics; items (may be NULL): [0] RR and [1] RC disk hits the azimuth kernels
+ * integrated.  Returns the number of kernels the call launched (1 or 3), <0 on error. */
+int  sim5_last_phase_ms(double* ms, int n, int64_t* items);
+
 /* FP64 DFMA-chain microbenchmark: returns measured TFLOP/s (2 flop per DFMA) of the device, <0 on error.
  * This is the roofline denominator for the compute-bound FP64 path (MEASURED_PEAKS.json has no FP64 entry). */
 double sim5_fp64_peak_tflops(int device, int iters);

@@ -51,6 +51,8 @@ def lib():
         L.sim5_trace_image.restype = C.c_int
         L.sim5_fp64_peak_tflops.argtypes = [C.c_int, C.c_int]
         L.sim5_fp64_peak_tflops.restype = C.c_double
+        L.sim5_last_phase_ms.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int64)]
+        L.sim5_last_phase_ms.restype = C.c_int
         dp = C.POINTER(C.c_double)
         L.sim5_batch_rf.argtypes = [C.c_int64, dp, dp, dp, dp]
         L.sim5_batch_rd.argtypes = [C.c_int64, dp, dp, dp, dp]
@@ -199,6 +201,17 @@ def fp64_peak_tflops(device=0, iters=8192):
     if v < 0:
         raise Sim5Error("sim5_fp64_peak_tflops failed: " + last_error())
     return v
+
+
+def last_phase_ms():
+    """Device time (ms) of each kernel of the most recent sim5_trace_image call, [trace] or [trace, azimuth RR,
+    azimuth RC], and the (RR, RC) disk-hit counts the azimuth kernels integrated."""
+    buf = (C.c_double * 3)()
+    items = (C.c_int64 * 2)()
+    n = lib().sim5_last_phase_ms(buf, 3, items)
+    if n < 0:
+        raise Sim5Error("sim5_last_phase_ms failed: " + last_error())
+    return [buf[i] for i in range(n)], (items[0], items[1])
 
 
 def write_text_dump(path, planes, p):

@@ -46,6 +46,8 @@ struct Context {
     int sm_count = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t evp[3] = {nullptr, nullptr, nullptr};   /* phase boundaries of the last image call: after phase A, after azimuth RR, after azimuth RC */
+    int phases = 0;                       /* 0: nothing recorded, 1: one trace kernel, 3: trace + two azimuth kernels */
     Scratch* h_scr = nullptr;
     Scratch* d_scr = nullptr;
     S5ImageConsts* h_consts = nullptr;    /* pinned staging */
@@ -112,6 +114,7 @@ int ensure_init(int device)
     c.stream = c.own_stream;
     CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c.ev0)); CK(cudaEventCreate(&c.ev1)); CK(cudaEventCreate(&c.ev2)); CK(cudaEventCreate(&c.ev3));
+    for (int i = 0; i < 3; i++) CK(cudaEventCreate(&c.evp[i]));
     CK(cudaHostAlloc((void**)&c.h_scr, sizeof(Scratch), cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void**)&c.d_scr, c.h_scr, 0));
     c.consts_cap = 1;
@@ -417,6 +420,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
             if (two_phase) {
                 grid = persistent_grid(s5::k_trace_eqplane<true>, S5_CTA_THREADS);
                 s5::k_trace_eqplane<true><<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d, q, c.d_counter, c.d_stats);
+                CK(cudaEventRecord(c.evp[0], c.stream));
             } else {
                 grid = persistent_grid(s5::k_trace_eqplane<false>, S5_CTA_THREADS);
                 s5::k_trace_eqplane<false><<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d, q, c.d_counter, c.d_stats);
@@ -425,13 +429,16 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                 int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_AZ_THREADS);
                 int g_rc = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RC>, S5_AZ_THREADS);
                 s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(consts, q, d.phi, c.d_counter + 1);
+                CK(cudaEventRecord(c.evp[1], c.stream));
                 s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(consts, q, d.phi, c.d_counter + 2);
+                CK(cudaEventRecord(c.evp[2], c.stream));
                 launches += 2;
             }
         }
         launches += 1;
         CK(cudaGetLastError());
     }
+    c.phases = launches;
     CK(cudaEventRecord(c.ev2, c.stream));
     if (async) return SIM5_OK;
     if (!devptr && npix > 0) {
@@ -466,6 +473,26 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = S5_CTA_THREADS;
     }
     return SIM5_OK;
+}
+
+extern "C" int sim5_last_phase_ms(double* ms, int n, int64_t* items)
+{
+    Context& c = g_ctx;
+    if (!c.ready || !ms || n < 1) { set_error("sim5_last_phase_ms: no context / no output"); return SIM5_ERR_BAD_PARAM; }
+    if (c.phases < 1) { set_error("sim5_last_phase_ms: no image call recorded"); return SIM5_ERR_BAD_PARAM; }
+    CK(cudaEventSynchronize(c.ev2));
+    float t = 0;
+    for (int i = 0; i < n; i++) ms[i] = 0.0;
+    if (items) items[0] = items[1] = 0;
+    if (c.phases == 1) { CK(cudaEventElapsedTime(&t, c.ev1, c.ev2)); ms[0] = t; return 1; }
+    cudaEvent_t seq[4] = {c.ev1, c.evp[0], c.evp[1], c.evp[2]};
+    for (int i = 0; i < 3 && i < n; i++) { CK(cudaEventElapsedTime(&t, seq[i], seq[i + 1])); ms[i] = t; }
+    if (items) {
+        unsigned long long cnt[2] = {0, 0};
+        CK(cudaMemcpy(cnt, c.d_counter + 4, sizeof cnt, cudaMemcpyDeviceToHost));
+        items[0] = (int64_t)cnt[0]; items[1] = (int64_t)cnt[1];
+    }
+    return 3;
 }
 
 /* ------------------------------------------------------------------ */
