@@ -60,6 +60,7 @@ extern "C" {
 #define SIM5_FLAG_DEVICE_PTRS   0x1  /* pointers in sim5_image_out are device pointers (no staging, no D2H) */
 #define SIM5_FLAG_NO_REFILL     0x2  /* debugging: disable warp-level lane refill / compaction */
 #define SIM5_FLAG_SINGLE_PASS    0x8  /* A/B testing: compute the azimuth inside the tracing kernel instead of the queued second phase */
+#define SIM5_FLAG_NO_OVERLAP    0x10 /* A/B testing: host planes are copied back after the whole image instead of chunk by chunk under the kernels */
 #define SIM5_FLAG_ASYNC         0x4  /* with DEVICE_PTRS: enqueue on the library stream (sim5_set_stream) and return without
                                         synchronising; stats are not filled.  Pair with sim5_synchronize(). */
 
@@ -185,6 +186,7 @@ typedef struct sim5_trace_stats {
 /* lifecycle ------------------------------------------------------------- */
 int  sim5_gpu_init(int device);        /* create context/streams/scratch on `device`; idempotent */
 int  sim5_set_stream(void* cuda_stream); /* launch on the caller's cudaStream_t (e.g. torch's current stream); NULL = library stream */
+int  sim5_set_chunk_rays(int64_t rays); /* host-plane calls trace and copy back in chunks of about this many rays (copy of chunk k under the kernels of chunk k+1); <= 0 restores the default (2^20) */
 int  sim5_synchronize(void);            /* wait for everything enqueued by SIM5_FLAG_ASYNC calls */
 void sim5_gpu_shutdown(void);
 int  sim5_gpu_device_count(void);      /* 0 when no usable device */

@@ -28,6 +28,9 @@ using s5::AzQueue;
 /* ------------------------------------------------------------------ */
 namespace {
 
+#define S5_MAX_CHUNKS 32
+#define S5_CHUNK_RAYS (1 << 20)     /* rays per chunk of a host-plane call: ~1.1 ms of kernels, ~0.6 ms of PCIe */
+
 struct Scratch {                  /* mapped pinned memory shared by host and device for scalar calls */
     s5::Geodesic g;
     s5::RayData rtd;
@@ -47,6 +50,9 @@ struct Context {
     cudaStream_t stream = nullptr, copy_stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     cudaEvent_t evp[3] = {nullptr, nullptr, nullptr};   /* phase boundaries of the last image call: after phase A, after azimuth RR, after azimuth RC */
+    cudaEvent_t ev_chunk[S5_MAX_CHUNKS] = {nullptr};      /* chunk k traced -> its device->host copy may start */
+    cudaEvent_t ev_copy_done = nullptr;
+    long long chunk_rays = 0;             /* 0: S5_CHUNK_RAYS */
     int phases = 0;                       /* 0: nothing recorded, 1: one trace kernel, 3: trace + two azimuth kernels */
     Scratch* h_scr = nullptr;
     Scratch* d_scr = nullptr;
@@ -115,6 +121,8 @@ int ensure_init(int device)
     CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c.ev0)); CK(cudaEventCreate(&c.ev1)); CK(cudaEventCreate(&c.ev2)); CK(cudaEventCreate(&c.ev3));
     for (int i = 0; i < 3; i++) CK(cudaEventCreate(&c.evp[i]));
+    for (int i = 0; i < S5_MAX_CHUNKS; i++) CK(cudaEventCreateWithFlags(&c.ev_chunk[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c.ev_copy_done, cudaEventDisableTiming));
     CK(cudaHostAlloc((void**)&c.h_scr, sizeof(Scratch), cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void**)&c.d_scr, c.h_scr, 0));
     c.consts_cap = 1;
@@ -266,6 +274,9 @@ extern "C" void sim5_gpu_shutdown(void)
     for (int i = 0; i < 8; i++) { if (c.batch[i]) cudaFree(c.batch[i]); c.batch[i] = nullptr; c.batch_bytes[i] = 0; }
     cudaFreeHost(c.h_scr); cudaFreeHost(c.h_consts); cudaFree(c.d_consts); cudaFree(c.d_counter); cudaFree(c.d_stats); cudaFreeHost(c.h_stats);
     cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1); cudaEventDestroy(c.ev2); cudaEventDestroy(c.ev3);
+    for (int i = 0; i < 3; i++) cudaEventDestroy(c.evp[i]);
+    for (int i = 0; i < S5_MAX_CHUNKS; i++) cudaEventDestroy(c.ev_chunk[i]);
+    cudaEventDestroy(c.ev_copy_done);
     cudaStreamDestroy(c.own_stream); cudaStreamDestroy(c.copy_stream);
     c.ready = false;
 }
@@ -278,6 +289,12 @@ extern "C" int sim5_set_stream(void* cuda_stream)
     g_ctx.stream = cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.own_stream;
     return SIM5_OK;
 }
+extern "C" int sim5_set_chunk_rays(int64_t rays)
+{
+    g_ctx.chunk_rays = rays > 0 ? (long long)rays : 0;
+    return SIM5_OK;
+}
+
 extern "C" int sim5_synchronize(void)
 {
     std::lock_guard<std::mutex> lk(g_ctx.mu);
@@ -399,63 +416,102 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     S5ImageConsts consts;                  /* travels by value as a kernel parameter: no H2D copy, async-safe */
     s5_fill_image_consts(p, &consts);
     /* two-phase azimuth: phase A queues the disk hits, phase B integrates phi per geodesic type */
+    bool two_phase = (p->mode != SIM5_MODE_STEPWISE) && (p->outputs & SIM5_OUT_PHI) && !(p->flags & SIM5_FLAG_SINGLE_PASS) && npix > 0;
+
+    /* Host planes: the rows are traced in CHUNKS so the device->host copy of chunk k (copy stream, copy engine) runs
+     * under the kernels of chunk k+1; only the last chunk's copy is exposed.  Device planes: one chunk. */
+    int nchunks = 1;
+    if (!devptr && !(p->flags & SIM5_FLAG_NO_OVERLAP) && npix > 0) {
+        long long want = (long long)(npix / (size_t)(c.chunk_rays > 0 ? c.chunk_rays : S5_CHUNK_RAYS));
+        nchunks = (int)(want < 1 ? 1 : (want > S5_MAX_CHUNKS ? S5_MAX_CHUNKS : want));
+    }
+    int chunk_rows = (nrows_local + nchunks - 1) / nchunks;
+    chunk_rows = ((chunk_rows + srows - 1) / srows) * srows;
+    if (chunk_rows < srows) chunk_rows = srows;
+    nchunks = nrows_local > 0 ? (nrows_local + chunk_rows - 1) / chunk_rows : 1;
+
     AzQueue q;
     memset(&q, 0, sizeof q);
-    bool two_phase = (p->mode != SIM5_MODE_STEPWISE) && (p->outputs & SIM5_OUT_PHI) && !(p->flags & SIM5_FLAG_SINGLE_PASS) && npix > 0;
     if (two_phase) {
-        rc = reserve(c.azq_f, npix * S5_AZ_NFIELDS * sizeof(double)); if (rc) return rc;
-        rc = reserve(c.azq_key, npix * sizeof(unsigned long long)); if (rc) return rc;
-        q.f = (double*)c.azq_f.p; q.key = (unsigned long long*)c.azq_key.p; q.count = c.d_counter + 4; q.cap = (long long)npix;
+        size_t qpix = (size_t)(nchunks > 1 ? chunk_rows : nrows_local) * (size_t)p->nx;
+        rc = reserve(c.azq_f, qpix * S5_AZ_NFIELDS * sizeof(double)); if (rc) return rc;
+        rc = reserve(c.azq_key, qpix * sizeof(unsigned long long)); if (rc) return rc;
+        q.f = (double*)c.azq_f.p; q.key = (unsigned long long*)c.azq_key.p; q.count = c.d_counter + 4; q.cap = (long long)qpix;
     }
     CK(cudaEventRecord(c.ev0, c.stream));
-    CK(cudaMemsetAsync(c.d_counter, 0, 8 * sizeof(unsigned long long), c.stream));
     CK(cudaMemsetAsync(c.d_stats, 0, sizeof(DevStats), c.stream));
     int grid = 0, launches = 0;
     CK(cudaEventRecord(c.ev1, c.stream));
-    if (npix > 0) {
+    for (int ch = 0; ch < nchunks && npix > 0; ch++) {
+        int lr0 = ch * chunk_rows;
+        int lrows = nrows_local - lr0 < chunk_rows ? nrows_local - lr0 : chunk_rows;
+        size_t pix0 = (size_t)lr0 * (size_t)p->nx;
+        S5ImageConsts cc = consts;
+        DevOut dd = d;
+        if (nchunks > 1) {
+            /* local rows [lr0, lr0+lrows) of this call == a call of its own whose row range starts (lr0/srows) split periods later */
+            cc.row_begin = consts.row_begin + (lr0 / srows) * split * srows;
+            cc.nrows_local = lrows;
+            cc.row_end = cc.row_begin + lrows * split;
+            for (int i = 0; i < 12; i++) {
+                if (!(p->outputs & kPlaneInfo[i].bit)) continue;
+                set_dev_plane(&dd, i, (char*)c.planes[i].p + pix0 * kPlaneInfo[i].elem);
+            }
+        }
+        CK(cudaMemsetAsync(c.d_counter, 0, 8 * sizeof(unsigned long long), c.stream));
         if (p->mode == SIM5_MODE_STEPWISE) {
             grid = persistent_grid(s5::k_trace_stepwise, S5_CTA_THREADS);
-            s5::k_trace_stepwise<<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d, c.d_counter, c.d_stats);
+            s5::k_trace_stepwise<<<grid, S5_CTA_THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
+        } else if (two_phase) {
+            grid = persistent_grid(s5::k_trace_eqplane<true>, S5_CTA_THREADS);
+            s5::k_trace_eqplane<true><<<grid, S5_CTA_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+            if (ch == 0) CK(cudaEventRecord(c.evp[0], c.stream));
+            int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_AZ_THREADS);
+            int g_rc = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RC>, S5_AZ_THREADS);
+            s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 1);
+            if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
+            s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 2);
+            if (ch == 0) CK(cudaEventRecord(c.evp[2], c.stream));
+            launches += 2;
         } else {
-            if (two_phase) {
-                grid = persistent_grid(s5::k_trace_eqplane<true>, S5_CTA_THREADS);
-                s5::k_trace_eqplane<true><<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d, q, c.d_counter, c.d_stats);
-                CK(cudaEventRecord(c.evp[0], c.stream));
-            } else {
-                grid = persistent_grid(s5::k_trace_eqplane<false>, S5_CTA_THREADS);
-                s5::k_trace_eqplane<false><<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d, q, c.d_counter, c.d_stats);
-            }
-            if (two_phase) {
-                int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_AZ_THREADS);
-                int g_rc = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RC>, S5_AZ_THREADS);
-                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(consts, q, d.phi, c.d_counter + 1);
-                CK(cudaEventRecord(c.evp[1], c.stream));
-                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(consts, q, d.phi, c.d_counter + 2);
-                CK(cudaEventRecord(c.evp[2], c.stream));
-                launches += 2;
-            }
+            grid = persistent_grid(s5::k_trace_eqplane<false>, S5_CTA_THREADS);
+            s5::k_trace_eqplane<false><<<grid, S5_CTA_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
         }
         launches += 1;
         CK(cudaGetLastError());
-    }
-    c.phases = launches;
-    CK(cudaEventRecord(c.ev2, c.stream));
-    if (async) return SIM5_OK;
-    if (!devptr && npix > 0) {
+        if (devptr) continue;
+        /* this chunk's rows go home on the copy stream while the next chunk computes */
+        cudaStream_t cs = c.stream;
+        if (nchunks > 1) {
+            CK(cudaEventRecord(c.ev_chunk[ch], c.stream));
+            CK(cudaStreamWaitEvent(c.copy_stream, c.ev_chunk[ch], 0));
+            cs = c.copy_stream;
+        } else {
+            CK(cudaEventRecord(c.ev2, c.stream));
+        }
         for (int i = 0; i < 12; i++) {
             if (!(p->outputs & kPlaneInfo[i].bit)) continue;
             size_t es = kPlaneInfo[i].elem;
+            const char* src = (const char*)c.planes[i].p + pix0 * es;
             if (split == 1) {
-                char* dst = (char*)host_plane(out, i) + (size_t)rb * p->nx * es;
-                CK(cudaMemcpyAsync(dst, c.planes[i].p, npix * es, cudaMemcpyDeviceToHost, c.stream));
+                char* dst = (char*)host_plane(out, i) + ((size_t)rb + (size_t)lr0) * p->nx * es;
+                CK(cudaMemcpyAsync(dst, src, (size_t)lrows * p->nx * es, cudaMemcpyDeviceToHost, cs));
             } else {
                 size_t blk = (size_t)srows * p->nx * es;
-                for (int b = 0; b < nrows_local / srows; b++) {
-                    int iy0 = rb + (b * split + p->split_index) * srows;
-                    CK(cudaMemcpyAsync((char*)host_plane(out, i) + (size_t)iy0 * p->nx * es, (char*)c.planes[i].p + (size_t)b * blk, blk, cudaMemcpyDeviceToHost, c.stream));
+                for (int b = 0; b < lrows / srows; b++) {
+                    int iy0 = rb + ((lr0 / srows + b) * split + p->split_index) * srows;
+                    CK(cudaMemcpyAsync((char*)host_plane(out, i) + (size_t)iy0 * p->nx * es, src + (size_t)b * blk, blk, cudaMemcpyDeviceToHost, cs));
                 }
             }
         }
+    }
+    c.phases = (nchunks == 1) ? launches : 0;      /* per-kernel times are defined for single-chunk calls only */
+    if (devptr || npix == 0) CK(cudaEventRecord(c.ev2, c.stream));
+    if (async) return SIM5_OK;
+    if (nchunks > 1) {
+        CK(cudaEventRecord(c.ev2, c.stream));
+        CK(cudaEventRecord(c.ev_copy_done, c.copy_stream));
+        CK(cudaStreamWaitEvent(c.stream, c.ev_copy_done, 0));
     }
     CK(cudaMemcpyAsync(c.h_stats, c.d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c.stream));
     CK(cudaEventRecord(c.ev3, c.stream));

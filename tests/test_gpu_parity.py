@@ -88,6 +88,37 @@ def test_row_ranges_and_interleaved_split_compose(gpu_api):
         assert np.array_equal(full[k], inter[k], equal_nan=True), k
 
 
+def test_chunked_copy_overlap_equals_single_pass(gpu_api):
+    """Host-plane calls trace in chunks and copy chunk k back under the kernels of chunk k+1: same planes and counters as the
+    unchunked call, for contiguous rows, ragged row counts, row sub-ranges and the interleaved multi-GPU split."""
+    L = gpu_api.lib()
+    try:
+        for cfg, nx, ny, split in ((2, 256, 256, 1), (2, 130, 77, 1), (3, 96, 160, 1), (2, 128, 256, 2), (4, 48, 40, 1), (1, 64, 192, 3)):
+            p = abi.default_params(cfg, nx, ny)
+            if split > 1:
+                p.split_count, p.split_index, p.split_rows = split, 1, 8
+            if cfg == 2 and split == 1 and nx == 130:
+                p.row_begin, p.row_end = 5, 70
+            p.flags = abi.FLAG_NO_OVERLAP
+            L.sim5_set_chunk_rays(0)
+            ref = gpu_api.HostPlanes(p, pinned=True)
+            for k in ref.arrays:
+                ref[k][...] = 0
+            _, st0 = gpu_api.trace_image(p, ref)
+            p.flags = 0
+            L.sim5_set_chunk_rays(400)
+            got = gpu_api.HostPlanes(p, pinned=True)
+            for k in got.arrays:
+                got[k][...] = 0
+            _, st1 = gpu_api.trace_image(p, got)
+            assert st1.kernel_launches > st0.kernel_launches, "the call was not chunked"
+            assert list(st0.class_count) == list(st1.class_count) and st0.total_steps == st1.total_steps and st0.rays == st1.rays
+            for k in ref.arrays:
+                assert np.array_equal(ref[k], got[k], equal_nan=True), (cfg, nx, ny, split, k)
+    finally:
+        L.sim5_set_chunk_rays(0)
+
+
 def test_empty_and_bad_parameters(gpu_api):
     L = gpu_api.lib()
     p = abi.default_params(1, 16)
@@ -116,6 +147,33 @@ def test_elliptic_batch_against_golden(gpu_api):
     for mine, ref in ((sn, g["sn"]), (cn, g["cn"]), (dn, g["dn"])):
         assert np.mean(mine == ref) > 0.99
         assert H.err_summary(mine, ref, floor=1e-3)["max"] < 1e-13
+
+
+@pytest.mark.skipif(not H.have_oracle(), reason="oracle/libsim5oracle.so not built")
+def test_fastfp_carlson_adversarial_operands(gpu_api):
+    """The branch-free division / square-root bodies of R_F, R_C, R_J (fastfp.cuh) and their plain-operator fallback
+    give the reference's bits on operands far outside the image's range: 2^-1000..2^1000, exact zeros, subnormals,
+    equal arguments, negative p / y (Cauchy principal values).  Checker: the C restatement (bit-identical to the
+    reference, tests/test_oracle.py)."""
+    lib = H.load_oracle()
+    rng = np.random.default_rng(7)
+    n = 200000
+
+    def wide(lo, hi):
+        return np.ldexp(rng.uniform(1.0, 2.0, n), rng.integers(lo, hi, n))
+    for lo, hi in ((-8, 8), (-90, 90), (-320, 320), (-1000, 1000)):
+        x, y, z = wide(lo, hi), wide(lo, hi), wide(lo, hi)
+        x[::7] = 0.0                                   # at most one zero argument is allowed
+        y[3::11] = x[3::11]                            # equal arguments
+        z[5::13] = 5e-324                              # subnormal
+        assert np.array_equal(gpu_api.batch_rf(x, y, z), H.batch_call(lib, "orc_batch_rf", [x, y, z]), equal_nan=True), ("rf", lo, hi)
+        yc = np.where(rng.random(n) < 0.3, -y, y)
+        assert np.array_equal(gpu_api.batch_rc(x, yc), H.batch_call(lib, "orc_batch_rc", [x, yc]), equal_nan=True), ("rc", lo, hi)
+        if hi <= 320:
+            pp = np.where(rng.random(n) < 0.3, -wide(lo, hi), wide(lo, hi))
+            assert np.array_equal(gpu_api.batch_rj(x, y, z, pp), H.batch_call(lib, "orc_batch_rj", [x, y, z, pp]), equal_nan=True), ("rj", lo, hi)
+            zd = np.maximum(z, 1e-300)
+            assert np.array_equal(gpu_api.batch_rd(x, y, zd), H.batch_call(lib, "orc_batch_rd", [x, y, zd]), equal_nan=True), ("rd", lo, hi)
 
 
 def test_device_libm_equals_host_instantiation_and_glibc(gpu_api):
