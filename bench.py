@@ -34,7 +34,9 @@ METRIC = "geodesics_per_second"
 UNIT = "rays/s"
 F_ALG_PHI = 16.8e3        # flop per ray, (r, phi, g, F): SURVEY.md 8(d) non-redundant algorithm, / = 15, sqrt = 13 flop
 F_ALG_TRACE = 3.7e3       # of which phase A (roots, crossing, r, g, F): 3 rf + 1 sncndn + roots + glue, per ray
-F_ALG_AZ_RR = 13.1e3      # and phase B per RR disk hit: 3 rf + 6 rj + 2 sncndn + glue
+F_ALG_AZ_RR = 13.1e3      # phase B per RR disk hit, the reference's non-redundant algorithm (bit-faithful kernels): 3 rf + 6 rj + 2 sncndn + glue
+F_ALG_AZ_FAST = 3.3e3     # phase B per RR disk hit, tolerance-mode algorithm (the default): 4 shared duplication sequences x 4.18 steps,
+                          # 23.5 R_C series, 6 R_J + 3 R_F tails, glue -- op count of tests/hostsim -DS5_COUNT_ITERS, DESIGN.md section 3
 BYTES_PER_RAY = 4 * 8 + 1
 SAMPLE_N = 1024           # CPU sample: the same camera at 1024x1024 (1/16 of the rays of the 4096^2 image)
 
@@ -156,7 +158,7 @@ def run_ours(args):
     p = workload_params(abi, n)
     p.device = local
     rows = sdist.apply_split(p, rank, world) if world > 1 else n
-    p.flags = abi.FLAG_DEVICE_PTRS | abi.FLAG_ASYNC
+    p.flags = abi.FLAG_DEVICE_PTRS | abi.FLAG_ASYNC | (abi.FLAG_EXACT_AZIMUTH if args.exact_azimuth else 0)
     names = ("r", "phi", "g", "flux")
     loc = {k: torch.empty((rows, n), dtype=torch.float64, device=dev) for k in names}
     loc["status"] = torch.empty((rows, n), dtype=torch.uint8, device=dev)
@@ -181,11 +183,11 @@ def run_ours(args):
             e1.record()
             kev.append((e0, e1))
             # per-kernel CUDA events recorded by the library on the launch stream, read back inside the timed region
-            pm, items = api.last_phase_ms()
+            pm, items, nk = api.last_phase_ms()
             for i, v in enumerate(pm):
                 phase_ms[i] += v
             phase_items[0], phase_items[1] = items
-            launches[0] += len(pm)
+            launches[0] += nk
         if world > 1:
             full = None
             for k, t in loc.items():
@@ -231,6 +233,8 @@ def run_ours(args):
     api.check(L.sim5_set_stream(None), "sim5_set_stream")
     ph = workload_params(abi, n)
     ph.device = local
+    if args.exact_azimuth:
+        ph.flags |= abi.FLAG_EXACT_AZIMUTH
     if world > 1:
         sdist.apply_split(ph, rank, world)
     hp = api.HostPlanes(ph, pinned=True)
@@ -267,12 +271,14 @@ def run_ours(args):
                        "sample": "same camera at %dx%d (1/16 of the rays), all host threads, 1 timed pass after 1 warm-up" % (SAMPLE_N, SAMPLE_N)}
             except Exception as e:  # the checker is optional for the benchmark itself
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
-        achieved_step = F_ALG_PHI * (rays_step / world) / (kernel_ms * 1e-3) / 1e12
+        f_rr = F_ALG_AZ_RR if args.exact_azimuth else F_ALG_AZ_FAST
+        flop_step = F_ALG_TRACE * (rays_step / world) + f_rr * phase_items[0] + F_ALG_AZ_RR * phase_items[1]     # work of the algorithm actually run
+        achieved_step = flop_step / (kernel_ms * 1e-3) / 1e12
         ph = [v / args.steps for v in phase_ms]
         dom = max(range(3), key=lambda i: ph[i])
-        knames = ("k_trace_eqplane<DEFER>", "k_azimuth<RR>", "k_azimuth<RC>")
+        knames = ("k_trace_eqplane<DEFER>", "k_azimuth<RR>" if args.exact_azimuth else "k_azimuth_fast", "k_azimuth<RC>")
         if dom == 1:
-            units, per_unit, what = phase_items[0], F_ALG_AZ_RR, "RR disk hits"
+            units, per_unit, what = phase_items[0], f_rr, "RR disk hits"
         elif dom == 0:
             units, per_unit, what = rays_step // world, F_ALG_TRACE, "rays"
         else:
@@ -297,7 +303,10 @@ def run_ours(args):
                          "kernel": knames[dom], "kernel_ms": ph[dom], "units_per_launch": units, "unit_kind": what, "flop_per_unit": per_unit,
                          "kernels_ms": dict(zip(knames, ph)), "azimuth_items": {"rr": phase_items[0], "rc": phase_items[1]},
                          "step": {"achieved": achieved_step, "frac": achieved_step / peak_tf if peak_tf else None,
-                                  "flop_per_ray": F_ALG_PHI, "kernels_ms_total": kernel_ms},
+                                  "flop_per_ray": flop_step / (rays_step / world), "kernels_ms_total": kernel_ms,
+                                  "reference_algorithm_equiv_tflops": F_ALG_PHI * (rays_step / world) / (kernel_ms * 1e-3) / 1e12,
+                                  "note": "achieved counts the flops of the algorithm actually run (tolerance-mode azimuth: 3.3 kflop per RR hit); "
+                                          "reference_algorithm_equiv uses SURVEY.md 8(d)'s 16.8 kflop per ray of the reference's non-redundant algorithm"},
                          "hbm_written_bytes_per_launch": (rays_step // world) * BYTES_PER_RAY},
             "cpu_baseline": cpu,
             "clocks": clocks,
@@ -316,6 +325,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=4096, help="image side (default: the BASELINE 4096)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exact-azimuth", action="store_true", help="A/B: bit-faithful azimuth kernels (SIM5_FLAG_EXACT_AZIMUTH) instead of the tolerance-mode default")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -61,6 +61,10 @@ extern "C" {
 #define SIM5_FLAG_NO_REFILL     0x2  /* debugging: disable warp-level lane refill / compaction */
 #define SIM5_FLAG_SINGLE_PASS    0x8  /* A/B testing: compute the azimuth inside the tracing kernel instead of the queued second phase */
 #define SIM5_FLAG_NO_OVERLAP    0x10 /* A/B testing: host planes are copied back after the whole image instead of chunk by chunk under the kernels */
+#define SIM5_FLAG_EXACT_AZIMUTH 0x20 /* compute phi of RR disk hits with the bit-faithful Carlson routines (the reference's iteration counts and
+                                        series, same bits as its CPU path) instead of the default tolerance-mode kernel, which evaluates the same
+                                        integrals to ~1e-14 with the 7th-order series in fewer steps.  r, g, flux and every status flag are
+                                        bit-faithful in both modes. */
 #define SIM5_FLAG_ASYNC         0x4  /* with DEVICE_PTRS: enqueue on the library stream (sim5_set_stream) and return without
                                         synchronising; stats are not filled.  Pair with sim5_synchronize(). */
 
@@ -209,8 +213,9 @@ int  sim5_trace_image(const sim5_image_params* p, const sim5_image_out* out, sim
 
 /* device time in ms of each kernel of the most recent sim5_trace_image call (CUDA events on the launch stream; waits for
  * the call to finish, so it also works after SIM5_FLAG_ASYNC): ms[0] trace kernel (phase A), ms[1] azimuth of the RR
- * geodesics, ms[2] azimuth of the RC geodesics; items (may be NULL): [0] RR and [1] RC disk hits the azimuth kernels
- * integrated.  Returns the number of kernels the call launched (1 or 3), <0 on error. */
+ * geodesics (tolerance-mode kernel + its redo pass, or the bit-faithful kernel), ms[2] azimuth of the RC geodesics; items
+ * (may be NULL): [0] RR and [1] RC disk hits the azimuth kernels integrated.  Returns the number of kernels the call
+ * launched (1, 3 or 4), <0 on error. */
 int  sim5_last_phase_ms(double* ms, int n, int64_t* items);
 
 /* FP64 DFMA-chain microbenchmark: returns measured TFLOP/s (2 flop per DFMA) of the device, <0 on error.
@@ -227,6 +232,10 @@ int sim5_batch_rf(int64_t n, const double* x, const double* y, const double* z, 
 int sim5_batch_rd(int64_t n, const double* x, const double* y, const double* z, double* out);           /* sim5elliptic.c:58 */
 int sim5_batch_rc(int64_t n, const double* x, const double* y, double* out);                            /* sim5elliptic.c:104 */
 int sim5_batch_rj(int64_t n, const double* x, const double* y, const double* z, const double* p, double* out); /* sim5elliptic.c:144 */
+/* tolerance-mode Carlson integrals of the azimuth phase (sim5_b200/csrc/ellfast.cuh): the same R_F / R_J to a few ulp, not bit for bit;
+ * NaN for arguments outside their domain (x zero or in [2^-60,2^60]; y, z, p in [2^-60,2^60]) */
+int sim5_batch_rf_hi(int64_t n, const double* x, const double* y, const double* z, double* out);
+int sim5_batch_rj_hi(int64_t n, const double* x, const double* y, const double* z, const double* p, double* out);
 int sim5_batch_sncndn(int64_t n, const double* u, const double* m, double* sn, double* cn, double* dn); /* sim5elliptic.c:535 */
 /* unary/binary libm-compatible device functions (correctly-rounded double-double implementations):
  * op: 0 sin, 1 cos, 2 log, 3 atan2(y=a,x=b), 4 acos, 5 asin, 6 atan, 7 pow(a,1./3.), 8 pow(a,1.5), 9 pow(a,4.), 10 exp */

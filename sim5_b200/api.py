@@ -60,9 +60,11 @@ def lib():
         L.sim5_batch_rd.argtypes = [C.c_int64, dp, dp, dp, dp]
         L.sim5_batch_rc.argtypes = [C.c_int64, dp, dp, dp]
         L.sim5_batch_rj.argtypes = [C.c_int64, dp, dp, dp, dp, dp]
+        L.sim5_batch_rf_hi.argtypes = [C.c_int64, dp, dp, dp, dp]
+        L.sim5_batch_rj_hi.argtypes = [C.c_int64, dp, dp, dp, dp, dp]
         L.sim5_batch_sncndn.argtypes = [C.c_int64, dp, dp, dp, dp, dp]
         L.sim5_batch_libm.argtypes = [C.c_int, C.c_int64, dp, dp, dp]
-        for f in ("sim5_batch_rf", "sim5_batch_rd", "sim5_batch_rc", "sim5_batch_rj", "sim5_batch_sncndn", "sim5_batch_libm"):
+        for f in ("sim5_batch_rf_hi", "sim5_batch_rj_hi", "sim5_batch_rf", "sim5_batch_rd", "sim5_batch_rc", "sim5_batch_rj", "sim5_batch_sncndn", "sim5_batch_libm"):
             getattr(L, f).restype = C.c_int
         _lib = L
     return _lib
@@ -183,6 +185,14 @@ def batch_rj(x, y, z, p):
     return _batch(lib().sim5_batch_rj, [x, y, z, p])
 
 
+def batch_rf_hi(x, y, z):
+    return _batch(lib().sim5_batch_rf_hi, [x, y, z])
+
+
+def batch_rj_hi(x, y, z, p):
+    return _batch(lib().sim5_batch_rj_hi, [x, y, z, p])
+
+
 def batch_sncndn(u, m):
     return _batch(lib().sim5_batch_sncndn, [u, m], nout=3)
 
@@ -207,13 +217,13 @@ def fp64_peak_tflops(device=0, iters=8192):
 
 def last_phase_ms():
     """Device time (ms) of each kernel of the most recent sim5_trace_image call, [trace] or [trace, azimuth RR,
-    azimuth RC], and the (RR, RC) disk-hit counts the azimuth kernels integrated."""
+    azimuth RC], the (RR, RC) disk-hit counts the azimuth kernels integrated, and the number of kernels launched."""
     buf = (C.c_double * 3)()
     items = (C.c_int64 * 2)()
     n = lib().sim5_last_phase_ms(buf, 3, items)
     if n < 0:
         raise Sim5Error("sim5_last_phase_ms failed: " + last_error())
-    return [buf[i] for i in range(n)], (items[0], items[1])
+    return [buf[i] for i in range(min(n, 3))], (items[0], items[1]), n
 
 
 def write_text_dump(path, planes, p):

@@ -53,7 +53,7 @@ struct Context {
     cudaEvent_t ev_chunk[S5_MAX_CHUNKS] = {nullptr};      /* chunk k traced -> its device->host copy may start */
     cudaEvent_t ev_copy_done = nullptr;
     long long chunk_rays = 0;             /* 0: S5_CHUNK_RAYS */
-    int phases = 0;                       /* 0: nothing recorded, 1: one trace kernel, 3: trace + two azimuth kernels */
+    int phases = 0;                       /* kernels launched by the last single-chunk image call: 0 none recorded, 1 trace only, 3 or 4 trace + azimuth kernels */
     Scratch* h_scr = nullptr;
     Scratch* d_scr = nullptr;
     S5ImageConsts* h_consts = nullptr;    /* pinned staging */
@@ -64,6 +64,7 @@ struct Context {
     DevStats* h_stats = nullptr;          /* pinned */
     Plane planes[12];
     Plane hist;
+    Plane azq_redo;
     Plane azq_f, azq_key;                 /* azimuth work-item queue (phase A -> phase B) */
     void* batch[8] = {nullptr};
     size_t batch_bytes[8] = {0};
@@ -271,6 +272,7 @@ extern "C" void sim5_gpu_shutdown(void)
     if (c.hist.p) cudaFree(c.hist.p); c.hist = Plane();
     if (c.azq_f.p) cudaFree(c.azq_f.p); c.azq_f = Plane();
     if (c.azq_key.p) cudaFree(c.azq_key.p); c.azq_key = Plane();
+    if (c.azq_redo.p) cudaFree(c.azq_redo.p); c.azq_redo = Plane();
     for (int i = 0; i < 8; i++) { if (c.batch[i]) cudaFree(c.batch[i]); c.batch[i] = nullptr; c.batch_bytes[i] = 0; }
     cudaFreeHost(c.h_scr); cudaFreeHost(c.h_consts); cudaFree(c.d_consts); cudaFree(c.d_counter); cudaFree(c.d_stats); cudaFreeHost(c.h_stats);
     cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1); cudaEventDestroy(c.ev2); cudaEventDestroy(c.ev3);
@@ -436,7 +438,9 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         size_t qpix = (size_t)(nchunks > 1 ? chunk_rows : nrows_local) * (size_t)p->nx;
         rc = reserve(c.azq_f, qpix * S5_AZ_NFIELDS * sizeof(double)); if (rc) return rc;
         rc = reserve(c.azq_key, qpix * sizeof(unsigned long long)); if (rc) return rc;
+        rc = reserve(c.azq_redo, qpix * sizeof(unsigned)); if (rc) return rc;
         q.f = (double*)c.azq_f.p; q.key = (unsigned long long*)c.azq_key.p; q.count = c.d_counter + 4; q.cap = (long long)qpix;
+        q.redo = (unsigned*)c.azq_redo.p;
     }
     CK(cudaEventRecord(c.ev0, c.stream));
     CK(cudaMemsetAsync(c.d_stats, 0, sizeof(DevStats), c.stream));
@@ -468,9 +472,16 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
             if (ch == 0) CK(cudaEventRecord(c.evp[0], c.stream));
             int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_AZ_THREADS);
             int g_rc = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RC>, S5_AZ_THREADS);
-            s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 1);
+            if (p->flags & SIM5_FLAG_EXACT_AZIMUTH) {
+                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 1, 0);
+            } else {
+                int g_f = persistent_grid(s5::k_azimuth_fast, S5_AZF_THREADS);
+                s5::k_azimuth_fast<<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
+                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 1, 1);   /* the redo list (normally empty) */
+                launches += 1;
+            }
             if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
-            s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 2);
+            s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 2, 0);
             if (ch == 0) CK(cudaEventRecord(c.evp[2], c.stream));
             launches += 2;
         } else {
@@ -548,7 +559,7 @@ extern "C" int sim5_last_phase_ms(double* ms, int n, int64_t* items)
         CK(cudaMemcpy(cnt, c.d_counter + 4, sizeof cnt, cudaMemcpyDeviceToHost));
         items[0] = (int64_t)cnt[0]; items[1] = (int64_t)cnt[1];
     }
-    return 3;
+    return c.phases;
 }
 
 /* ------------------------------------------------------------------ */
@@ -630,6 +641,22 @@ extern "C" int sim5_batch_rf(int64_t n, const double* x, const double* y, const 
     BATCH_BEGIN();
     int rc; if ((rc = stage_in(0, x, n)) || (rc = stage_in(1, y, n)) || (rc = stage_in(2, z, n)) || (rc = stage_in(3, nullptr, n))) return rc;
     s5::k_batch_rf<<<batch_grid(n), 128, 0, g_ctx.stream>>>(n, B(0), B(1), B(2), B(3));
+    if ((rc = stage_out(3, out, n))) return rc;
+    BATCH_END();
+}
+extern "C" int sim5_batch_rf_hi(int64_t n, const double* x, const double* y, const double* z, double* out)
+{
+    BATCH_BEGIN();
+    int rc; if ((rc = stage_in(0, x, n)) || (rc = stage_in(1, y, n)) || (rc = stage_in(2, z, n)) || (rc = stage_in(3, nullptr, n))) return rc;
+    s5::k_batch_rf_hi<<<batch_grid(n), 128, 0, g_ctx.stream>>>(n, B(0), B(1), B(2), B(3));
+    if ((rc = stage_out(3, out, n))) return rc;
+    BATCH_END();
+}
+extern "C" int sim5_batch_rj_hi(int64_t n, const double* x, const double* y, const double* z, const double* p, double* out)
+{
+    BATCH_BEGIN();
+    int rc; if ((rc = stage_in(0, x, n)) || (rc = stage_in(1, y, n)) || (rc = stage_in(2, z, n)) || (rc = stage_in(4, p, n)) || (rc = stage_in(3, nullptr, n))) return rc;
+    s5::k_batch_rj_hi<<<batch_grid(n), 128, 0, g_ctx.stream>>>(n, B(0), B(1), B(2), B(4), B(3));
     if ((rc = stage_out(3, out, n))) return rc;
     BATCH_END();
 }

@@ -40,7 +40,8 @@ struct DevStats {                 /* device-side counters, flushed once per CTA 
 struct AzQueue {
     double* f;                    /* [S5_AZ_NFIELDS][cap] */
     unsigned long long* key;      /* [cap]: bits 0..47 output index, bits 48..51 nrr, bit 56 rf_ok */
-    unsigned long long* count;    /* [0] RR items, [1] RC items */
+    unsigned long long* count;    /* [0] RR items, [1] RC items, [2] RR items the tolerance-mode kernel handed back (redo list) */
+    unsigned* redo;               /* [cap] slots of those items */
     long long cap;                /* 0: no queue -> the azimuth is computed inline by phase A */
 };
 
@@ -170,10 +171,10 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
 #endif
 template <int TYPE>
 __global__ void __launch_bounds__(S5_AZ_THREADS, 1)
-k_azimuth(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double* __restrict__ phi, unsigned long long* __restrict__ tile_counter)
+k_azimuth(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double* __restrict__ phi, unsigned long long* __restrict__ tile_counter, int from_redo)
 {
     __shared__ unsigned long long s_base;
-    const long long count = (long long)q.count[TYPE == GEOD_TYPE_RR ? 0 : 1];
+    const long long count = (long long)q.count[from_redo ? 2 : (TYPE == GEOD_TYPE_RR ? 0 : 1)];
     const long long cap = q.cap;
     const double a_eff = fmax(1e-4, gconsts.a);
     const double cos_i = gconsts.cos_i;
@@ -187,7 +188,7 @@ k_azimuth(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double* __re
         const bool valid = it < count;
         if (!valid) it = count - 1;          /* every thread runs the routine (it has barriers); the surplus ones redo the last item */
         {
-            long long slot = (TYPE == GEOD_TYPE_RR) ? it : cap - 1 - it;
+            long long slot = from_redo ? (long long)q.redo[it] : ((TYPE == GEOD_TYPE_RR) ? it : cap - 1 - it);
             const double* f = q.f + slot;
             AzIn z;
             z.e0 = f[0 * cap];  z.e1 = f[1 * cap];  z.e2 = f[2 * cap];   z.e3 = f[3 * cap];
@@ -202,6 +203,43 @@ k_azimuth(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double* __re
             double v = azimuth_from_t<true>(z);
             if (valid) phi[key & 0xffffffffffffULL] = v;
         }
+    }
+}
+
+/* phase B, tolerance mode (the default): azimuth of the queued RR hits with azimuth_fast_rr (pixel.cuh).  The routine is
+ * ~20 KB of SASS, so free-running warps stay inside the instruction cache and no CTA barriers are needed; items cost the
+ * same to within one duplication step, so a static grid-stride split is balanced.  Items whose arguments leave the fast
+ * routines' domain are appended to the redo list and integrated by k_azimuth<RR> afterwards. */
+#ifndef S5_AZF_THREADS
+#define S5_AZF_THREADS 256        /* r01f sweep (profiles/r01f_sweep.log): 256 x 2 CTAs/SM 3.14 ms, 128 x 4 3.32, 128 x 6 (80 regs, spills) 3.31, 128 x 3 3.46 */
+#endif
+#ifndef S5_MIN_CTAS_AZF
+#define S5_MIN_CTAS_AZF 2
+#endif
+__global__ void __launch_bounds__(S5_AZF_THREADS, S5_MIN_CTAS_AZF)
+k_azimuth_fast(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double* __restrict__ phi)
+{
+    const long long count = (long long)q.count[0];
+    const long long cap = q.cap;
+    const double a_eff = fmax(1e-4, gconsts.a);
+    const double cos_i = gconsts.cos_i;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < count; it += stride) {
+        const double* f = q.f + it;
+        AzIn z;
+        z.e0 = f[0 * cap];  z.e1 = f[1 * cap];  z.e2 = f[2 * cap];   z.e3 = f[3 * cap];
+        z.l = f[4 * cap];   z.m2m = f[5 * cap]; z.m2p = f[6 * cap];  z.mm = f[7 * cap];
+        z.Tpp = f[8 * cap]; z.Tip = f[9 * cap]; z.Rpc = f[10 * cap]; z.beta = f[11 * cap];
+        z.K_mm = f[12 * cap]; z.rf_u = 0.0; z.isn_inf = 0.0; z.r = f[15 * cap]; z.P = f[16 * cap];
+        unsigned long long key = q.key[it];
+        z.a = a_eff; z.cos_i = cos_i;
+        z.type = GEOD_TYPE_RR;
+        z.nrr = (int)((key >> 48) & 15);
+        z.rf_ok = false;
+        bool ok;
+        double v = azimuth_fast_rr(z, &ok);
+        if (ok) phi[key & 0xffffffffffffULL] = v;
+        else q.redo[atomicAdd(&q.count[2], 1ULL)] = (unsigned)it;
     }
 }
 
@@ -426,6 +464,11 @@ __global__ void k_batch_rc(long long n, const double* x, const double* y, double
 { for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = rc(x[i], y[i]); }
 __global__ void k_batch_rj(long long n, const double* x, const double* y, const double* z, const double* p, double* o)
 { for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = rj(x[i], y[i], z[i], p[i]); }
+/* tolerance-mode Carlson routines of ellfast.cuh (arguments outside their domain give NaN here; the kernels hand such items to the bit-faithful path) */
+__global__ void k_batch_rf_hi(long long n, const double* x, const double* y, const double* z, double* o)
+{ for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = hi_domain(x[i], y[i], z[i]) ? rf_hi(x[i], y[i], z[i]) : NAN; }
+__global__ void k_batch_rj_hi(long long n, const double* x, const double* y, const double* z, const double* p, double* o)
+{ for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = (hi_domain(x[i], y[i], z[i]) && hi_domain_p(p[i])) ? rj_hi(x[i], y[i], z[i], p[i]) : NAN; }
 __global__ void k_batch_sncndn(long long n, const double* u, const double* m, double* sn, double* cn, double* dn)
 { for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) jacobi_sncndn(u[i], m[i], &sn[i], &cn[i], &dn[i]); }
 __global__ void k_batch_libm(int op, long long n, const double* a, const double* b, double* o)

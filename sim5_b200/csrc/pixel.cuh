@@ -17,6 +17,7 @@
 #include "raytrace.cuh"
 #include "polar.cuh"
 #include "image_consts.h"
+#include "ellfast.cuh"
 
 namespace s5 {
 
@@ -269,6 +270,123 @@ S5_HD S5_INL double azimuth_equatorial(const Geodesic* g, const RayCache& k, dou
     az_make(g, k, r, P, &z);
     return azimuth_from(z);
 }
+S5_HD S5_MID double azimuth_fast_rr(const AzIn& z, bool* ok);
+/* the azimuth as the image kernels compute it by default: tolerance mode for RR hits, bit-faithful for everything else */
+S5_HD S5_INL double azimuth_equatorial_default(const Geodesic* g, const RayCache& k, double r, double P)
+{
+    AzIn z;
+    az_make(g, k, r, P, &z);
+    if (z.type == GEOD_TYPE_RR) {
+        bool ok;
+        double v = azimuth_fast_rr(z, &ok);
+        if (ok) return v;
+    }
+    return azimuth_from(z);
+}
+
+/*
+ * Tolerance-mode azimuth of an RR disk hit (phase B, the dominant kernel): the same integral as azimuth_from_t, to
+ * ~1e-14 instead of bit for bit (bar: 1e-9, BASELINE.json north_star), with less work:
+ *   - the amplitudes are algebraic: sn^2 at infinity is (b-d)/(a-d) and cn^2 = (a-b)/(a-d); at r,
+ *     sn^2 = (b-d)(r-a)/((a-d)(r-b)) and cn^2 = (a-b)(r-d)/((a-d)(r-b)) (no cancellation).  The reference gets them as
+ *     cn(sn^-1(sn)) through two jacobi_sncndn calls (sim5elliptic.c:676-690 via :1026,1041); here neither is needed;
+ *   - sn^-1(sn, m) = sn * R_F(cn^2, 1 - m sn^2, 1) is the R_F that the Pi of the same amplitude needs anyway, so each
+ *     limit is ONE duplication sequence giving R_F and the R_J of both poles (rfj_hi<2, true>);
+ *   - the 7th-order Carlson series of ellfast.cuh (about 4 duplication steps instead of 6.4).
+ * 4 duplication sequences and 6 R_J per hit (2 x {R_F, R_J, R_J}, the complete R_J and one R_J + R_F of the polar part)
+ * instead of 3 R_F + 6 R_J + 2 sncndn over 9 sequences.  *ok = false (and a NaN result) when an argument leaves the
+ * domain of the fast routines or the reference would take one of its special branches; the caller then has the
+ * bit-faithful kernel redo the item.
+ */
+S5_HD S5_MID double azimuth_fast_rr(const AzIn& z, bool* ok)
+{
+    const double r = z.r;
+    int ppc = (z.nrr > 0) && (z.P > z.Rpc);
+    double a2 = sq(z.a);
+    double sq1 = sqrt(1. - a2);
+    double rp = 1. + sq1, rm = 1. - sq1;
+    double a = z.e0, b = z.e1, c = z.e2, d = z.e3;
+    double ad = a - d, bd = b - d, ab = a - b, ac = a - c;
+    double m2 = ((b - c) * ad) / (ac * bd);
+    double pre = -2.0 / sqrt(ac * bd);
+    double aa2 = ad / bd;
+    double c2p = ((rp - b) * ad) / ((rp - a) * bd);
+    double c2m = ((rm - b) * ad) / ((rm - a) * bd);
+    bool good = true;
+
+    /* limit at infinity */
+    double s2i = bd / ad, ci2 = ab / ad;
+    double qi = 1.0 - s2i * m2;
+    double pi_[2] = {1.0 - c2p * s2i, 1.0 - c2m * s2i};
+    bool gi = (s2i >= 0.0) && hi_domain(ci2, qi, 1.0) && hi_domain_p(pi_[0]) && hi_domain_p(pi_[1]);
+    if (!gi) { ci2 = qi = pi_[0] = pi_[1] = 1.0; good = false; }
+    double Fi, Ji[2];
+    rfj_hi<2, true>(ci2, qi, 1.0, pi_, &Fi, Ji);
+    double si = sqrt(s2i);
+    double u_inf = si * Fi;
+    double Pinf_p = si * (Fi + c2p * s2i * Ji[0] * (1.0 / 3.0));
+    double Pinf_m = si * (Fi + c2m * s2i * Ji[1] * (1.0 / 3.0));
+
+    /* limit at r */
+    double rb = r - b;
+    double s2r = (bd * (r - a)) / (ad * rb), cr2 = (ab * (r - d)) / (ad * rb);
+    double qr = 1.0 - s2r * m2;
+    double pr_[2] = {1.0 - c2p * s2r, 1.0 - c2m * s2r};
+    bool gr = (s2r >= 0.0) && hi_domain(cr2, qr, 1.0) && hi_domain_p(pr_[0]) && hi_domain_p(pr_[1]);
+    if (!gr) { cr2 = qr = pr_[0] = pr_[1] = 1.0; good = false; }
+    double Fr, Jr[2];
+    rfj_hi<2, true>(cr2, qr, 1.0, pr_, &Fr, Jr);
+    double sr = sqrt(s2r);
+    double u_r = sr * Fr;
+    double Pr_p = sr * (Fr + c2p * s2r * Jr[0] * (1.0 / 3.0));
+    double Pr_m = sr * (Fr + c2m * s2r * Jr[1] * (1.0 / 3.0));
+
+    double sgn = ppc ? +1.0 : -1.0;
+    double A = pre / (rp - a) * ((1. / c2p) * (((c2p - aa2) * Pinf_p + aa2 * u_inf) + sgn * ((c2p - aa2) * Pr_p + aa2 * u_r)));
+    double B = pre / (rm - a) * ((1. / c2m) * (((c2m - aa2) * Pinf_m + aa2 * u_inf) + sgn * ((c2m - aa2) * Pr_m + aa2 * u_r)));
+    double phi = 1. / sq1 * (A * (z.a * rp - z.l * a2 / 2.) - B * (z.a * rm - z.l * a2 / 2.));
+
+    /* polar part: integral_T_mp(m2m, m2p, 1, X) for X = 0 and X = cos_i (sim5elliptic.c:1142-1159) */
+    double msum = z.m2m + z.m2p;
+    double tm = z.m2p / msum;
+    double tn = z.m2p / (z.m2p - 1.0);
+    double tpre = 1. / sqrt(msum) / (1.0 - z.m2p);
+    double qc = 1.0 - tm, pc = 1.0 - tn;
+    double cu = z.cos_i / sqrt(z.m2p);
+    double cu2 = cu * cu;
+    double ns2 = -tn * (1.0 - cu2);
+    double qu = 1.0 - (1.0 - cu2) * tm;
+    double pu = 1.0 + ns2;
+    bool gp = (z.cos_i > 0.0) && (cu2 < 1.0) && (tm < 1.0) && !(tn == 1.0) && hi_domain(0.0, qc, 1.0) && hi_domain_p(pc) && hi_domain(cu2, qu, 1.0) && hi_domain_p(pu);
+    if (!gp) { qc = pc = cu2 = qu = pu = 1.0; good = false; }
+    double rfK = (tm == z.mm) ? z.K_mm : rf_hi(0.0, qc, 1.0);
+    double comp = rfK + tn * rj_hi(0.0, qc, 1.0, pc) * (1.0 / 3.0);
+    double Fu, Ju;
+    rfj_hi<1, true>(cu2, qu, 1.0, &pu, &Fu, &Ju);
+    double vu = sqrt(1.0 - cu2) * (Fu - ns2 * Ju * (1.0 / 3.0));
+    double la = z.l / z.a;
+    double T0 = tpre * comp;
+    double phi_pp = 2.0 * la * T0;
+    double phi_mp = la * T0;
+    double phi_ip = la * (tpre * vu);
+
+    double T;
+    double sign_dm = (z.beta >= 0.0) ? +1.0 : -1.0;
+    if (sign_dm > 0.0) {
+        T = -(z.Tpp - z.Tip);
+        phi -= phi_pp - phi_ip;
+    } else {
+        T = -z.Tip;
+        phi -= phi_ip;
+    }
+    if (z.P >= T + z.Tpp) {
+        phi += phi_pp;
+        sign_dm = -sign_dm;
+    }
+    phi += (sign_dm < 0) ? phi_mp : phi_pp - phi_mp;
+    *ok = good;
+    return good ? phi : NAN;
+}
 
 /* emission-side quantities of the polarized mode for a disk hit at (r, m=0), position parameter P */
 S5_HD S5_MID void polarized_hit(const S5ImageConsts& c, const Geodesic* gd, double r, double P, PixelOut* o)
@@ -336,7 +454,7 @@ S5_HD S5_INL bool trace_eqplane_pixel_t(const S5ImageConsts& c, int ix, int iy, 
                     if (gd.type == GEOD_TYPE_RR || gd.type == GEOD_TYPE_RC) { az_make(&gd, k, r, P, defer); deferred = true; }
                     else o->phi = NAN;               /* geodesic_position_azm returns NaN for the other types */
                 } else {
-                    o->phi = azimuth_equatorial(&gd, k, r, P);
+                    o->phi = (c.flags & SIM5_FLAG_EXACT_AZIMUTH) ? azimuth_equatorial(&gd, k, r, P) : azimuth_equatorial_default(&gd, k, r, P);
                 }
             }
             if (c.mode == SIM5_MODE_POLARIZED) {

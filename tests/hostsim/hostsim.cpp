@@ -43,6 +43,8 @@ void hs_batch_rf(long n, const double* x, const double* y, const double* z, doub
 void hs_batch_rd(long n, const double* x, const double* y, const double* z, double* o) { for (long i = 0; i < n; i++) o[i] = rd(x[i], y[i], z[i]); }
 void hs_batch_rc(long n, const double* x, const double* y, double* o) { for (long i = 0; i < n; i++) o[i] = rc(x[i], y[i]); }
 void hs_batch_rj(long n, const double* x, const double* y, const double* z, const double* p, double* o) { for (long i = 0; i < n; i++) o[i] = rj(x[i], y[i], z[i], p[i]); }
+void hs_batch_rf_hi(long n, const double* x, const double* y, const double* z, double* o) { for (long i = 0; i < n; i++) o[i] = hi_domain(x[i], y[i], z[i]) ? rf_hi(x[i], y[i], z[i]) : NAN; }
+void hs_batch_rj_hi(long n, const double* x, const double* y, const double* z, const double* p, double* o) { for (long i = 0; i < n; i++) o[i] = (hi_domain(x[i], y[i], z[i]) && hi_domain_p(p[i])) ? rj_hi(x[i], y[i], z[i], p[i]) : NAN; }
 void hs_batch_sncndn(long n, const double* u, const double* m, double* sn, double* cn, double* dn) { for (long i = 0; i < n; i++) jacobi_sncndn(u[i], m[i], &sn[i], &cn[i], &dn[i]); }
 
 // geodesic_init_inf through the scalar-API path (cr_sincos of the inclination); g is the 240-byte reference struct
@@ -120,3 +122,11 @@ double hs_trace_image(const sim5_image_params* p, const sim5_image_out* out, int
 }
 
 }
+
+#if defined(S5_COUNT_ITERS)
+// op-counting build only: the tolerance-mode Carlson counters of ellfast.cuh
+extern "C" void hs_hi_counts(long long* out, int reset)
+{
+    for (int i = 0; i < 4; i++) { out[i] = s5::s5_hi_counts[i]; if (reset) s5::s5_hi_counts[i] = 0; }
+}
+#endif

@@ -1,0 +1,81 @@
+"""Tolerance-mode Carlson integrals (sim5_b200/csrc/ellfast.cuh, used by the default azimuth kernel): accuracy against
+mpmath (the mathematical value) and against the bit-faithful restatement, and the whole azimuth against the reference.
+The bar of BASELINE.json's north_star for phi is 1e-9; the functions are good to a few ulp."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+from sim5_b200 import abi
+
+
+@pytest.fixture(scope="module")
+def hs():
+    return C.CDLL(os.path.join(H.ROOT, "tests", "_build", "libhostsim.so"))
+
+
+def _args(n, seed):
+    """(c^2, 1-(1-c^2)m, 1, p): the shapes elliptic_pi_cos produces, incl. the complete case c = 0 and wide p."""
+    rng = np.random.default_rng(seed)
+    c2 = rng.uniform(0.0, 1.0, n)
+    c2[::5] = 0.0
+    m = rng.uniform(1e-3, 0.9999, n)
+    q = 1.0 - (1.0 - c2) * m
+    p = np.where(rng.random(n) < 0.5, 1.0 + rng.uniform(-0.999, 8.0, n) * (1.0 - c2), 10.0 ** rng.uniform(-6, 6, n))
+    p = np.maximum(p, 1e-9)
+    return c2, q, np.ones(n), p
+
+
+def test_against_mpmath(hs):
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    x, y, z, p = _args(1500, 11)
+    rf = H.batch_call(hs, "hs_batch_rf_hi", [x, y, z])
+    rj = H.batch_call(hs, "hs_batch_rj_hi", [x, y, z, p])
+    worst_f = worst_j = 0.0
+    for i in range(x.size):
+        tf = mp.elliprf(mp.mpf(float(x[i])), mp.mpf(float(y[i])), 1)
+        tj = mp.elliprj(mp.mpf(float(x[i])), mp.mpf(float(y[i])), 1, mp.mpf(float(p[i])))
+        worst_f = max(worst_f, float(abs((mp.mpf(float(rf[i])) - tf) / tf)))
+        worst_j = max(worst_j, float(abs((mp.mpf(float(rj[i])) - tj) / tj)))
+    assert worst_f < 2e-15 and worst_j < 4e-15, (worst_f, worst_j)
+
+
+@pytest.mark.skipif(not H.have_oracle(), reason="oracle/libsim5oracle.so not built")
+def test_against_bit_faithful_restatement(hs):
+    lib = H.load_oracle()
+    x, y, z, p = _args(200000, 12)
+    rf = H.batch_call(hs, "hs_batch_rf_hi", [x, y, z])
+    rj = H.batch_call(hs, "hs_batch_rj_hi", [x, y, z, p])
+    assert H.err_summary(rf, H.batch_call(lib, "orc_batch_rf", [x, y, z]))["max"] < 3e-15
+    assert H.err_summary(rj, H.batch_call(lib, "orc_batch_rj", [x, y, z, p]))["max"] < 6e-15
+    # outside the domain the routines decline (NaN) instead of looping or returning garbage
+    bad = H.batch_call(hs, "hs_batch_rj_hi", [x[:4], y[:4], z[:4], np.array([-1.0, 0.0, 1e300, np.nan])])
+    assert np.all(np.isnan(bad))
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built")
+def test_default_and_exact_azimuth_against_reference():
+    """phi of the default (tolerance-mode) path stays two orders of magnitude inside the 1e-9 bar; the exact flag restores
+    the bit-faithful routine; r, g, flux and the status byte are the same doubles in both modes."""
+    p = abi.default_params(2, 192)
+    ref, _, _ = H.run_ref(p)
+    fast, _, _ = H.run_hostsim(p)
+    p.flags = abi.FLAG_EXACT_AZIMUTH
+    exact, _, _ = H.run_hostsim(p)
+    e_fast = H.err_summary(fast["phi"], ref["phi"], 1.0)
+    e_exact = H.err_summary(exact["phi"], ref["phi"], 1.0)
+    assert e_fast["max"] < 1e-10 and e_fast["p999"] < 1e-11, e_fast
+    assert e_exact["max"] < 1e-11 and e_exact["exact"] > 0.99, e_exact
+    for k in ("r", "g", "flux", "status"):
+        assert np.array_equal(fast[k], exact[k]), k
+
+
+@pytest.mark.gpu
+def test_device_matches_host_instantiation(gpu_api, hs):
+    x, y, z, p = _args(100000, 13)
+    assert np.array_equal(gpu_api.batch_rf_hi(x, y, z), H.batch_call(hs, "hs_batch_rf_hi", [x, y, z]), equal_nan=True) or \
+        H.err_summary(gpu_api.batch_rf_hi(x, y, z), H.batch_call(hs, "hs_batch_rf_hi", [x, y, z]))["max"] < 2e-15
+    assert H.err_summary(gpu_api.batch_rj_hi(x, y, z, p), H.batch_call(hs, "hs_batch_rj_hi", [x, y, z, p]))["max"] < 4e-15

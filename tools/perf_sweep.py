@@ -16,17 +16,24 @@ try:
 except AssertionError as e:
     res["golden"] = str(e)
 def t(p, reps=3):
+    p.flags |= abi.FLAG_NO_OVERLAP            # one chunk: kernel_ms is the kernels alone and the per-kernel times are defined
     planes = api.HostPlanes(p)
     best = 1e30
     for _ in range(reps):
-        _, st = api.trace_image(p, planes); best = min(best, st.kernel_ms)
+        _, st = api.trace_image(p, planes)
+        if st.kernel_ms < best:
+            best = st.kernel_ms
+            res["_phases"] = [round(v, 3) for v in api.last_phase_ms()[0]]
     return best, st
-p = abi.default_params(2); ms, st = t(p); res["cfg2_phi_ms"] = round(ms,3); res["cfg2_phi_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
+p = abi.default_params(2); ms, st = t(p); res["cfg2_phi_ms"] = round(ms,3); res["cfg2_phases_ms"] = res.pop("_phases"); res["cfg2_phi_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
+if os.environ.get("SWEEP_EXACT"):
+    p = abi.default_params(2); p.flags = abi.FLAG_EXACT_AZIMUTH; ms, st = t(p); res["cfg2_exact_ms"] = round(ms,3); res["cfg2_exact_phases_ms"] = res.pop("_phases")
 p = abi.default_params(2); p.outputs = abi.OUT_R|abi.OUT_G|abi.OUT_FLUX|abi.OUT_STATUS; ms, st = t(p); res["cfg2_nophi_ms"] = round(ms,3); res["cfg2_nophi_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
 p = abi.default_params(3); ms, st = t(p); res["cfg3_ms"] = round(ms,3); res["cfg3_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
 p = abi.default_params(4, 512); ms, st = t(p, 1); res["cfg4_512_ms"] = round(ms,2); res["cfg4_steps_s"] = "%%.3e" %% (st.total_steps/ms*1e3)
 if os.environ.get("SWEEP_NOREFILL"):
     p.flags = abi.FLAG_NO_REFILL; ms, st = t(p, 1); res["cfg4_512_norefill_ms"] = round(ms,2)
+res.pop("_phases", None)
 print(json.dumps(res))
 ''' % (ROOT, ROOT)
 libs = sorted(glob.glob(os.path.join(ROOT, "sim5_b200", "variants", "*.so"))) or [os.path.join(ROOT, "sim5_b200", "libsim5b200.so")]
