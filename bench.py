@@ -272,13 +272,14 @@ def run_ours(args):
             except Exception as e:  # the checker is optional for the benchmark itself
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
         f_rr = F_ALG_AZ_RR if args.exact_azimuth else F_ALG_AZ_FAST
-        flop_step = F_ALG_TRACE * (rays_step / world) + f_rr * phase_items[0] + F_ALG_AZ_RR * phase_items[1]     # work of the algorithm actually run
+        flop_step = F_ALG_TRACE * (rays_step / world) + f_rr * (phase_items[0] + (0 if args.exact_azimuth else phase_items[1])) \
+            + (F_ALG_AZ_RR * phase_items[1] if args.exact_azimuth else 0)      # work of the algorithm actually run
         achieved_step = flop_step / (kernel_ms * 1e-3) / 1e12
         ph = [v / args.steps for v in phase_ms]
         dom = max(range(3), key=lambda i: ph[i])
-        knames = ("k_trace_eqplane<DEFER>", "k_azimuth<RR>" if args.exact_azimuth else "k_azimuth_fast", "k_azimuth<RC>")
+        knames = ("k_trace_eqplane<DEFER>", "k_azimuth<RR>", "k_azimuth<RC>") if args.exact_azimuth else ("k_trace_eqplane<DEFER>", "k_azimuth_fast", "k_azimuth<RR|RC> redo")
         if dom == 1:
-            units, per_unit, what = phase_items[0], f_rr, "RR disk hits"
+            units, per_unit, what = (phase_items[0], f_rr, "RR disk hits") if args.exact_azimuth else (phase_items[0] + phase_items[1], f_rr, "RR+RC disk hits")
         elif dom == 0:
             units, per_unit, what = rays_step // world, F_ALG_TRACE, "rays"
         else:

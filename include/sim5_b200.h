@@ -213,9 +213,9 @@ int  sim5_trace_image(const sim5_image_params* p, const sim5_image_out* out, sim
 
 /* device time in ms of each kernel of the most recent sim5_trace_image call (CUDA events on the launch stream; waits for
  * the call to finish, so it also works after SIM5_FLAG_ASYNC): ms[0] trace kernel (phase A), ms[1] azimuth of the RR
- * geodesics (tolerance-mode kernel + its redo pass, or the bit-faithful kernel), ms[2] azimuth of the RC geodesics; items
- * (may be NULL): [0] RR and [1] RC disk hits the azimuth kernels integrated.  Returns the number of kernels the call
- * launched (1, 3 or 4), <0 on error. */
+ * and RC hits by the tolerance-mode kernel (default) or of the RR hits by the bit-faithful kernel (SIM5_FLAG_EXACT_AZIMUTH),
+ * ms[2] the bit-faithful redo passes (default; normally empty lists) or the bit-faithful RC kernel; items (may be NULL):
+ * [0] RR and [1] RC disk hits integrated.  Returns the number of kernels the call launched (1, 3 or 4), <0 on error. */
 int  sim5_last_phase_ms(double* ms, int n, int64_t* items);
 
 /* FP64 DFMA-chain microbenchmark: returns measured TFLOP/s (2 flop per DFMA) of the device, <0 on error.

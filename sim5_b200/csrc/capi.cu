@@ -474,14 +474,25 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
             int g_rc = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RC>, S5_AZ_THREADS);
             if (p->flags & SIM5_FLAG_EXACT_AZIMUTH) {
                 s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 1, 0);
+                if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
+                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 2, 0);
             } else {
-                int g_f = persistent_grid(s5::k_azimuth_fast, S5_AZF_THREADS);
-                s5::k_azimuth_fast<<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
-                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 1, 1);   /* the redo list (normally empty) */
+#if defined(S5_AZF_MERGED)
+                int g_f = persistent_grid(s5::k_azimuth_fast<0>, S5_AZF_THREADS);
+                s5::k_azimuth_fast<0><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
+#else
+                int g_f = persistent_grid(s5::k_azimuth_fast<1>, S5_AZF_THREADS);
+                s5::k_azimuth_fast<1><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
+                g_f = persistent_grid(s5::k_azimuth_fast<2>, S5_AZF_THREADS);
+                s5::k_azimuth_fast<2><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
+                launches += 1;
+#endif
+                if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
+                /* the redo lists (normally empty, a few dozen items at 4096^2): bit-faithful kernels */
+                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 1, 1);
+                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 2, 1);
                 launches += 1;
             }
-            if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
-            s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 2, 0);
             if (ch == 0) CK(cudaEventRecord(c.evp[2], c.stream));
             launches += 2;
         } else {

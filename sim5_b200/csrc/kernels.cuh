@@ -40,8 +40,8 @@ struct DevStats {                 /* device-side counters, flushed once per CTA 
 struct AzQueue {
     double* f;                    /* [S5_AZ_NFIELDS][cap] */
     unsigned long long* key;      /* [cap]: bits 0..47 output index, bits 48..51 nrr, bit 56 rf_ok */
-    unsigned long long* count;    /* [0] RR items, [1] RC items, [2] RR items the tolerance-mode kernel handed back (redo list) */
-    unsigned* redo;               /* [cap] slots of those items */
+    unsigned long long* count;    /* [0] RR items, [1] RC items, [2] RR / [3] RC items the tolerance-mode kernel handed back (redo lists) */
+    unsigned* redo;               /* [cap] slots of those items: RR from the front, RC from the back */
     long long cap;                /* 0: no queue -> the azimuth is computed inline by phase A */
 };
 
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(S5_AZ_THREADS, 1)
 k_azimuth(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double* __restrict__ phi, unsigned long long* __restrict__ tile_counter, int from_redo)
 {
     __shared__ unsigned long long s_base;
-    const long long count = (long long)q.count[from_redo ? 2 : (TYPE == GEOD_TYPE_RR ? 0 : 1)];
+    const long long count = (long long)q.count[(from_redo ? 2 : 0) + (TYPE == GEOD_TYPE_RR ? 0 : 1)];
     const long long cap = q.cap;
     const double a_eff = fmax(1e-4, gconsts.a);
     const double cos_i = gconsts.cos_i;
@@ -188,7 +188,8 @@ k_azimuth(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double* __re
         const bool valid = it < count;
         if (!valid) it = count - 1;          /* every thread runs the routine (it has barriers); the surplus ones redo the last item */
         {
-            long long slot = from_redo ? (long long)q.redo[it] : ((TYPE == GEOD_TYPE_RR) ? it : cap - 1 - it);
+            long long slot = (TYPE == GEOD_TYPE_RR) ? it : cap - 1 - it;
+            if (from_redo) slot = (long long)q.redo[slot];
             const double* f = q.f + slot;
             AzIn z;
             z.e0 = f[0 * cap];  z.e1 = f[1 * cap];  z.e2 = f[2 * cap];   z.e3 = f[3 * cap];
@@ -206,40 +207,52 @@ k_azimuth(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double* __re
     }
 }
 
-/* phase B, tolerance mode (the default): azimuth of the queued RR hits with azimuth_fast_rr (pixel.cuh).  The routine is
- * ~20 KB of SASS, so free-running warps stay inside the instruction cache and no CTA barriers are needed; items cost the
- * same to within one duplication step, so a static grid-stride split is balanced.  Items whose arguments leave the fast
- * routines' domain are appended to the redo list and integrated by k_azimuth<RR> afterwards. */
+/* phase B, tolerance mode (the default): azimuth of the queued hits with azimuth_fast_rr / azimuth_fast_rc (pixel.cuh).
+ * One launch covers both queues (RR items 0..n_rr-1 from the front, then the RC items from the back; a warp is of one
+ * type except the single warp at the boundary).  The routines are ~20 KB of SASS each, so free-running warps stay inside
+ * the instruction cache and no CTA barriers are needed; items of a type cost the same to within one duplication step, so
+ * a static grid-stride split is balanced.  Items whose arguments leave the fast routines' domain go to the redo lists and
+ * are integrated by the bit-faithful k_azimuth<TYPE> afterwards. */
 #ifndef S5_AZF_THREADS
 #define S5_AZF_THREADS 256        /* r01f sweep (profiles/r01f_sweep.log): 256 x 2 CTAs/SM 3.14 ms, 128 x 4 3.32, 128 x 6 (80 regs, spills) 3.31, 128 x 3 3.46 */
 #endif
 #ifndef S5_MIN_CTAS_AZF
 #define S5_MIN_CTAS_AZF 2
 #endif
+/* WHICH: 0 both queues in one launch, 1 the RR queue only, 2 the RC queue only */
+template <int WHICH>
 __global__ void __launch_bounds__(S5_AZF_THREADS, S5_MIN_CTAS_AZF)
 k_azimuth_fast(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double* __restrict__ phi)
 {
-    const long long count = (long long)q.count[0];
+    const long long n_rr = (WHICH == 2) ? 0 : (long long)q.count[0];
+    const long long count = n_rr + ((WHICH == 1) ? 0 : (long long)q.count[1]);
     const long long cap = q.cap;
     const double a_eff = fmax(1e-4, gconsts.a);
     const double cos_i = gconsts.cos_i;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < count; it += stride) {
-        const double* f = q.f + it;
+        const bool is_rr = (WHICH == 1) || (WHICH == 0 && it < n_rr);
+        const long long slot = is_rr ? it : cap - 1 - (it - n_rr);
+        const double* f = q.f + slot;
         AzIn z;
         z.e0 = f[0 * cap];  z.e1 = f[1 * cap];  z.e2 = f[2 * cap];   z.e3 = f[3 * cap];
         z.l = f[4 * cap];   z.m2m = f[5 * cap]; z.m2p = f[6 * cap];  z.mm = f[7 * cap];
         z.Tpp = f[8 * cap]; z.Tip = f[9 * cap]; z.Rpc = f[10 * cap]; z.beta = f[11 * cap];
         z.K_mm = f[12 * cap]; z.rf_u = 0.0; z.isn_inf = 0.0; z.r = f[15 * cap]; z.P = f[16 * cap];
-        unsigned long long key = q.key[it];
+        unsigned long long key = q.key[slot];
         z.a = a_eff; z.cos_i = cos_i;
-        z.type = GEOD_TYPE_RR;
+        z.type = is_rr ? GEOD_TYPE_RR : GEOD_TYPE_RC;
         z.nrr = (int)((key >> 48) & 15);
         z.rf_ok = false;
         bool ok;
-        double v = azimuth_fast_rr(z, &ok);
-        if (ok) phi[key & 0xffffffffffffULL] = v;
-        else q.redo[atomicAdd(&q.count[2], 1ULL)] = (unsigned)it;
+        double v = is_rr ? azimuth_fast_rr(z, &ok) : azimuth_fast_rc(z, &ok);
+        if (ok) {
+            phi[key & 0xffffffffffffULL] = v;
+        } else if (is_rr) {
+            q.redo[atomicAdd(&q.count[2], 1ULL)] = (unsigned)slot;
+        } else {
+            q.redo[cap - 1 - (long long)atomicAdd(&q.count[3], 1ULL)] = (unsigned)slot;
+        }
     }
 }
 

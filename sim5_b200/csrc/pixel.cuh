@@ -271,17 +271,65 @@ S5_HD S5_INL double azimuth_equatorial(const Geodesic* g, const RayCache& k, dou
     return azimuth_from(z);
 }
 S5_HD S5_MID double azimuth_fast_rr(const AzIn& z, bool* ok);
+S5_HD S5_MID double azimuth_fast_rc(const AzIn& z, bool* ok);
 /* the azimuth as the image kernels compute it by default: tolerance mode for RR hits, bit-faithful for everything else */
 S5_HD S5_INL double azimuth_equatorial_default(const Geodesic* g, const RayCache& k, double r, double P)
 {
     AzIn z;
     az_make(g, k, r, P, &z);
-    if (z.type == GEOD_TYPE_RR) {
+    if (z.type == GEOD_TYPE_RR || z.type == GEOD_TYPE_RC) {
         bool ok;
-        double v = azimuth_fast_rr(z, &ok);
+        double v = (z.type == GEOD_TYPE_RR) ? azimuth_fast_rr(z, &ok) : azimuth_fast_rc(z, &ok);
         if (ok) return v;
     }
     return azimuth_from(z);
+}
+
+/* polar part of the azimuth in tolerance mode: integral_T_mp(m2m, m2p, 1, X) for X = 0 and X = cos_i (sim5elliptic.c:1142-1159)
+ * and the turning-point bookkeeping of geodesic_position_azm (sim5kerr-geod.c:528-553) for an equatorial hit */
+S5_HD S5_MID double azimuth_fast_polar(const AzIn& z, bool* ok)
+{
+    bool good = true;
+    double phi = 0.0;
+    double msum = z.m2m + z.m2p;
+    double tm = z.m2p / msum;
+    double tn = z.m2p / (z.m2p - 1.0);
+    double tpre = 1. / sqrt(msum) / (1.0 - z.m2p);
+    double qc = 1.0 - tm, pc = 1.0 - tn;
+    double cu = z.cos_i / sqrt(z.m2p);
+    double cu2 = cu * cu;
+    double ns2 = -tn * (1.0 - cu2);
+    double qu = 1.0 - (1.0 - cu2) * tm;
+    double pu = 1.0 + ns2;
+    bool gp = (z.cos_i > 0.0) && (cu2 < 1.0) && (tm < 1.0) && !(tn == 1.0) && hi_domain(0.0, qc, 1.0) && hi_domain_p(pc) && hi_domain(cu2, qu, 1.0) && hi_domain_p(pu);
+    if (!gp) { qc = pc = cu2 = qu = pu = 1.0; good = false; }
+    double rfK = (tm == z.mm) ? z.K_mm : rf_hi(0.0, qc, 1.0);
+    double comp = rfK + tn * rj_hi(0.0, qc, 1.0, pc) * (1.0 / 3.0);
+    double Fu, Ju;
+    rfj_hi<1, true>(cu2, qu, 1.0, &pu, &Fu, &Ju);
+    double vu = sqrt(1.0 - cu2) * (Fu - ns2 * Ju * (1.0 / 3.0));
+    double la = z.l / z.a;
+    double T0 = tpre * comp;
+    double phi_pp = 2.0 * la * T0;
+    double phi_mp = la * T0;
+    double phi_ip = la * (tpre * vu);
+
+    double T;
+    double sign_dm = (z.beta >= 0.0) ? +1.0 : -1.0;
+    if (sign_dm > 0.0) {
+        T = -(z.Tpp - z.Tip);
+        phi -= phi_pp - phi_ip;
+    } else {
+        T = -z.Tip;
+        phi -= phi_ip;
+    }
+    if (z.P >= T + z.Tpp) {
+        phi += phi_pp;
+        sign_dm = -sign_dm;
+    }
+    phi += (sign_dm < 0) ? phi_mp : phi_pp - phi_mp;
+    *ok = good;
+    return phi;
 }
 
 /*
@@ -346,46 +394,131 @@ S5_HD S5_MID double azimuth_fast_rr(const AzIn& z, bool* ok)
     double B = pre / (rm - a) * ((1. / c2m) * (((c2m - aa2) * Pinf_m + aa2 * u_inf) + sgn * ((c2m - aa2) * Pr_m + aa2 * u_r)));
     double phi = 1. / sq1 * (A * (z.a * rp - z.l * a2 / 2.) - B * (z.a * rm - z.l * a2 / 2.));
 
-    /* polar part: integral_T_mp(m2m, m2p, 1, X) for X = 0 and X = cos_i (sim5elliptic.c:1142-1159) */
-    double msum = z.m2m + z.m2p;
-    double tm = z.m2p / msum;
-    double tn = z.m2p / (z.m2p - 1.0);
-    double tpre = 1. / sqrt(msum) / (1.0 - z.m2p);
-    double qc = 1.0 - tm, pc = 1.0 - tn;
-    double cu = z.cos_i / sqrt(z.m2p);
-    double cu2 = cu * cu;
-    double ns2 = -tn * (1.0 - cu2);
-    double qu = 1.0 - (1.0 - cu2) * tm;
-    double pu = 1.0 + ns2;
-    bool gp = (z.cos_i > 0.0) && (cu2 < 1.0) && (tm < 1.0) && !(tn == 1.0) && hi_domain(0.0, qc, 1.0) && hi_domain_p(pc) && hi_domain(cu2, qu, 1.0) && hi_domain_p(pu);
-    if (!gp) { qc = pc = cu2 = qu = pu = 1.0; good = false; }
-    double rfK = (tm == z.mm) ? z.K_mm : rf_hi(0.0, qc, 1.0);
-    double comp = rfK + tn * rj_hi(0.0, qc, 1.0, pc) * (1.0 / 3.0);
-    double Fu, Ju;
-    rfj_hi<1, true>(cu2, qu, 1.0, &pu, &Fu, &Ju);
-    double vu = sqrt(1.0 - cu2) * (Fu - ns2 * Ju * (1.0 / 3.0));
-    double la = z.l / z.a;
-    double T0 = tpre * comp;
-    double phi_pp = 2.0 * la * T0;
-    double phi_mp = la * T0;
-    double phi_ip = la * (tpre * vu);
-
-    double T;
-    double sign_dm = (z.beta >= 0.0) ? +1.0 : -1.0;
-    if (sign_dm > 0.0) {
-        T = -(z.Tpp - z.Tip);
-        phi -= phi_pp - phi_ip;
-    } else {
-        T = -z.Tip;
-        phi -= phi_ip;
-    }
-    if (z.P >= T + z.Tpp) {
-        phi += phi_pp;
-        sign_dm = -sign_dm;
-    }
-    phi += (sign_dm < 0) ? phi_mp : phi_pp - phi_mp;
+    bool okp;
+    phi += azimuth_fast_polar(z, &okp);
+    good = good && okp;
     *ok = good;
     return good ? phi : NAN;
+}
+
+/* Cauchy principal value of R_J for p < 0 on top of the shared sequence: R_J(x,y,z,p) = a (b R_J(x,y,z,pt) + 3 (R_C(rho,tau) - R_F(x,y,z)))
+ * with x <= y <= z (sim5elliptic.c:166-177, 204).  pv_prepare turns p into the positive pt the sequence is run with. */
+struct PvTerm { double a, b, rcx; bool neg; };
+S5_HD S5_INL double pv_prepare(double x, double y, double z, double p, PvTerm* t)
+{
+    t->neg = !(p > 0.0);
+    if (!t->neg) { t->a = t->b = t->rcx = 0.0; return p; }
+    t->a = 1.0 / (y - p);
+    t->b = t->a * (z - y) * (y - x);
+    double pt = y + t->b;
+    double rho = x * z / y;
+    double tau = p * pt / y;                       /* < 0: R_C(rho, tau) = sqrt(rho / (rho - tau)) R_C(rho - tau, -tau) */
+    double xs = rho - tau;
+    t->rcx = (rho > 0.0) ? sqrt(rho / xs) * rc_hi(xs, -tau) : 0.0;
+    return pt;
+}
+S5_HD S5_INL double pv_finish(double J, double F, const PvTerm& t) { return t.neg ? t.a * (t.b * J + 3.0 * (t.rcx - F)) : J; }
+
+/*
+ * Tolerance-mode azimuth of an RC disk hit (two real roots a > b and the pair u +- iv): B&F 260.04 and 341.03 as the
+ * reference combines them (sim5elliptic.c:1081-1112, 755-792), with the same economies as azimuth_fast_rr: the amplitudes
+ * cn at r and at infinity are the algebraic arguments of elliptic_f_cos themselves, F and the Pi of both poles share one
+ * duplication sequence per limit, the complete integrals are evaluated only when the two limits lie on different sides
+ * of cn = 0, and the complex f1 term of integral_R1 is spelled as the real atan / log it reduces to.
+ */
+S5_HD S5_MID double azimuth_fast_rc(const AzIn& z, bool* ok)
+{
+    const double r = z.r;
+    double a2s = sq(z.a);
+    double sq1 = sqrt(1. - a2s);
+    double rpm[2] = {1. + sq1, 1. - sq1};
+    double a = z.e0, b = z.e1, u = z.e2, v2 = sq(z.e3);
+    double A_ = sqrt(sq(a - u) + v2), B_ = sqrt(sq(b - u) + v2);
+    double m = (sq(A_ + B_) - sq(a - b)) / (4. * A_ * B_);
+    double g = 1. / sqrt(A_ * B_);
+    double alpha2 = (B_ + A_) / (B_ - A_);
+    double cl[2] = {(r * (A_ - B_) + a * B_ - b * A_) / (r * (A_ + B_) - a * B_ - b * A_), (A_ - B_) / (A_ + B_)};   /* cn at r, at infinity */
+    bool good = (m > 0.0) && (m < 1.0) && (cl[0] != 0.0) && (cl[1] != 0.0);
+    double alpha1[2], nn[2], mma[2];
+    #pragma unroll
+    for (int k = 0; k < 2; k++) {
+        double p = rpm[k];
+        alpha1[k] = (B_ * a + b * A_ - p * A_ - p * B_) / (B_ * a - b * A_ + p * A_ - p * B_);
+        double al2 = sq(alpha1[k]);
+        nn[k] = al2 / (al2 - 1.);
+        mma[k] = (m + (1. - m) * al2) / (1. - al2);
+        good = good && (nn[k] == nn[k]) && (fabs(nn[k]) < 1e18) && (nn[k] != 1.0);
+    }
+    /* per limit: F(|c|) and the two Pi(|c|, n_k), f1 */
+    double Fh[2], Ph[2][2], f1[2][2];
+    #pragma unroll
+    for (int j = 0; j < 2; j++) {
+        double c = fabs(cl[j]);
+        double c2 = c * c, s2 = 1.0 - c2;
+        double q = 1.0 - s2 * m;
+        double pp[2] = {1.0 - nn[0] * s2, 1.0 - nn[1] * s2};
+        bool gj = (c2 < 1.0) && hi_domain(c2, q, 1.0) && (pp[0] != 0.0) && (pp[1] != 0.0) && hi_domain_p(fabs(pp[0])) && hi_domain_p(fabs(pp[1]));
+        if (!gj) { c2 = q = 1.0; s2 = 0.0; pp[0] = pp[1] = 1.0; good = false; }
+        PvTerm t0, t1;
+        double pt[2] = {pv_prepare(c2, q, 1.0, pp[0], &t0), pv_prepare(c2, q, 1.0, pp[1], &t1)};
+        if (!(hi_domain_p(pt[0]) && hi_domain_p(pt[1]))) { pt[0] = pt[1] = 1.0; good = false; }
+        double F, J[2];
+        rfj_hi<2, true>(c2, q, 1.0, pt, &F, J);
+        double s = sqrt(s2), dn = sqrt(q);
+        Fh[j] = s * F;
+        Ph[j][0] = s * (F + nn[0] * s2 * pv_finish(J[0], F, t0) * (1.0 / 3.0));
+        Ph[j][1] = s * (F + nn[1] * s2 * pv_finish(J[1], F, t1) * (1.0 / 3.0));
+        #pragma unroll
+        for (int k = 0; k < 2; k++) {
+            double am = fabs(mma[k]);
+            if (am > 1e-5) {
+                double sm = sqrt(am);
+                double y = sm * s / dn;
+                f1[j][k] = (mma[k] > 0.0) ? atan(y) / sm : -0.5 * log(fabs((1.0 + y) / (1.0 - y))) / sm;
+            } else {
+                f1[j][k] = s / dn;
+            }
+        }
+    }
+    /* complete integrals, needed when the limits straddle cn = 0 */
+    bool straddle = (cl[0] >= 0.0) != (cl[1] >= 0.0);
+    double Kc = 0.0, Pc[2] = {0.0, 0.0};
+    if (straddle) {
+        double qc = 1.0 - m;
+        double pp[2] = {1.0 - nn[0], 1.0 - nn[1]};
+        bool gc = hi_domain(0.0, qc, 1.0) && (pp[0] != 0.0) && (pp[1] != 0.0) && hi_domain_p(fabs(pp[0])) && hi_domain_p(fabs(pp[1]));
+        if (!gc) { qc = 1.0; pp[0] = pp[1] = 1.0; good = false; }
+        PvTerm t0, t1;
+        double pt[2] = {pv_prepare(0.0, qc, 1.0, pp[0], &t0), pv_prepare(0.0, qc, 1.0, pp[1], &t1)};
+        if (!(hi_domain_p(pt[0]) && hi_domain_p(pt[1]))) { pt[0] = pt[1] = 1.0; good = false; }
+        double J[2];
+        rfj_hi<2, true>(0.0, qc, 1.0, pt, &Kc, J);
+        Pc[0] = Kc + nn[0] * pv_finish(J[0], Kc, t0) * (1.0 / 3.0);
+        Pc[1] = Kc + nn[1] * pv_finish(J[1], Kc, t1) * (1.0 / 3.0);
+    }
+    /* u(c) = F_cos(c): F(|c|) or 2K - F(|c|); Pi_cos alike.  index 0 = at r (u1), 1 = at infinity (u2) */
+    double uu[2], AB[2];
+    #pragma unroll
+    for (int j = 0; j < 2; j++) uu[j] = (cl[j] >= 0.0) ? Fh[j] : 2.0 * Kc - Fh[j];
+    /* when both limits are on the negative side the 2K (2 Pi_c) terms cancel in the differences: Kc = Pc = 0 above is then exact */
+    #pragma unroll
+    for (int k = 0; k < 2; k++) {
+        double p = rpm[k];
+        double R1v[2];
+        #pragma unroll
+        for (int j = 0; j < 2; j++) {
+            double Pi = (cl[j] > 0.0) ? Ph[j][k] : ((cl[j] == 0.0) ? Pc[k] : 2.0 * Pc[k] - Ph[j][k]);
+            R1v[j] = 1. / (1. - sq(alpha1[k])) * (Pi + alpha1[k] * f1[j][k]);
+        }
+        double t0 = alpha2 * (uu[1] - uu[0]);
+        double t1 = (alpha1[k] - alpha2) * (R1v[1] - R1v[0]);
+        AB[k] = (B_ - A_) * g / (B_ * a + b * A_ - p * A_ - p * B_) * (t0 + t1);
+    }
+    double phi = 1. / sq1 * (AB[0] * (z.a * rpm[0] - z.l * a2s / 2.) - AB[1] * (z.a * rpm[1] - z.l * a2s / 2.));
+    bool okp;
+    phi += azimuth_fast_polar(z, &okp);
+    *ok = good && okp;
+    return *ok ? phi : NAN;
 }
 
 /* emission-side quantities of the polarized mode for a disk hit at (r, m=0), position parameter P */

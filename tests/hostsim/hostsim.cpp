@@ -82,6 +82,36 @@ long hs_azimuth_mismatches(const sim5_image_params* p)
     return bad;
 }
 
+// tolerance-mode azimuth coverage: counts[0] RR hits, [1] of them handed back to the bit-faithful path, [2] RC hits, [3] handed back
+void hs_fast_azimuth_coverage(const sim5_image_params* p, long* counts)
+{
+    S5ImageConsts c;
+    s5_fill_image_consts(p, &c);
+    long n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+    #pragma omp parallel for schedule(dynamic, 4) reduction(+:n0,n1,n2,n3)
+    for (int iy = 0; iy < c.ny; iy++) {
+        for (int ix = 0; ix < c.nx; ix++) {
+            double alpha, beta;
+            pixel_impact(c, ix, iy, &alpha, &beta);
+            Geodesic gd; int err = 0; RayCache k;
+            if (!init_inf_cached(c, alpha, beta, &gd, &err, &k)) continue;
+            for (int order = 0; order <= c.max_order; order++) {
+                double P = crossing_cached(&gd, order, k);
+                if (isnan(P)) break;
+                double r = geodesic_position_rad(&gd, P);
+                if (!(r >= c.rmin_emit)) continue;
+                AzIn z;
+                az_make(&gd, k, r, P, &z);
+                bool ok = true;
+                if (gd.type == GEOD_TYPE_RR) { azimuth_fast_rr(z, &ok); n0++; n1 += !ok; }
+                else if (gd.type == GEOD_TYPE_RC) { azimuth_fast_rc(z, &ok); n2++; n3 += !ok; }
+                break;
+            }
+        }
+    }
+    counts[0] = n0; counts[1] = n1; counts[2] = n2; counts[3] = n3;
+}
+
 double hs_trace_image(const sim5_image_params* p, const sim5_image_out* out, int nthreads)
 {
     S5ImageConsts c;
