@@ -115,7 +115,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": config_dict(args.gpus, 4096),
+        "data": "synthetic", "config": config_dict(args.gpus, 4096, args.gather),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -124,10 +124,13 @@ def run_reference(args):
     return 0
 
 
-def config_dict(n_gpus, n):
+def config_dict(n_gpus, n, gather="peer"):
     return {"workload": "BASELINE configs[1]: Novikov-Thorne thin-disk image %dx%d, a=0.998, i=75deg, rmax=r_ms+20, "
                         "outputs r/phi/g/F*g^4/status, crossing orders 0-1" % (n, n),
-            "rays_per_step": n * n, "parallelism": "rows interleaved over %d GPU(s) in 32-row blocks, NCCL gather to rank 0" % n_gpus,
+            "rays_per_step": n * n,
+            "parallelism": ("one GPU, whole image" if n_gpus == 1 else
+                            "rows interleaved over %d GPUs in 32-row blocks; %s" % (n_gpus, "every rank stores its rows into rank 0's image planes over NVLink peer memory (CUDA IPC), barrier at the end"
+                                                                                    if gather == "peer" else "NCCL gather of compact planes to rank 0 + re-assembly")),
             "l2": "no input reads (rays are generated from the pixel index); %d MB of output planes per step > 126 MB L2" % (n * n * BYTES_PER_RAY // 1000000),
             "e2e_note": "each rank copies its own rows to its own pinned host planes" if n_gpus > 1 else "pinned host planes"}
 
@@ -160,15 +163,32 @@ def run_ours(args):
     rows = sdist.apply_split(p, rank, world) if world > 1 else n
     p.flags = abi.FLAG_DEVICE_PTRS | abi.FLAG_ASYNC | (abi.FLAG_EXACT_AZIMUTH if args.exact_azimuth else 0)
     names = ("r", "phi", "g", "flux")
-    loc = {k: torch.empty((rows, n), dtype=torch.float64, device=dev) for k in names}
-    loc["status"] = torch.empty((rows, n), dtype=torch.uint8, device=dev)
-    out = abi.ImageOut()
-    for k, t in loc.items():
-        setattr(out, k, t.data_ptr())
-    gath = None
-    if world > 1 and rank == 0:
-        gath = {k: [torch.empty_like(t) for _ in range(world)] for k, t in loc.items()}
+    peer = world > 1 and args.gather == "peer"
     st = abi.TraceStats()
+    gath = None
+    if peer:
+        # the image lives in rank 0's HBM; every rank maps those planes (CUDA IPC, peer access over NVLink/NVSwitch) and its
+        # kernels store their interleaved row blocks straight into the final image: the transfer rides under the FP64 work,
+        # there is no gather and no re-assembly pass
+        p.flags |= abi.FLAG_FULL_INDEX
+        if rank == 0:
+            image = api.DevicePlanes(p)
+            blob = [image.handles()]
+        else:
+            image, blob = None, [None]
+        dist.broadcast_object_list(blob, src=0)
+        if rank != 0:
+            image = api.DevicePlanes.from_handles(p, blob[0])
+        out = image.out
+        loc = None
+    else:
+        loc = {k: torch.empty((rows, n), dtype=torch.float64, device=dev) for k in names}
+        loc["status"] = torch.empty((rows, n), dtype=torch.uint8, device=dev)
+        out = abi.ImageOut()
+        for k, t in loc.items():
+            setattr(out, k, t.data_ptr())
+        if world > 1 and rank == 0:
+            gath = {k: [torch.empty_like(t) for _ in range(world)] for k, t in loc.items()}
     kev = []
     phase_ms = [0.0, 0.0, 0.0]      # summed device time of k_trace_eqplane, k_azimuth<RR>, k_azimuth<RC> over the timed steps
     phase_items = [0, 0]            # RR / RC disk hits integrated by the azimuth kernels (per step)
@@ -188,7 +208,7 @@ def run_ours(args):
                 phase_ms[i] += v
             phase_items[0], phase_items[1] = items
             launches[0] += nk
-        if world > 1:
+        if world > 1 and not peer:
             full = None
             for k, t in loc.items():
                 dist.gather(t, gath[k] if rank == 0 else None, dst=0)
@@ -238,6 +258,8 @@ def run_ours(args):
     if world > 1:
         sdist.apply_split(ph, rank, world)
     hp = api.HostPlanes(ph, pinned=True)
+    for a in hp.arrays.values():
+        a[...] = 0                      # at N>1 a rank fills only its own rows
     for _ in range(2):
         api.trace_image(ph, hp)
     fence()
@@ -252,7 +274,16 @@ def run_ours(args):
     fence()
     clocks = sampler.stop() if sampler else None
     e2e_value = rays_step * args.steps / float(e2e_s.item())
-    checksum = float(hp["g"].sum())
+    cs = torch.tensor([float(hp["g"].sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)      # every rank's own rows -> checksum of the whole image
+    checksum = float(cs.item())
+    image_check = None
+    if peer and rank == 0:
+        # the image the ranks assembled in rank 0's HBM through peer stores, against the host-API result of all ranks
+        dev_sum = float(image.to_host("g").sum())
+        image_check = {"sum_g_device_image": dev_sum, "sum_g_host_api": checksum, "rel_diff": abs(dev_sum - checksum) / max(abs(checksum), 1e-300)}
+        assert image_check["rel_diff"] < 1e-12, image_check
 
     if rank == 0:
         # CPU baseline beside it (N=1 only): the unmodified reference on the host cores, bounded sample
@@ -294,9 +325,9 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config_dict(world, n),
+            "dtype": "f64", "data": "synthetic", "config": config_dict(world, n, args.gather),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(abi.ImageParams),
-                    "d2h_bytes_per_step": (rays_step // world) * BYTES_PER_RAY, "checksum_g": checksum},
+                    "d2h_bytes_per_step": (rays_step // world) * BYTES_PER_RAY, "checksum_g": checksum, "peer_image_check": image_check},
             "gpu_launches": launches[0] * world,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf if (peak_tf and achieved) else None, "traffic": traffic,
@@ -314,6 +345,13 @@ def run_ours(args):
         }
         print(json.dumps(line))
     if world > 1:
+        if peer:
+            fence()
+            if rank != 0:
+                image.close()
+            fence()
+            if rank == 0:
+                image.close()
         dist.destroy_process_group()
     return 0
 
@@ -326,6 +364,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=4096, help="image side (default: the BASELINE 4096)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N>1: 'peer' = every rank stores its rows into rank 0's image over NVLink peer memory (default); "
+                         "'nccl' = compact planes + torch.distributed gather + re-assembly on rank 0 (A/B)")
     ap.add_argument("--exact-azimuth", action="store_true", help="A/B: bit-faithful azimuth kernels (SIM5_FLAG_EXACT_AZIMUTH) instead of the tolerance-mode default")
     args = ap.parse_args()
     if args.impl == "reference":

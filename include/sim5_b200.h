@@ -65,6 +65,9 @@ extern "C" {
                                         series, same bits as its CPU path) instead of the default tolerance-mode kernel, which evaluates the same
                                         integrals to ~1e-14 with the 7th-order series in fewer steps.  r, g, flux and every status flag are
                                         bit-faithful in both modes. */
+#define SIM5_FLAG_FULL_INDEX    0x40 /* with DEVICE_PTRS and split_count > 1: the planes are FULL-image planes (index iy*nx+ix) instead of this call's
+                                        compact rows -- e.g. the peer-mapped planes of the rank that assembles the image (sim5_ipc_import), so
+                                        every GPU stores its rows directly into the final image over NVLink and no gather is needed */
 #define SIM5_FLAG_ASYNC         0x4  /* with DEVICE_PTRS: enqueue on the library stream (sim5_set_stream) and return without
                                         synchronising; stats are not filled.  Pair with sim5_synchronize(). */
 
@@ -204,6 +207,11 @@ void  sim5_host_free(void* p);
 void* sim5_device_alloc(size_t bytes);
 void  sim5_device_free(void* p);
 int   sim5_device_to_host(void* dst, const void* src, size_t bytes);
+/* CUDA IPC for one-process-per-GPU jobs on one node: export a sim5_device_alloc'd plane as a 64-byte handle, import it in
+ * another process (peer access over NVLink is enabled on first use), release the mapping before the owner frees the plane */
+int   sim5_ipc_export(const void* device_ptr, void* handle64);
+void* sim5_ipc_import(const void* handle64);
+int   sim5_ipc_release(void* imported_ptr);
 
 /* defaults: fills every field with the SURVEY.md 8(d) definition of BASELINE config `cfg` (1..5) */
 int  sim5_default_params(int cfg, sim5_image_params* p);

@@ -47,6 +47,12 @@ def lib():
         L.sim5_device_free.argtypes = [C.c_void_p]
         L.sim5_device_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.sim5_device_to_host.restype = C.c_int
+        L.sim5_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+        L.sim5_ipc_export.restype = C.c_int
+        L.sim5_ipc_import.argtypes = [C.c_void_p]
+        L.sim5_ipc_import.restype = C.c_void_p
+        L.sim5_ipc_release.argtypes = [C.c_void_p]
+        L.sim5_ipc_release.restype = C.c_int
         L.sim5_default_params.argtypes = [C.c_int, C.POINTER(abi.ImageParams)]
         L.sim5_default_params.restype = C.c_int
         L.sim5_trace_image.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(abi.ImageOut), C.POINTER(abi.TraceStats)]
@@ -155,6 +161,61 @@ def trace_image_device(p, out_struct):
     st = abi.TraceStats()
     check(lib().sim5_trace_image(C.byref(p), C.byref(out_struct), C.byref(st)), "sim5_trace_image")
     return st
+
+
+class DevicePlanes:
+    """Full-image output planes in DEVICE memory owned by this process (sim5_device_alloc), exportable to the other
+    ranks of a one-process-per-GPU job as CUDA IPC handles (peer-mapped planes: every rank stores its rows into them)."""
+
+    def __init__(self, p, names=("r", "phi", "g", "flux", "status")):
+        self.n = p.nx * p.ny
+        self.shape = (p.ny, p.nx)
+        self.ptrs, self.dtypes = {}, {}
+        self.out = abi.ImageOut()
+        for name, bit, ct in abi.PLANES:
+            if name in names and (p.outputs & bit):
+                nbytes = self.n * C.sizeof(ct)
+                ptr = lib().sim5_device_alloc(nbytes)
+                if not ptr:
+                    raise Sim5Error("sim5_device_alloc failed: " + last_error())
+                self.ptrs[name], self.dtypes[name] = ptr, _NP[ct]
+                setattr(self.out, name, ptr)
+        self._owned = True
+
+    def handles(self):
+        hs = {}
+        for name, ptr in self.ptrs.items():
+            buf = C.create_string_buffer(64)
+            check(lib().sim5_ipc_export(C.c_void_p(ptr), buf), "sim5_ipc_export")
+            hs[name] = buf.raw
+        return hs
+
+    @classmethod
+    def from_handles(cls, p, hs):
+        self = cls.__new__(cls)
+        self.n, self.shape = p.nx * p.ny, (p.ny, p.nx)
+        self.ptrs, self.dtypes, self.out, self._owned = {}, {}, abi.ImageOut(), False
+        for name, bit, ct in abi.PLANES:
+            if name in hs:
+                ptr = lib().sim5_ipc_import(C.create_string_buffer(hs[name], 64))
+                if not ptr:
+                    raise Sim5Error("sim5_ipc_import failed: " + last_error())
+                self.ptrs[name], self.dtypes[name] = ptr, _NP[ct]
+                setattr(self.out, name, ptr)
+        return self
+
+    def to_host(self, name):
+        a = np.empty(self.n, dtype=self.dtypes[name])
+        check(lib().sim5_device_to_host(a.ctypes.data, C.c_void_p(self.ptrs[name]), a.nbytes), "sim5_device_to_host")
+        return a
+
+    def close(self):
+        for ptr in self.ptrs.values():
+            if self._owned:
+                lib().sim5_device_free(C.c_void_p(ptr))
+            else:
+                lib().sim5_ipc_release(C.c_void_p(ptr))
+        self.ptrs = {}
 
 
 def _dp(a):

@@ -47,7 +47,8 @@ struct Context {
     bool warned = false;
     int device = -1;
     int sm_count = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, own_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, own_stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;      /* the RC azimuth chain runs on aux_stream beside the RR chain */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     cudaEvent_t evp[3] = {nullptr, nullptr, nullptr};   /* phase boundaries of the last image call: after phase A, after azimuth RR, after azimuth RC */
     cudaEvent_t ev_chunk[S5_MAX_CHUNKS] = {nullptr};      /* chunk k traced -> its device->host copy may start */
@@ -120,6 +121,9 @@ int ensure_init(int device)
     CK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     c.stream = c.own_stream;
     CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c.aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     CK(cudaEventCreate(&c.ev0)); CK(cudaEventCreate(&c.ev1)); CK(cudaEventCreate(&c.ev2)); CK(cudaEventCreate(&c.ev3));
     for (int i = 0; i < 3; i++) CK(cudaEventCreate(&c.evp[i]));
     for (int i = 0; i < S5_MAX_CHUNKS; i++) CK(cudaEventCreateWithFlags(&c.ev_chunk[i], cudaEventDisableTiming));
@@ -279,7 +283,8 @@ extern "C" void sim5_gpu_shutdown(void)
     for (int i = 0; i < 3; i++) cudaEventDestroy(c.evp[i]);
     for (int i = 0; i < S5_MAX_CHUNKS; i++) cudaEventDestroy(c.ev_chunk[i]);
     cudaEventDestroy(c.ev_copy_done);
-    cudaStreamDestroy(c.own_stream); cudaStreamDestroy(c.copy_stream);
+    cudaStreamDestroy(c.own_stream); cudaStreamDestroy(c.copy_stream); cudaStreamDestroy(c.aux_stream);
+    cudaEventDestroy(c.ev_fork); cudaEventDestroy(c.ev_join);
     c.ready = false;
 }
 
@@ -331,6 +336,33 @@ extern "C" void* sim5_device_alloc(size_t bytes)
     return p;
 }
 extern "C" void sim5_device_free(void* p) { if (p) cudaFree(p); }
+/* CUDA IPC: lets the ranks of a one-process-per-GPU job store their rows straight into the image planes of the rank that
+ * assembles the image (peer memory over NVLink / NVSwitch), instead of gathering compact planes afterwards */
+extern "C" int sim5_ipc_export(const void* device_ptr, void* handle64)
+{
+    if (!device_ptr || !handle64) { set_error("sim5_ipc_export: null argument"); return SIM5_ERR_BAD_PARAM; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void*>(device_ptr)));
+    memcpy(handle64, &h, 64);
+    return SIM5_OK;
+}
+extern "C" void* sim5_ipc_import(const void* handle64)
+{
+    if (!handle64) { set_error("sim5_ipc_import: null handle"); return nullptr; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    if (!cuda_ok(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return nullptr;
+    return p;
+}
+extern "C" int sim5_ipc_release(void* imported_ptr)
+{
+    if (!imported_ptr) return SIM5_OK;
+    CK(cudaIpcCloseMemHandle(imported_ptr));
+    return SIM5_OK;
+}
+
 extern "C" int sim5_device_to_host(void* dst, const void* src, size_t bytes)
 {
     if (ensure_init(-1) != SIM5_OK) return SIM5_ERR_NO_DEVICE;
@@ -406,7 +438,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     bool async = devptr && (p->flags & SIM5_FLAG_ASYNC);
     DevOut d;
     memset(&d, 0, sizeof d);
-    d.compact = (!devptr || split > 1) ? 1 : 0;
+    d.compact = (!devptr || (split > 1 && !(p->flags & SIM5_FLAG_FULL_INDEX))) ? 1 : 0;
     for (int i = 0; i < 12; i++) {
         if (!(p->outputs & kPlaneInfo[i].bit)) continue;
         if (devptr) { set_dev_plane(&d, i, host_plane(out, i)); continue; }
@@ -481,16 +513,26 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                 int g_f = persistent_grid(s5::k_azimuth_fast<0>, S5_AZF_THREADS);
                 s5::k_azimuth_fast<0><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
 #else
+                /* RR chain on the launch stream, RC chain (3 % of the hits) on the auxiliary stream: the two bit-faithful redo
+                 * passes are latency-bound single waves, so they run side by side instead of back to back */
+                CK(cudaEventRecord(c.ev_fork, c.stream));
+                CK(cudaStreamWaitEvent(c.aux_stream, c.ev_fork, 0));
                 int g_f = persistent_grid(s5::k_azimuth_fast<1>, S5_AZF_THREADS);
                 s5::k_azimuth_fast<1><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
                 g_f = persistent_grid(s5::k_azimuth_fast<2>, S5_AZF_THREADS);
-                s5::k_azimuth_fast<2><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
+                s5::k_azimuth_fast<2><<<g_f, S5_AZF_THREADS, 0, c.aux_stream>>>(cc, q, dd.phi);
+                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.aux_stream>>>(cc, q, dd.phi, c.d_counter + 2, 1);
+                CK(cudaEventRecord(c.ev_join, c.aux_stream));
                 launches += 1;
 #endif
                 if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
-                /* the redo lists (normally empty, a few dozen items at 4096^2): bit-faithful kernels */
+                /* the redo list: items outside the fast routines' domain or flagged by the conditioning guard (~0.3 %) */
                 s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 1, 1);
+#if defined(S5_AZF_MERGED)
                 s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 2, 1);
+#else
+                CK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
+#endif
                 launches += 1;
             }
             if (ch == 0) CK(cudaEventRecord(c.evp[2], c.stream));

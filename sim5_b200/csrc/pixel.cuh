@@ -285,18 +285,72 @@ S5_HD S5_INL double azimuth_equatorial_default(const Geodesic* g, const RayCache
     return azimuth_from(z);
 }
 
+/* Cauchy principal value of R_J for p < 0 on top of the shared sequence: R_J(x,y,z,p) = a (b R_J(x,y,z,pt) + 3 (R_C(rho,tau) - R_F(x,y,z)))
+ * with x <= y <= z (sim5elliptic.c:166-177, 204).  pv_prepare turns p into the positive pt the sequence is run with. */
+struct PvTerm { double a, b, rcx; bool neg; };
+S5_HD S5_INL double pv_prepare(double x, double y, double z, double p, PvTerm* t)
+{
+    t->neg = !(p > 0.0);
+    if (!t->neg) { t->a = t->b = t->rcx = 0.0; return p; }
+    t->a = ff::rcp_ap(y - p);
+    t->b = t->a * (z - y) * (y - x);
+    double pt = y + t->b;
+    double ry = ff::rcp_ap(y);
+    double rho = x * z * ry;
+    double tau = p * pt * ry;                       /* < 0: R_C(rho, tau) = sqrt(rho / (rho - tau)) R_C(rho - tau, -tau) */
+    double xs = rho - tau;
+    t->rcx = (rho > 0.0) ? ff::sqrt_ap(rho * ff::rcp_ap(xs)) * rc_hi(xs, -tau) : 0.0;
+    return pt;
+}
+S5_HD S5_INL double pv_finish(double J, double F, const PvTerm& t) { return t.neg ? t.a * (t.b * J + 3.0 * (t.rcx - F)) : J; }
+
 /* polar part of the azimuth in tolerance mode: integral_T_mp(m2m, m2p, 1, X) for X = 0 and X = cos_i (sim5elliptic.c:1142-1159)
  * and the turning-point bookkeeping of geodesic_position_azm (sim5kerr-geod.c:528-553) for an equatorial hit */
-S5_HD S5_MID double azimuth_fast_polar(const AzIn& z, bool* ok)
+/* Parity is measured against the REFERENCE's doubles, and the reference evaluates phi as a sum of separately rounded terms
+ * that can be much larger than phi (1/c2 ((c2-a2) Pi + a2 u) with |c2| << a2 when a root of R(r) sits next to r+ or r-;
+ * A - B; the polar turning-point terms).  Its own rounding noise is then ~1e-16 * mag, which a different (even a more
+ * accurate) evaluation cannot reproduce.  Where that noise could approach the 1e-9 bar -- mag > S5_AZ_COND_LIMIT max(|phi|,1),
+ * a few pixels per million -- the item is handed to the bit-faithful kernel instead. */
+#ifndef S5_AZ_COND_LIMIT
+#define S5_AZ_COND_LIMIT 3.0e4
+#endif
+#if defined(S5_AZ_DIAG)
+#undef S5_AZ_COND_LIMIT
+#define S5_AZ_COND_LIMIT 1.0e300      /* calibration build: never fall back, so the unguarded deviation is visible */
+#endif
+#if defined(S5_AZ_DIAG) && !defined(__CUDA_ARCH__)
+static thread_local double s5_last_kappa;       /* calibration builds (tools/calibrate_azimuth_guard.py): the indicator of the last item */
+#endif
+/* The reference passes the amplitude of each incomplete integral through 1 - cn^2 and 1 - sn^2 conversions (elliptic_f_cos,
+ * elliptic_pi_cos, jacobi_isn: sim5elliptic.c:262-270, 436-448, 485) and through cn(sn^-1(.)) round trips, which put an ABSOLUTE
+ * noise of ~1e-16 on both cn^2 and sn^2.  Its F then carries a noise of ~1e-16 / (2 cn sn dn) and its Pi(n) one of
+ * ~1e-16 / (2 cn sn dn |1 - n sn^2|) -- large next to the turning point (sn -> 0), at cn -> 0 and at the pole of Pi.
+ * amp_noise returns these in units of 1e-16 with a safety factor of 8 (p = 1 for F). */
+S5_HD S5_INL float amp_noise(float csd, float p)        /* csd = cn * sn * dn */
+{
+    return 4.0f * ff::rcpf_ap(fabsf(csd * p));                         /* inf / NaN for degenerate amplitudes: the guard then fails, as it should */
+}
+/* the guard is bookkeeping, not a result: it runs in FP32 (the FP32 and SFU pipes idle next to the FP64 work) */
+S5_HD S5_INL float gf(double x) { return fabsf((float)x); }
+
+S5_HD S5_INL bool azimuth_well_conditioned(float mag, double phi)
+{
+#if defined(S5_AZ_DIAG) && !defined(__CUDA_ARCH__)
+    s5_last_kappa = (double)mag / fmax(fabs(phi), 1.0);
+#endif
+    return mag <= (float)S5_AZ_COND_LIMIT * fmaxf(gf(phi), 1.0f);       /* false for NaN, for inf */
+}
+
+S5_HD S5_MID double azimuth_fast_polar(const AzIn& z, bool* ok, float* mag)
 {
     bool good = true;
     double phi = 0.0;
     double msum = z.m2m + z.m2p;
-    double tm = z.m2p / msum;
-    double tn = z.m2p / (z.m2p - 1.0);
-    double tpre = 1. / sqrt(msum) / (1.0 - z.m2p);
+    double tm = ff::div_ap(z.m2p, msum);
+    double tn = ff::div_ap(z.m2p, z.m2p - 1.0);
+    double tpre = -ff::rsqrt_nc(msum) * ff::rcp_ap(z.m2p - 1.0);
     double qc = 1.0 - tm, pc = 1.0 - tn;
-    double cu = z.cos_i / sqrt(z.m2p);
+    double cu = z.cos_i * ff::rsqrt_nc(z.m2p);
     double cu2 = cu * cu;
     double ns2 = -tn * (1.0 - cu2);
     double qu = 1.0 - (1.0 - cu2) * tm;
@@ -307,8 +361,8 @@ S5_HD S5_MID double azimuth_fast_polar(const AzIn& z, bool* ok)
     double comp = rfK + tn * rj_hi(0.0, qc, 1.0, pc) * (1.0 / 3.0);
     double Fu, Ju;
     rfj_hi<1, true>(cu2, qu, 1.0, &pu, &Fu, &Ju);
-    double vu = sqrt(1.0 - cu2) * (Fu - ns2 * Ju * (1.0 / 3.0));
-    double la = z.l / z.a;
+    double vu = ff::sqrt_ap0(1.0 - cu2) * (Fu - ns2 * Ju * (1.0 / 3.0));
+    double la = ff::div_ap(z.l, z.a);
     double T0 = tpre * comp;
     double phi_pp = 2.0 * la * T0;
     double phi_mp = la * T0;
@@ -328,6 +382,7 @@ S5_HD S5_MID double azimuth_fast_polar(const AzIn& z, bool* ok)
         sign_dm = -sign_dm;
     }
     phi += (sign_dm < 0) ? phi_mp : phi_pp - phi_mp;
+    *mag = 2.0f * gf(phi_pp) + gf(phi_ip) + gf(phi_mp);
     *ok = good;
     return phi;
 }
@@ -346,78 +401,72 @@ S5_HD S5_MID double azimuth_fast_polar(const AzIn& z, bool* ok)
  * domain of the fast routines or the reference would take one of its special branches; the caller then has the
  * bit-faithful kernel redo the item.
  */
+/* one limit (amplitude sn^2 = s2, cn^2 = c2) of the RR radial integrals for both poles: adds sgn * ((n_k - aa2) Pi(n_k) + aa2 u)
+ * to br[k] and the matching magnitudes (terms + the reference's amplitude noise) to gm[k]; consumed at once so that nothing
+ * but the two brackets stays live across the second duplication sequence */
+S5_HD S5_INL bool rr_limit(double s2, double c2, double m2, double aa2, double c2p, double c2m, double sgn, double* br, float* gm)
+{
+    bool good = true;
+    double q = 1.0 - s2 * m2;
+    double pp[2] = {1.0 - c2p * s2, 1.0 - c2m * s2};
+    const float p0f[2] = {(float)pp[0], (float)pp[1]};
+    bool g = (s2 >= 0.0) && hi_domain(c2, q, 1.0) && hi_domain_p(fabs(pp[0])) && hi_domain_p(fabs(pp[1]));
+    if (!g) { c2 = q = pp[0] = pp[1] = 1.0; good = false; }
+    PvTerm t0, t1;                                     /* p < 0 (principal value): rays whose turning point lies inside r- */
+    pp[0] = pv_prepare(c2, q, 1.0, pp[0], &t0);
+    pp[1] = pv_prepare(c2, q, 1.0, pp[1], &t1);
+    if (!(hi_domain_p(pp[0]) && hi_domain_p(pp[1]))) { pp[0] = pp[1] = 1.0; good = false; }
+    double F, J[2];
+    rfj_hi<2, true>(c2, q, 1.0, pp, &F, J);
+    double sn = ff::sqrt_ap0(s2);
+    double u = sn * F;
+    double Pp = sn * (F + c2p * s2 * pv_finish(J[0], F, t0) * (1.0 / 3.0));
+    double Pm = sn * (F + c2m * s2 * pv_finish(J[1], F, t1) * (1.0 / 3.0));
+    br[0] += sgn * ((c2p - aa2) * Pp + aa2 * u);
+    br[1] += sgn * ((c2m - aa2) * Pm + aa2 * u);
+    float csd = ff::sqrtf_ap(gf(c2) * gf(s2) * gf(q));
+    float gu = gf(aa2) * (gf(u) + amp_noise(csd, 1.0f));
+    gm[0] += gf(c2p - aa2) * (gf(Pp) + amp_noise(csd, p0f[0])) + gu;
+    gm[1] += gf(c2m - aa2) * (gf(Pm) + amp_noise(csd, p0f[1])) + gu;
+    return good;
+}
+
 S5_HD S5_MID double azimuth_fast_rr(const AzIn& z, bool* ok)
 {
     const double r = z.r;
     int ppc = (z.nrr > 0) && (z.P > z.Rpc);
     double a2 = sq(z.a);
-    double sq1 = sqrt(1. - a2);
+    double sq1 = ff::sqrt_ap(1. - a2);
     double rp = 1. + sq1, rm = 1. - sq1;
     double a = z.e0, b = z.e1, c = z.e2, d = z.e3;
     double ad = a - d, bd = b - d, ab = a - b, ac = a - c;
-    double m2 = ((b - c) * ad) / (ac * bd);
-    double pre = -2.0 / sqrt(ac * bd);
-    double aa2 = ad / bd;
-    double c2p = ((rp - b) * ad) / ((rp - a) * bd);
-    double c2m = ((rm - b) * ad) / ((rm - a) * bd);
-    bool good = true;
+    double rbd = ff::rcp_ap(bd), rad = ff::rcp_ap(ad);
+    double pre = -2.0 * ff::rsqrt_nc(ac * bd);
+    double m2 = ((b - c) * ad) * (0.25 * pre * pre);          /* 1 / (ac bd) = pre^2 / 4 */
+    double aa2 = ad * rbd;
+    double c2p = ff::div_ap((rp - b) * aa2, rp - a);
+    double c2m = ff::div_ap((rm - b) * aa2, rm - a);
+    double br[2] = {0.0, 0.0};
+    float gm[2] = {0.0f, 0.0f};
+    /* limit at infinity: sn^2 = (b-d)/(a-d); limit at r: sn^2 = (b-d)(r-a)/((a-d)(r-b)) */
+    bool good = rr_limit(bd * rad, ab * rad, m2, aa2, c2p, c2m, 1.0, br, gm);
+    double rrb = rad * ff::rcp_ap(r - b);
+    good = rr_limit((bd * (r - a)) * rrb, (ab * (r - d)) * rrb, m2, aa2, c2p, c2m, ppc ? +1.0 : -1.0, br, gm) && good;
 
-    /* limit at infinity */
-    double s2i = bd / ad, ci2 = ab / ad;
-    double qi = 1.0 - s2i * m2;
-    double pi_[2] = {1.0 - c2p * s2i, 1.0 - c2m * s2i};
-    bool gi = (s2i >= 0.0) && hi_domain(ci2, qi, 1.0) && hi_domain_p(pi_[0]) && hi_domain_p(pi_[1]);
-    if (!gi) { ci2 = qi = pi_[0] = pi_[1] = 1.0; good = false; }
-    double Fi, Ji[2];
-    rfj_hi<2, true>(ci2, qi, 1.0, pi_, &Fi, Ji);
-    double si = sqrt(s2i);
-    double u_inf = si * Fi;
-    double Pinf_p = si * (Fi + c2p * s2i * Ji[0] * (1.0 / 3.0));
-    double Pinf_m = si * (Fi + c2m * s2i * Ji[1] * (1.0 / 3.0));
-
-    /* limit at r */
-    double rb = r - b;
-    double s2r = (bd * (r - a)) / (ad * rb), cr2 = (ab * (r - d)) / (ad * rb);
-    double qr = 1.0 - s2r * m2;
-    double pr_[2] = {1.0 - c2p * s2r, 1.0 - c2m * s2r};
-    bool gr = (s2r >= 0.0) && hi_domain(cr2, qr, 1.0) && hi_domain_p(pr_[0]) && hi_domain_p(pr_[1]);
-    if (!gr) { cr2 = qr = pr_[0] = pr_[1] = 1.0; good = false; }
-    double Fr, Jr[2];
-    rfj_hi<2, true>(cr2, qr, 1.0, pr_, &Fr, Jr);
-    double sr = sqrt(s2r);
-    double u_r = sr * Fr;
-    double Pr_p = sr * (Fr + c2p * s2r * Jr[0] * (1.0 / 3.0));
-    double Pr_m = sr * (Fr + c2m * s2r * Jr[1] * (1.0 / 3.0));
-
-    double sgn = ppc ? +1.0 : -1.0;
-    double A = pre / (rp - a) * ((1. / c2p) * (((c2p - aa2) * Pinf_p + aa2 * u_inf) + sgn * ((c2p - aa2) * Pr_p + aa2 * u_r)));
-    double B = pre / (rm - a) * ((1. / c2m) * (((c2m - aa2) * Pinf_m + aa2 * u_inf) + sgn * ((c2m - aa2) * Pr_m + aa2 * u_r)));
-    double phi = 1. / sq1 * (A * (z.a * rp - z.l * a2 / 2.) - B * (z.a * rm - z.l * a2 / 2.));
+    double rsq1 = ff::rcp_ap(sq1);
+    double wA = (z.a * rp - z.l * a2 * 0.5) * rsq1, wB = (z.a * rm - z.l * a2 * 0.5) * rsq1;
+    double oA = ff::div_ap(pre, (rp - a) * c2p), oB = ff::div_ap(pre, (rm - a) * c2m);
+    double phi = (oA * br[0]) * wA - (oB * br[1]) * wB;
+    /* size of the rounded terms the reference adds up, plus the noise its amplitudes carry (azimuth_well_conditioned, amp_noise) */
+    float mag = gf(wA * oA) * gm[0] + gf(wB * oB) * gm[1];
 
     bool okp;
-    phi += azimuth_fast_polar(z, &okp);
-    good = good && okp;
+    float pmag;
+    phi += azimuth_fast_polar(z, &okp, &pmag);
+    good = good && okp && azimuth_well_conditioned(mag + pmag, phi);
     *ok = good;
     return good ? phi : NAN;
 }
-
-/* Cauchy principal value of R_J for p < 0 on top of the shared sequence: R_J(x,y,z,p) = a (b R_J(x,y,z,pt) + 3 (R_C(rho,tau) - R_F(x,y,z)))
- * with x <= y <= z (sim5elliptic.c:166-177, 204).  pv_prepare turns p into the positive pt the sequence is run with. */
-struct PvTerm { double a, b, rcx; bool neg; };
-S5_HD S5_INL double pv_prepare(double x, double y, double z, double p, PvTerm* t)
-{
-    t->neg = !(p > 0.0);
-    if (!t->neg) { t->a = t->b = t->rcx = 0.0; return p; }
-    t->a = 1.0 / (y - p);
-    t->b = t->a * (z - y) * (y - x);
-    double pt = y + t->b;
-    double rho = x * z / y;
-    double tau = p * pt / y;                       /* < 0: R_C(rho, tau) = sqrt(rho / (rho - tau)) R_C(rho - tau, -tau) */
-    double xs = rho - tau;
-    t->rcx = (rho > 0.0) ? sqrt(rho / xs) * rc_hi(xs, -tau) : 0.0;
-    return pt;
-}
-S5_HD S5_INL double pv_finish(double J, double F, const PvTerm& t) { return t.neg ? t.a * (t.b * J + 3.0 * (t.rcx - F)) : J; }
 
 /*
  * Tolerance-mode azimuth of an RC disk hit (two real roots a > b and the pair u +- iv): B&F 260.04 and 341.03 as the
@@ -430,27 +479,29 @@ S5_HD S5_MID double azimuth_fast_rc(const AzIn& z, bool* ok)
 {
     const double r = z.r;
     double a2s = sq(z.a);
-    double sq1 = sqrt(1. - a2s);
+    double sq1 = ff::sqrt_ap(1. - a2s);
     double rpm[2] = {1. + sq1, 1. - sq1};
     double a = z.e0, b = z.e1, u = z.e2, v2 = sq(z.e3);
-    double A_ = sqrt(sq(a - u) + v2), B_ = sqrt(sq(b - u) + v2);
-    double m = (sq(A_ + B_) - sq(a - b)) / (4. * A_ * B_);
-    double g = 1. / sqrt(A_ * B_);
-    double alpha2 = (B_ + A_) / (B_ - A_);
-    double cl[2] = {(r * (A_ - B_) + a * B_ - b * A_) / (r * (A_ + B_) - a * B_ - b * A_), (A_ - B_) / (A_ + B_)};   /* cn at r, at infinity */
+    double A_ = ff::sqrt_ap(sq(a - u) + v2), B_ = ff::sqrt_ap(sq(b - u) + v2);
+    double g = ff::rsqrt_nc(A_ * B_);
+    double m = (sq(A_ + B_) - sq(a - b)) * (0.25 * g * g);
+    double alpha2 = ff::div_ap(B_ + A_, B_ - A_);
+    double cl[2] = {ff::div_ap(r * (A_ - B_) + a * B_ - b * A_, r * (A_ + B_) - a * B_ - b * A_), ff::div_ap(A_ - B_, A_ + B_)};   /* cn at r, at infinity */
     bool good = (m > 0.0) && (m < 1.0) && (cl[0] != 0.0) && (cl[1] != 0.0);
     double alpha1[2], nn[2], mma[2];
     #pragma unroll
     for (int k = 0; k < 2; k++) {
         double p = rpm[k];
-        alpha1[k] = (B_ * a + b * A_ - p * A_ - p * B_) / (B_ * a - b * A_ + p * A_ - p * B_);
+        alpha1[k] = ff::div_ap(B_ * a + b * A_ - p * A_ - p * B_, B_ * a - b * A_ + p * A_ - p * B_);
         double al2 = sq(alpha1[k]);
-        nn[k] = al2 / (al2 - 1.);
-        mma[k] = (m + (1. - m) * al2) / (1. - al2);
+        double ral = ff::rcp_ap(al2 - 1.);
+        nn[k] = al2 * ral;
+        mma[k] = -(m + (1. - m) * al2) * ral;
         good = good && (nn[k] == nn[k]) && (fabs(nn[k]) < 1e18) && (nn[k] != 1.0);
     }
     /* per limit: F(|c|) and the two Pi(|c|, n_k), f1 */
     double Fh[2], Ph[2][2], f1[2][2];
+    float nP[2][2], nF[2];
     #pragma unroll
     for (int j = 0; j < 2; j++) {
         double c = fabs(cl[j]);
@@ -464,7 +515,11 @@ S5_HD S5_MID double azimuth_fast_rc(const AzIn& z, bool* ok)
         if (!(hi_domain_p(pt[0]) && hi_domain_p(pt[1]))) { pt[0] = pt[1] = 1.0; good = false; }
         double F, J[2];
         rfj_hi<2, true>(c2, q, 1.0, pt, &F, J);
-        double s = sqrt(s2), dn = sqrt(q);
+        double s = ff::sqrt_ap0(s2), dn = ff::sqrt_ap(q);
+        float csd = ff::sqrtf_ap(gf(c2) * gf(s2) * gf(q));     /* the reference's amplitude noise, as in azimuth_fast_rr */
+        nF[j] = amp_noise(csd, 1.0f);
+        nP[j][0] = amp_noise(csd, (float)pp[0]);
+        nP[j][1] = amp_noise(csd, (float)pp[1]);
         Fh[j] = s * F;
         Ph[j][0] = s * (F + nn[0] * s2 * pv_finish(J[0], F, t0) * (1.0 / 3.0));
         Ph[j][1] = s * (F + nn[1] * s2 * pv_finish(J[1], F, t1) * (1.0 / 3.0));
@@ -472,11 +527,11 @@ S5_HD S5_MID double azimuth_fast_rc(const AzIn& z, bool* ok)
         for (int k = 0; k < 2; k++) {
             double am = fabs(mma[k]);
             if (am > 1e-5) {
-                double sm = sqrt(am);
-                double y = sm * s / dn;
-                f1[j][k] = (mma[k] > 0.0) ? atan(y) / sm : -0.5 * log(fabs((1.0 + y) / (1.0 - y))) / sm;
+                double rsm = ff::rsqrt_nc(am);
+                double y = am * rsm * s * ff::rcp_ap(dn);
+                f1[j][k] = (mma[k] > 0.0) ? atan(y) * rsm : -0.5 * log(fabs(ff::div_ap(1.0 + y, 1.0 - y))) * rsm;
             } else {
-                f1[j][k] = s / dn;
+                f1[j][k] = ff::div_ap(s, dn);
             }
         }
     }
@@ -498,6 +553,7 @@ S5_HD S5_MID double azimuth_fast_rc(const AzIn& z, bool* ok)
     }
     /* u(c) = F_cos(c): F(|c|) or 2K - F(|c|); Pi_cos alike.  index 0 = at r (u1), 1 = at infinity (u2) */
     double uu[2], AB[2];
+    float MG[2];
     #pragma unroll
     for (int j = 0; j < 2; j++) uu[j] = (cl[j] >= 0.0) ? Fh[j] : 2.0 * Kc - Fh[j];
     /* when both limits are on the negative side the 2K (2 Pi_c) terms cancel in the differences: Kc = Pc = 0 above is then exact */
@@ -505,19 +561,28 @@ S5_HD S5_MID double azimuth_fast_rc(const AzIn& z, bool* ok)
     for (int k = 0; k < 2; k++) {
         double p = rpm[k];
         double R1v[2];
+        float R1m = 0.0f;
+        double r1a = ff::rcp_ap(1. - sq(alpha1[k]));
         #pragma unroll
         for (int j = 0; j < 2; j++) {
             double Pi = (cl[j] > 0.0) ? Ph[j][k] : ((cl[j] == 0.0) ? Pc[k] : 2.0 * Pc[k] - Ph[j][k]);
-            R1v[j] = 1. / (1. - sq(alpha1[k])) * (Pi + alpha1[k] * f1[j][k]);
+            R1v[j] = r1a * (Pi + alpha1[k] * f1[j][k]);
+            /* the reference forms Pi(c<0) = 2 Pi_c - Pi(|c|) and F(c<0) = 2K - F(|c|) from separately rounded pieces */
+            R1m += (gf(Ph[j][k]) + nP[j][k] + 2.0f * gf(Pc[k]) + gf(alpha1[k] * f1[j][k])) * gf(r1a);
         }
         double t0 = alpha2 * (uu[1] - uu[0]);
         double t1 = (alpha1[k] - alpha2) * (R1v[1] - R1v[0]);
-        AB[k] = (B_ - A_) * g / (B_ * a + b * A_ - p * A_ - p * B_) * (t0 + t1);
+        double outer = ff::div_ap((B_ - A_) * g, B_ * a + b * A_ - p * A_ - p * B_);
+        AB[k] = outer * (t0 + t1);
+        MG[k] = gf(outer) * (gf(alpha2) * (gf(Fh[0]) + nF[0] + gf(Fh[1]) + nF[1] + 4.0f * gf(Kc)) + gf(alpha1[k] - alpha2) * R1m);
     }
-    double phi = 1. / sq1 * (AB[0] * (z.a * rpm[0] - z.l * a2s / 2.) - AB[1] * (z.a * rpm[1] - z.l * a2s / 2.));
+    double rsq1 = ff::rcp_ap(sq1);
+    double phi = rsq1 * (AB[0] * (z.a * rpm[0] - z.l * a2s * 0.5) - AB[1] * (z.a * rpm[1] - z.l * a2s * 0.5));
+    float mag = (MG[0] * gf(z.a * rpm[0] - z.l * a2s * 0.5) + MG[1] * gf(z.a * rpm[1] - z.l * a2s * 0.5)) * gf(rsq1);
     bool okp;
-    phi += azimuth_fast_polar(z, &okp);
-    *ok = good && okp;
+    float pmag;
+    phi += azimuth_fast_polar(z, &okp, &pmag);
+    *ok = good && okp && azimuth_well_conditioned(mag + pmag, phi);
     return *ok ? phi : NAN;
 }
 

@@ -8,6 +8,7 @@
 // reference before any GPU time is spent.  It is NOT part of the product: libsim5b200.so never
 // links or loads it and has no CPU path.
 #include <omp.h>
+#include <stdio.h>
 #include "../../sim5_b200/csrc/pixel.cuh"
 
 using namespace s5;
@@ -158,5 +159,38 @@ double hs_trace_image(const sim5_image_params* p, const sim5_image_out* out, int
 extern "C" void hs_hi_counts(long long* out, int reset)
 {
     for (int i = 0; i < 4; i++) { out[i] = s5::s5_hi_counts[i]; if (reset) s5::s5_hi_counts[i] = 0; }
+}
+#endif
+
+#if defined(S5_AZ_DIAG)
+// calibration build only: the conditioning indicator of azimuth_well_conditioned for every disk hit (0 elsewhere) and the
+// tolerance-mode phi WITHOUT the guard's fallback, so tools/calibrate_azimuth_guard.py can plot deviation against indicator
+extern "C" void hs_fast_azimuth_kappa(const sim5_image_params* p, double* kappa, double* phi_fast)
+{
+    S5ImageConsts c;
+    s5_fill_image_consts(p, &c);
+    #pragma omp parallel for schedule(dynamic, 4)
+    for (int iy = 0; iy < c.ny; iy++) for (int ix = 0; ix < c.nx; ix++) {
+        size_t i = (size_t)iy * c.nx + ix;
+        kappa[i] = 0.0; phi_fast[i] = 0.0;
+        double alpha, beta;
+        pixel_impact(c, ix, iy, &alpha, &beta);
+        Geodesic gd; int err = 0; RayCache k;
+        if (!init_inf_cached(c, alpha, beta, &gd, &err, &k)) continue;
+        for (int order = 0; order <= c.max_order; order++) {
+            double P = crossing_cached(&gd, order, k);
+            if (isnan(P)) break;
+            double r = geodesic_position_rad(&gd, P);
+            if (!(r >= c.rmin_emit)) continue;
+            AzIn z; az_make(&gd, k, r, P, &z);
+            bool ok = false; double v = NAN;
+            s5_last_kappa = 0.0;
+            if (gd.type == GEOD_TYPE_RR) v = azimuth_fast_rr(z, &ok);
+            else if (gd.type == GEOD_TYPE_RC) v = azimuth_fast_rc(z, &ok);
+            kappa[i] = s5_last_kappa;
+            phi_fast[i] = v;
+            break;
+        }
+    }
 }
 #endif

@@ -290,3 +290,28 @@ def test_full_size_properties(gpu_api):
     assert np.all((done == abi.ST_HORIZON) | (done == abi.ST_ESCAPE) | (done == abi.ST_ERRBREAK))
     esc = done == abi.ST_ESCAPE
     assert np.quantile(keep["qerr"][esc], 0.99) < 1e-3          # Carter-constant drift, the reference's own invariant
+
+
+def test_full_index_split_writes_into_one_image(gpu_api):
+    """SIM5_FLAG_FULL_INDEX: the calls of an interleaved split (one per GPU in a multi-GPU job) store their rows straight into
+    ONE full-image set of device planes -- what the ranks do with rank 0's peer-mapped planes -- and the result is the image
+    of a single unsplit call; CUDA IPC export/import entry points exist and reject null arguments."""
+    p = abi.default_params(2, 160, 192)
+    full, _ = _gpu_planes(gpu_api, p)
+    img = gpu_api.DevicePlanes(p)
+    try:
+        for r in range(3):
+            q = abi.default_params(2, 160, 192)
+            q.flags = abi.FLAG_DEVICE_PTRS | abi.FLAG_FULL_INDEX
+            q.split_count, q.split_index, q.split_rows = 3, r, 8
+            st = gpu_api.trace_image_device(q, img.out)
+            assert st.rays == 160 * 192 // 3
+        for k in ("r", "phi", "g", "flux", "status"):
+            assert np.array_equal(img.to_host(k), full[k], equal_nan=True), k
+        h = img.handles()
+        assert set(h) == {"r", "phi", "g", "flux", "status"} and all(len(v) == 64 for v in h.values())
+    finally:
+        img.close()
+    L = gpu_api.lib()
+    assert L.sim5_ipc_export(None, None) == abi.ERR_BAD_PARAM
+    assert not L.sim5_ipc_import(None)
