@@ -136,6 +136,8 @@ def config_dict(n_gpus, n, gather="peer"):
 
 
 def run_ours(args):
+    # NCCL prints its version / debug lines to stdout by default; stdout carries exactly one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import ctypes as C
