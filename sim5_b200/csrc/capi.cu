@@ -499,8 +499,8 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
             grid = persistent_grid(s5::k_trace_stepwise, S5_CTA_THREADS);
             s5::k_trace_stepwise<<<grid, S5_CTA_THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
         } else if (two_phase) {
-            grid = persistent_grid(s5::k_trace_eqplane<true>, S5_CTA_THREADS);
-            s5::k_trace_eqplane<true><<<grid, S5_CTA_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+            grid = persistent_grid(s5::k_trace_eqplane<true>, S5_EQ_THREADS);
+            s5::k_trace_eqplane<true><<<grid, S5_EQ_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
             if (ch == 0) CK(cudaEventRecord(c.evp[0], c.stream));
             int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_AZ_THREADS);
             int g_rc = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RC>, S5_AZ_THREADS);
@@ -538,8 +538,8 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
             if (ch == 0) CK(cudaEventRecord(c.evp[2], c.stream));
             launches += 2;
         } else {
-            grid = persistent_grid(s5::k_trace_eqplane<false>, S5_CTA_THREADS);
-            s5::k_trace_eqplane<false><<<grid, S5_CTA_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+            grid = persistent_grid(s5::k_trace_eqplane<false>, S5_EQ_THREADS);
+            s5::k_trace_eqplane<false><<<grid, S5_EQ_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
         }
         launches += 1;
         CK(cudaGetLastError());

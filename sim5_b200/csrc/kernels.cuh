@@ -46,8 +46,11 @@ struct AzQueue {
 };
 
 #define S5_CTA_THREADS 128
+#ifndef S5_EQ_THREADS
+#define S5_EQ_THREADS 512          /* CTA size of the eq-plane trace kernels; r01p sweep: 512 x 1 CTA/SM 5.38 ms, 256 x 2 5.55, 128 x 4 5.68, 64 x 8 5.68 */
+#endif
 #ifndef S5_MIN_CTAS_EQ
-#define S5_MIN_CTAS_EQ 4          /* resident CTAs per SM the eq-plane kernel is compiled for (register cap = 65536/(128*n)); r01c sweep: 4 is the knee */
+#define S5_MIN_CTAS_EQ 1          /* resident CTAs per SM the eq-plane kernel is compiled for: 512 threads x 1 CTA = 128 registers per thread */
 #endif
 #ifndef S5_MIN_CTAS_STEP
 #define S5_MIN_CTAS_STEP 1
@@ -93,7 +96,7 @@ __device__ __forceinline__ void flush_stats(const unsigned int* s_cnt, unsigned 
 /* modes EQPLANE / POLARIZED : analytic geodesic per pixel             */
 /* ------------------------------------------------------------------ */
 template <bool DEFER>
-__global__ void __launch_bounds__(S5_CTA_THREADS, S5_MIN_CTAS_EQ)
+__global__ void __launch_bounds__(S5_EQ_THREADS, S5_MIN_CTAS_EQ)
 k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQueue q, unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
 {
     __shared__ S5ImageConsts c;
@@ -106,16 +109,29 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
     const long long npix = (long long)c.nrows_local * nx;
     const long long ntiles = (npix + 31) >> 5;
 
+#if !defined(S5_EQ_FREERUN)
+    __shared__ unsigned long long s_tile;
+#endif
     for (;;) {
         unsigned long long t = 0;
+#if !defined(S5_EQ_FREERUN)
+        /* the CTA takes one tile per warp at a time and passes a barrier per batch, so its 16 warps walk the (183 KB) routine together and
+         * share instruction-cache lines: r01q sweep 5.33 vs 5.40 ms free-running (cfg 3: 2.67 vs 2.81 ms); -DS5_EQ_FREERUN restores per-warp pulls */
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, (unsigned long long)(S5_EQ_THREADS / 32));
+        __syncthreads();
+        if ((long long)s_tile >= ntiles) break;
+        t = s_tile + (threadIdx.x >> 5);
+#else
         if (lane == 0) t = atomicAdd(tile_counter, 1ULL);
         t = __shfl_sync(0xffffffffu, t, 0);
         if ((long long)t >= ntiles) break;
+#endif
         long long p = ((long long)t << 5) + lane;
         AzIn z;
         bool deferred = false;
         size_t i = 0;
-        if (p < npix) {
+        if ((long long)t < ntiles && p < npix) {
             int lr = (int)(p / nx);
             int ix = (int)(p - (long long)lr * nx);
             int iy = s5_local_to_image_row(&c, lr);
@@ -348,7 +364,7 @@ k_trace_stepwise(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsi
 /* ------------------------------------------------------------------ */
 /* mode HISTOGRAM : g-factor transfer function over a (spin, incl) lattice */
 /* ------------------------------------------------------------------ */
-__global__ void __launch_bounds__(S5_CTA_THREADS, S5_MIN_CTAS_EQ)
+__global__ void __launch_bounds__(S5_CTA_THREADS, 4)       /* the histogram kernel keeps 128-thread CTAs (4 tiles of one image per CTA) */
 k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice image */, int img_begin, int img_end,
                   double* __restrict__ hist, unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
 {

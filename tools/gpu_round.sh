@@ -9,7 +9,7 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_o
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_trace_eqplane|k_azimuth" -s 8 -c 4 -f -o gpurun_out/${TAG}_prof_eqplane \
+ncu --set full --clock-control none --import-source on -k regex:"k_trace_eqplane|k_azimuth" -s 12 -c 6 -f -o gpurun_out/${TAG}_prof_eqplane \
     python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
 python tools/micro_carlson.py > gpurun_out/${TAG}_micro.log 2>&1
 cat gpurun_out/${TAG}_bench.json
