@@ -41,6 +41,9 @@ extern "C" {
 #define SIM5_MODE_POLARIZED      1   /* EQPLANE + local tetrad g-factor, emission angle, Walker-Penrose chi, Chandrasekhar delta */
 #define SIM5_MODE_STEPWISE       2   /* raytrace() stepping through an optically thin torus */
 #define SIM5_MODE_HISTOGRAM      3   /* transfer function: g-factor histograms over a (spin, inclination) lattice */
+#define SIM5_MODE_SPECTRUM       4   /* observed thermal spectrum of the thin disk: sum over the image of the (limb-darkened, colour-corrected)
+                                        black-body intensity of every disk hit -- DiskRaytrace.spectrum of the reference's Python layer
+                                        (python/sim5diskraytrace.py:43-134) on the image grid, blackbody() of sim5radiation.c:56-78 */
 
 /* output plane selector bits (all planes are row-major [ny][nx], index iy*nx+ix) */
 #define SIM5_OUT_R            0x001  /* radius of the disk hit                      (double) */
@@ -160,6 +163,12 @@ typedef struct sim5_image_params {
      * own index).  Host planes keep full-image indexing; DEVICE planes are compact: local row
      * lr = (b / split_count) * split_rows + (iy - row_begin) % split_rows, index lr*nx + ix. */
     int32_t  split_count, split_index, split_rows, reserved2;
+    /* SPECTRUM: n_energy <= 256 energies E_k = e_min_kev * (e_max_kev/e_min_kev)^(k/(n_energy-1)) at the detector;
+     * per disk hit T = (F(r)/sigma_SB)^(1/4), g and the emission cosine mu_e from the Keplerian emitter frame,
+     * spectrum[k] += B_E(T; hardening spec_hardf, limb darkening 0.5+0.75 mu_e if spec_limb) at E_k/g * g^3 * dalpha*dbeta
+     * [erg cm^-2 s^-1 keV^-1 srad^-1 x (GM/c^2)^2]; the caller multiplies by (GM/c^2 / D)^2 */
+    int32_t  n_energy, spec_limb;
+    double   e_min_kev, e_max_kev, spec_hardf;
 } sim5_image_params;
 
 typedef struct sim5_image_out {
@@ -176,6 +185,7 @@ typedef struct sim5_image_out {
     int32_t *steps;
     uint8_t *status;
     double  *hist;               /* [n_spin][n_incl][n_bins] */
+    double  *spectrum;           /* SPECTRUM: [n_energy], always a HOST array (it is 2 KB) */
 } sim5_image_out;
 
 typedef struct sim5_trace_stats {
@@ -213,7 +223,8 @@ int   sim5_ipc_export(const void* device_ptr, void* handle64);
 void* sim5_ipc_import(const void* handle64);
 int   sim5_ipc_release(void* imported_ptr);
 
-/* defaults: fills every field with the SURVEY.md 8(d) definition of BASELINE config `cfg` (1..5) */
+/* defaults: fills every field with the SURVEY.md 8(d) definition of BASELINE config `cfg` (1..5); 6 = the SPECTRUM preset
+ * (the camera of config 2 at 2048^2, 128 energies 0.05..50 keV, hardening 1.7, limb darkening on) */
 int  sim5_default_params(int cfg, sim5_image_params* p);
 
 /* THE batched entry: replaces the per-pixel loop of disk-image.c:53-105 */

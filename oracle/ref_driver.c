@@ -365,6 +365,74 @@ double ref_trace_histogram(const sim5_image_params* p, double* hist, int nthread
     return dt;
 }
 
+/*
+ * Thermal disk spectrum (mode SPECTRUM): DiskRaytrace.spectrum of the reference's Python layer
+ * (python/sim5diskraytrace.py:43-134) on the image grid instead of its polar grid: for every disk hit
+ * T = (F/sigma_SB)^(1/4) (python/sim5diskmodel.py:48), g and the emission cosine from the Keplerian emitter frame
+ * (:340-391), spectrum += blackbody(T, hardf, mu_e or -1, energies/g) * g^3 * dalpha*dbeta (:124).  Every physics call
+ * is the reference's own (blackbody() of sim5radiation.c:56-78).  spec is [n_energy]; rows [row_begin,row_end) and the
+ * interleaved split are honoured so partial spectra of a multi-GPU job can be checked too.  One partial sum per row, rows
+ * added in row order.
+ */
+double ref_trace_spectrum(const sim5_image_params* p, double* spec, int nthreads, int quiet)
+{
+    if (!p || !spec || p->n_energy < 1 || p->n_energy > 256) return -1.0;
+    int nx = p->nx, ny = p->ny, ne = p->n_energy;
+    int rb = p->row_begin, re = p->row_end;
+    if (rb == 0 && re == 0) re = ny;
+    double a = p->bh_spin;
+    double rmin = (p->r_emit_min > 0.0) ? p->r_emit_min : r_ms(a);
+    double rmax = p->rmax;
+    double da = 2.0*rmax/(double)nx;
+    double db = 2.0*rmax*((double)ny/(double)nx)/(double)ny;
+    double dA = da*db;
+    double E[256];
+    int k;
+    for (k = 0; k < ne; k++) E[k] = (ne <= 1) ? p->e_min_kev : p->e_min_kev*pow(p->e_max_kev/p->e_min_kev, (double)k/(double)(ne-1));
+    sim5_image_params q = *p;
+    q.mode = SIM5_MODE_POLARIZED;
+    q.outputs = SIM5_OUT_R | SIM5_OUT_G | SIM5_OUT_MUE;
+    disk_nt_setup(p->disk_mass, a, p->disk_mdot, p->disk_alpha, 0);
+    int saved = quiet ? silence_stderr() : -1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+    double t0 = omp_get_wtime();
+#else
+    struct timespec ts0, ts1; clock_gettime(CLOCK_MONOTONIC, &ts0);
+#endif
+    double* part = (double*)calloc((size_t)ne*(size_t)ny, sizeof(double));
+    int iy;
+    #pragma omp parallel for schedule(dynamic,4)
+    for (iy = rb; iy < re; iy++) {
+        if (p->split_count > 1 && ((iy - rb) / (p->split_rows > 0 ? p->split_rows : 1)) % p->split_count != p->split_index) continue;
+        double* h = part + (size_t)iy*ne;
+        double Eg[256], Iv[256];
+        for (int ix = 0; ix < nx; ix++) {
+            double alpha = (((double)(ix)+.5)/(double)(nx)-0.5)*2.0*rmax;
+            double beta  = (((double)(iy)+.5)/(double)(ny)-0.5)*2.0*rmax * ((double)ny/(double)nx);
+            pixel_result o;
+            pixel_eqplane(&q, rmin, alpha, beta, &o);
+            int cls = SIM5_ST_CLASS(o.status);
+            if (!(cls == SIM5_ST_HIT0 || cls == SIM5_ST_HIT1 || cls == SIM5_ST_HIT2)) continue;
+            double T = sqrt(sqrt(disk_nt_flux(o.r)/5.670400e-05));
+            if (!(T > 0.0) || !(o.g > 0.0)) continue;
+            for (int j = 0; j < ne; j++) Eg[j] = E[j]/o.g;
+            blackbody(T, p->spec_hardf, (p->spec_limb && o.mue >= 0.0) ? o.mue : -1.0, Eg, Iv, ne);
+            for (int j = 0; j < ne; j++) h[j] += Iv[j]*(o.g*o.g*o.g)*dA;
+        }
+    }
+    for (k = 0; k < ne; k++) { double s = 0.0; for (iy = rb; iy < re; iy++) s += part[(size_t)iy*ne+k]; spec[k] = s; }
+    free(part);
+#ifdef _OPENMP
+    double dt = omp_get_wtime() - t0;
+#else
+    clock_gettime(CLOCK_MONOTONIC, &ts1);
+    double dt = (ts1.tv_sec-ts0.tv_sec) + 1e-9*(ts1.tv_nsec-ts0.tv_nsec);
+#endif
+    if (quiet) restore_stderr(saved);
+    return dt;
+}
+
 /* element-wise wrappers (n-element SoA loops over single reference functions) for unit parity tests */
 void ref_batch_rf(long n, const double* x, const double* y, const double* z, double* o) { for (long i=0;i<n;i++) o[i]=rf(x[i],y[i],z[i]); }
 void ref_batch_rd(long n, const double* x, const double* y, const double* z, double* o) { for (long i=0;i<n;i++) o[i]=rd(x[i],y[i],z[i]); }

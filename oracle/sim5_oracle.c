@@ -12,7 +12,7 @@
  *     (both sides are the same call-for-call arithmetic on the same glibc; observed: 0 differing doubles);
  *   - oracle/_ref itself, live, whenever it is built (same test file, larger images).
  *
- * Scope: the analytic path of BASELINE configs 1, 2, 3 and 5 (modes EQPLANE, POLARIZED, HISTOGRAM).  The
+ * Scope: the analytic path of BASELINE configs 1, 2, 3 and 5 (modes EQPLANE, POLARIZED, HISTOGRAM) and the SPECTRUM mode.  The
  * step-wise integrator (config 4) is checked against oracle/_ref and its golden fixture only;
  * orc_trace_image returns -3 for SIM5_MODE_STEPWISE.
  *
@@ -973,6 +973,68 @@ double orc_trace_histogram(const sim5_image_params* p, double* hist, int nthread
             for (iy = 0; iy < ny; iy++) s += rows[(size_t)iy * nb + b];
             H[b] = s;
         }
+    }
+    free(rows);
+    return now_s() - t0;
+}
+
+/* black-body specific intensity on an energy grid.  sim5radiation.c:56-78 (constants of sim5const.h:33-87) */
+static void planck_grid(double T, double hardf, double cos_mu, const double* E, double* Iv, int n)
+{
+    const double h = 6.626069e-27, c = 2.997925e+10, kB = 1.380650e-16, kev2hz = 2.417990e+17;
+    if (T <= 0.0) return;
+    double limbf = (cos_mu >= 0.0) ? 0.5 + 0.75 * cos_mu : 1.0;
+    double BB1 = limbf * 2.0 * h / SQ(c) / (hardf * hardf * hardf * hardf) * (kev2hz * kev2hz * kev2hz * kev2hz);
+    double BB2 = (h * kev2hz) / (kB * hardf * T);
+    for (int i = 0; i < n; i++) Iv[i] = BB1 * (E[i] * E[i] * E[i]) / expm1(BB2 * E[i]);
+}
+
+/* thermal disk spectrum (mode SPECTRUM; same definition as oracle/ref_driver.c ref_trace_spectrum, which follows
+ * python/sim5diskraytrace.py:43-134 on the image grid) */
+double orc_trace_spectrum(const sim5_image_params* p, double* spec, int nthreads)
+{
+    if (!p || !spec || p->n_energy < 1 || p->n_energy > 256) return -1.0;
+    int nx = p->nx, ny = p->ny, ne = p->n_energy, rb = p->row_begin, re = p->row_end;
+    if (rb == 0 && re == 0) re = ny;
+    double rmin = (p->r_emit_min > 0.0) ? p->r_emit_min : orc_r_ms(p->bh_spin);
+    double rmax = p->rmax;
+    double dA = (2.0 * rmax / (double)nx) * (2.0 * rmax * ((double)ny / (double)nx) / (double)ny);
+    double E[256];
+    for (int k = 0; k < ne; k++) E[k] = (ne <= 1) ? p->e_min_kev : p->e_min_kev * pow(p->e_max_kev / p->e_min_kev, (double)k / (double)(ne - 1));
+    sim5_image_params q = *p;
+    q.mode = SIM5_MODE_POLARIZED;
+    q.outputs = SIM5_OUT_R | SIM5_OUT_G | SIM5_OUT_MUE;
+    orc_disk disk;
+    disk_setup(&disk, p->disk_mass, p->bh_spin, p->disk_mdot);
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    double t0 = now_s();
+    double* rows = (double*)calloc((size_t)ne * (size_t)ny, sizeof(double));
+    int iy;
+    #pragma omp parallel for schedule(dynamic, 4)
+    for (iy = rb; iy < re; iy++) {
+        if (p->split_count > 1 && ((iy - rb) / (p->split_rows > 0 ? p->split_rows : 1)) % p->split_count != p->split_index) continue;
+        double* h = rows + (size_t)iy * ne;
+        double Eg[256], Iv[256];
+        for (int ix = 0; ix < nx; ix++) {
+            double alpha = (((double)(ix) + .5) / (double)(nx) - 0.5) * 2.0 * rmax;
+            double beta = (((double)(iy) + .5) / (double)(ny) - 0.5) * 2.0 * rmax * ((double)ny / (double)nx);
+            orc_pixel o;
+            trace_pixel(&q, &disk, rmin, alpha, beta, &o);
+            int cls = SIM5_ST_CLASS(o.status);
+            if (!(cls == SIM5_ST_HIT0 || cls == SIM5_ST_HIT1 || cls == SIM5_ST_HIT2)) continue;
+            double T = sqrt(sqrt(disk_flux(&disk, o.r) / 5.670400e-05));
+            if (!(T > 0.0) || !(o.g > 0.0)) continue;
+            for (int j = 0; j < ne; j++) Eg[j] = E[j] / o.g;
+            planck_grid(T, p->spec_hardf, (p->spec_limb && o.mue >= 0.0) ? o.mue : -1.0, Eg, Iv, ne);
+            for (int j = 0; j < ne; j++) h[j] += Iv[j] * (o.g * o.g * o.g) * dA;
+        }
+    }
+    for (int k = 0; k < ne; k++) {
+        double s = 0.0;
+        for (iy = rb; iy < re; iy++) s += rows[(size_t)iy * ne + k];
+        spec[k] = s;
     }
     free(rows);
     return now_s() - t0;

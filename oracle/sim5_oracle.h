@@ -13,6 +13,7 @@ extern "C" {
  * -3 STEPWISE (not restated; checked against oracle/_ref and tests/golden/image_cfg4_16.npz). */
 double orc_trace_image(const sim5_image_params* p, const sim5_image_out* out, int nthreads, sim5_trace_stats* stats);
 double orc_trace_histogram(const sim5_image_params* p, double* hist, int nthreads);
+double orc_trace_spectrum(const sim5_image_params* p, double* spec, int nthreads);
 int    orc_max_threads(void);
 double orc_r_ms(double a);
 double orc_rf(double x, double y, double z);

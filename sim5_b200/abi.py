@@ -7,7 +7,7 @@ import ctypes as C
 import math
 
 # modes
-MODE_EQPLANE, MODE_POLARIZED, MODE_STEPWISE, MODE_HISTOGRAM = 0, 1, 2, 3
+MODE_EQPLANE, MODE_POLARIZED, MODE_STEPWISE, MODE_HISTOGRAM, MODE_SPECTRUM = 0, 1, 2, 3, 4
 # outputs
 OUT_R, OUT_PHI, OUT_G, OUT_FLUX = 0x001, 0x002, 0x004, 0x008
 OUT_CHI, OUT_DELTA, OUT_MUE = 0x010, 0x020, 0x040
@@ -47,6 +47,8 @@ class ImageParams(C.Structure):
         ("spin_max", C.c_double), ("incl_min_deg", C.c_double), ("incl_max_deg", C.c_double),
         ("g_min", C.c_double), ("g_max", C.c_double), ("rmax_offset", C.c_double),
         ("split_count", C.c_int32), ("split_index", C.c_int32), ("split_rows", C.c_int32), ("reserved2", C.c_int32),
+        ("n_energy", C.c_int32), ("spec_limb", C.c_int32),
+        ("e_min_kev", C.c_double), ("e_max_kev", C.c_double), ("spec_hardf", C.c_double),
     ]
 
 
@@ -55,7 +57,7 @@ class ImageOut(C.Structure):
         ("r", C.c_void_p), ("phi", C.c_void_p), ("g", C.c_void_p), ("flux", C.c_void_p),
         ("chi", C.c_void_p), ("delta", C.c_void_p), ("mue", C.c_void_p), ("intensity", C.c_void_p),
         ("tau", C.c_void_p), ("qerr", C.c_void_p), ("steps", C.c_void_p), ("status", C.c_void_p),
-        ("hist", C.c_void_p),
+        ("hist", C.c_void_p), ("spectrum", C.c_void_p),
     ]
 
 
@@ -85,8 +87,16 @@ def ell_kepler(r, a):
     return (r * r - 2. * a * math.sqrt(r) + a * a) / (math.sqrt(r) * r - 2. * math.sqrt(r) + a)
 
 
+def spectrum_energies(p):
+    """The detector energies [keV] of a SPECTRUM call, spelled as the library computes them (libm pow)."""
+    n = p.n_energy
+    if n == 1:
+        return [p.e_min_kev]
+    return [p.e_min_kev * math.pow(p.e_max_kev / p.e_min_kev, k / (n - 1)) for k in range(n)]
+
+
 def default_params(cfg, nx=None, ny=None):
-    """BASELINE.json configs 1..5 with the open parameters fixed as in SURVEY.md 8(d)."""
+    """BASELINE.json configs 1..5 with the open parameters fixed as in SURVEY.md 8(d); 6 = the SPECTRUM preset."""
     p = ImageParams()
     p.struct_size = C.sizeof(ImageParams)
     p.max_order = 1
@@ -97,6 +107,7 @@ def default_params(cfg, nx=None, ny=None):
     p.n_spin, p.n_incl, p.n_bins = 64, 32, 256
     p.spin_max, p.incl_min_deg, p.incl_max_deg = 0.998, 5.0, 85.0
     p.g_min, p.g_max, p.rmax_offset = 0.0, 2.0, 20.0
+    p.n_energy, p.spec_limb, p.e_min_kev, p.e_max_kev, p.spec_hardf = 128, 1, 0.05, 50.0, 1.7
     if cfg == 1:
         p.mode, p.nx, p.ny = MODE_EQPLANE, 512, 512
         p.bh_spin, p.incl = 0.9, deg2rad(70.0)
@@ -122,8 +133,13 @@ def default_params(cfg, nx=None, ny=None):
         p.bh_spin, p.incl = 0.998, deg2rad(75.0)   # unused: the lattice defines spin/inclination
         p.rmax = 0.0
         p.outputs = 0
+    elif cfg == 6:
+        p.mode, p.nx, p.ny = MODE_SPECTRUM, 2048, 2048
+        p.bh_spin, p.incl = 0.998, deg2rad(75.0)
+        p.rmax = r_ms(p.bh_spin) + 20.0
+        p.outputs = 0
     else:
-        raise ValueError("cfg must be 1..5")
+        raise ValueError("cfg must be 1..6")
     p.torus_ell = ell_kepler(p.torus_rc, p.bh_spin)
     if nx is not None:
         p.nx = nx

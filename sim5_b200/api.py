@@ -138,6 +138,10 @@ class HostPlanes:
             a = np.zeros(nh, dtype=np.float64)
             self.arrays["hist"] = a
             self.out.hist = a.ctypes.data
+        if p.mode == abi.MODE_SPECTRUM:
+            a = np.zeros(p.n_energy, dtype=np.float64)
+            self.arrays["spectrum"] = a
+            self.out.spectrum = a.ctypes.data
 
     def __getitem__(self, k):
         return self.arrays[k]

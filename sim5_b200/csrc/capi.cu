@@ -255,6 +255,61 @@ int trace_histogram(const sim5_image_params* p, const sim5_image_out* out, sim5_
     return SIM5_OK;
 }
 
+/* mode SPECTRUM: rows [row_begin,row_end) (and the interleaved split) of one image summed into out->spectrum[n_energy] (host) */
+int trace_spectrum(const sim5_image_params* p, const sim5_image_out* out, sim5_trace_stats* stats)
+{
+    Context& c = g_ctx;
+    if (!out->spectrum) { set_error("SPECTRUM mode needs out->spectrum"); return SIM5_ERR_NO_OUTPUT; }
+    if (p->n_energy < 1 || p->n_energy > S5_SPEC_MAX_E || !(p->e_min_kev > 0.0) || !(p->e_max_kev >= p->e_min_kev) || !(p->spec_hardf > 0.0)) {
+        set_error("bad spectrum grid (1 <= n_energy <= 256, 0 < e_min_kev <= e_max_kev, spec_hardf > 0)"); return SIM5_ERR_BAD_PARAM;
+    }
+    int rb = p->row_begin, re = p->row_end;
+    if (rb == 0 && re == 0) re = p->ny;
+    if (rb < 0 || re > p->ny || rb > re) { set_error("bad row range"); return SIM5_ERR_BAD_PARAM; }
+    if (p->max_order < 0 || p->max_order > 2) { set_error("max_order must be 0..2"); return SIM5_ERR_BAD_PARAM; }
+    int split = p->split_count > 1 ? p->split_count : 1;
+    int srows = p->split_rows > 0 ? p->split_rows : 1;
+    if (split > 1 && ((p->split_index < 0 || p->split_index >= split) || (re - rb) % (split * srows) != 0)) { set_error("bad split"); return SIM5_ERR_BAD_PARAM; }
+    sim5_image_params q = *p;
+    q.mode = SIM5_MODE_POLARIZED;                      /* the pixel pipeline the spectrum sits on: g and mu_e from the emitter frame */
+    q.outputs = SIM5_OUT_R | SIM5_OUT_G | SIM5_OUT_MUE;
+    S5ImageConsts consts;
+    s5_fill_image_consts(&q, &consts);
+    const int ne = p->n_energy;
+    int rc = reserve(c.hist, 2 * (size_t)S5_SPEC_MAX_E * sizeof(double));
+    if (rc) return rc;
+    double* d_e = (double*)c.hist.p;
+    double* d_spec = d_e + S5_SPEC_MAX_E;
+    double h_e[S5_SPEC_MAX_E];
+    for (int k = 0; k < ne; k++) h_e[k] = s5_spectrum_energy(p, k);
+    CK(cudaEventRecord(c.ev0, c.stream));
+    CK(cudaMemcpyAsync(d_e, h_e, ne * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    CK(cudaMemsetAsync(d_spec, 0, S5_SPEC_MAX_E * sizeof(double), c.stream));
+    CK(cudaMemsetAsync(c.d_counter, 0, sizeof(unsigned long long), c.stream));
+    CK(cudaMemsetAsync(c.d_stats, 0, sizeof(DevStats), c.stream));
+    int grid = persistent_grid(s5::k_trace_spectrum, S5_CTA_THREADS);
+    CK(cudaEventRecord(c.ev1, c.stream));
+    if (consts.nrows_local > 0) s5::k_trace_spectrum<<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d_e, d_spec, c.d_counter, c.d_stats);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c.ev2, c.stream));
+    CK(cudaMemcpyAsync(out->spectrum, d_spec, ne * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaMemcpyAsync(c.h_stats, c.d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaEventRecord(c.ev3, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    c.phases = 0;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->rays = (int64_t)consts.nrows_local * p->nx;
+        for (int i = 0; i < 32; i++) stats->class_count[i] = (int64_t)c.h_stats->cls[i];
+        for (int i = 0; i < 8; i++) stats->gtype_count[i] = (int64_t)c.h_stats->gtype[i];
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c.ev1, c.ev2); stats->kernel_ms = ms;
+        cudaEventElapsedTime(&ms, c.ev0, c.ev3); stats->total_ms = ms;
+        stats->kernel_launches = 1; stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = S5_CTA_THREADS;
+    }
+    return SIM5_OK;
+}
+
 } /* anonymous namespace */
 
 /* ------------------------------------------------------------------ */
@@ -373,7 +428,7 @@ extern "C" int sim5_device_to_host(void* dst, const void* src, size_t bytes)
 /* the open parameters of the five BASELINE configs */
 extern "C" int sim5_default_params(int cfg, sim5_image_params* p)
 {
-    if (!p || cfg < 1 || cfg > 5) return SIM5_ERR_BAD_PARAM;
+    if (!p || cfg < 1 || cfg > 6) return SIM5_ERR_BAD_PARAM;
     memset(p, 0, sizeof(*p));
     p->struct_size = (int32_t)sizeof(*p);
     p->max_order = 1;
@@ -383,6 +438,7 @@ extern "C" int sim5_default_params(int cfg, sim5_image_params* p)
     p->n_spin = 64; p->n_incl = 32; p->n_bins = 256;
     p->spin_max = 0.998; p->incl_min_deg = 5.0; p->incl_max_deg = 85.0;
     p->g_min = 0.0; p->g_max = 2.0; p->rmax_offset = 20.0;
+    p->n_energy = 128; p->spec_limb = 1; p->e_min_kev = 0.05; p->e_max_kev = 50.0; p->spec_hardf = 1.7;
     switch (cfg) {
         case 1: p->mode = SIM5_MODE_EQPLANE; p->nx = p->ny = 512; p->bh_spin = 0.9; p->incl = 70.0 / 180.0 * M_PI;
                 p->rmax = s5_host_r_ms(p->bh_spin) + 8.0; p->outputs = SIM5_OUT_R | SIM5_OUT_G | SIM5_OUT_FLUX | SIM5_OUT_STATUS; break;
@@ -395,6 +451,8 @@ extern "C" int sim5_default_params(int cfg, sim5_image_params* p)
                 p->rmax = 25.0; p->outputs = SIM5_OUT_INTENSITY | SIM5_OUT_TAU | SIM5_OUT_STEPS | SIM5_OUT_STATUS; break;
         case 5: p->mode = SIM5_MODE_HISTOGRAM; p->nx = p->ny = 1024; p->bh_spin = 0.998; p->incl = 75.0 / 180.0 * M_PI;
                 p->rmax = 0.0; p->outputs = 0; break;
+        case 6: p->mode = SIM5_MODE_SPECTRUM; p->nx = p->ny = 2048; p->bh_spin = 0.998; p->incl = 75.0 / 180.0 * M_PI;
+                p->rmax = s5_host_r_ms(p->bh_spin) + 20.0; p->outputs = 0; break;
     }
     {   /* ellK(torus_rc, a), sim5kerr.c:1050-1071 */
         double r = p->torus_rc, a = p->bh_spin;
@@ -411,12 +469,13 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     if (!p || !out) { set_error("null params/out"); return SIM5_ERR_BAD_PARAM; }
     if (p->struct_size != (int32_t)sizeof(sim5_image_params)) { set_error("sim5_image_params.struct_size mismatch"); return SIM5_ERR_BAD_PARAM; }
     if (p->nx <= 0 || p->ny <= 0) { set_error("empty image"); return SIM5_ERR_BAD_PARAM; }
-    if (p->mode < SIM5_MODE_EQPLANE || p->mode > SIM5_MODE_HISTOGRAM) { set_error("unknown mode"); return SIM5_ERR_BAD_PARAM; }
+    if (p->mode < SIM5_MODE_EQPLANE || p->mode > SIM5_MODE_SPECTRUM) { set_error("unknown mode"); return SIM5_ERR_BAD_PARAM; }
     std::lock_guard<std::mutex> lk(g_ctx.mu);
     int rc = ensure_init(p->device);
     if (rc) return rc;
     Context& c = g_ctx;
     if (p->mode == SIM5_MODE_HISTOGRAM) return trace_histogram(p, out, stats);
+    if (p->mode == SIM5_MODE_SPECTRUM) return trace_spectrum(p, out, stats);
 
     int rb = p->row_begin, re = p->row_end;
     if (rb == 0 && re == 0) re = p->ny;

@@ -42,6 +42,10 @@ struct S5ImageConsts {
     /* histogram */
     double g_min, g_max, da, db;  /* pixel size in alpha and beta (histogram weight F*g^4*da*db) */
     int n_bins, pad1;
+    /* spectrum (sim5radiation.c:56-78 blackbody(), constants of sim5const.h) */
+    double bb1;          /* 2 h / c^2 / hardf^4 * kev2freq^4 */
+    double bb2;          /* h kev2freq / (k_B hardf)  -- BB2 of blackbody() is bb2 / T */
+    int n_energy, spec_limb;
     /* Chandrasekhar table (harness, sim5_b200.h) */
     double chandra[SIM5_CHANDRA_N];
 };
@@ -135,7 +139,23 @@ static inline void s5_fill_image_consts(const sim5_image_params* p, S5ImageConst
         c->da = 2.0 * p->rmax / (double)p->nx;
         c->db = 2.0 * p->rmax * ((double)p->ny / (double)p->nx) / (double)p->ny;
     }
+    {
+        /* planck_h, speed_of_light, boltzmann_k, kev2freq of sim5const.h:33-87; expression order of sim5radiation.c:73-75 */
+        const double planck_h = 6.626069e-27, speed_of_light = 2.997925e+10, boltzmann_k = 1.380650e-16, kev2freq = 2.417990e+17;
+        double hf = p->spec_hardf > 0.0 ? p->spec_hardf : 1.0;
+        c->bb1 = 2.0 * planck_h / (speed_of_light * speed_of_light) / (hf * hf * hf * hf) * (kev2freq * kev2freq * kev2freq * kev2freq);
+        c->bb2 = (planck_h * kev2freq) / (boltzmann_k * hf);
+        c->n_energy = p->n_energy;
+        c->spec_limb = p->spec_limb;
+    }
     for (int i = 0; i < SIM5_CHANDRA_N; i++) c->chandra[i] = SIM5_CHANDRA_DELTA[i];
+}
+
+/* detector energies of a SPECTRUM call [keV], host libm: shared by the library, the reference driver and the oracle */
+static inline double s5_spectrum_energy(const sim5_image_params* p, int k)
+{
+    if (p->n_energy <= 1) return p->e_min_kev;
+    return p->e_min_kev * pow(p->e_max_kev / p->e_min_kev, (double)k / (double)(p->n_energy - 1));
 }
 
 #endif

@@ -434,6 +434,73 @@ k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice i
 }
 
 /* ------------------------------------------------------------------ */
+/* mode SPECTRUM : thermal disk spectrum summed over the image          */
+/* ------------------------------------------------------------------ */
+/* Phase A per pixel (polarized flavour: g and mu_e from the emitter frame), then the black-body sum.  The sum is done
+ * TRANSPOSED inside the warp: lane j owns the energies k = j, j+32, ... (<= 8 per lane) and walks the warp's 32 hits, whose
+ * three per-hit numbers arrive by shuffle -- so every lane accumulates in registers and there is no per-term reduction.
+ * Lanes flush once per kernel: shared-memory atomics per CTA, then one global atomic per CTA and energy. */
+#define S5_SPEC_MAX_E 256
+__global__ void __launch_bounds__(S5_CTA_THREADS, 3)      /* 168 registers: the 8 energies + 8 accumulators per lane live across the pixel routine */
+k_trace_spectrum(const __grid_constant__ S5ImageConsts gconsts, const double* __restrict__ energies, double* __restrict__ spec,
+                 unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
+{
+    __shared__ S5ImageConsts c;
+    __shared__ unsigned int s_cnt[40];
+    __shared__ double s_spec[S5_SPEC_MAX_E];
+    if (threadIdx.x < 40) s_cnt[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < S5_SPEC_MAX_E; i += blockDim.x) s_spec[i] = 0.0;
+    stage_consts(&c, &gconsts);
+
+    const int lane = threadIdx.x & 31;
+    const long long nx = c.nx;
+    const long long npix = (long long)c.nrows_local * nx;
+    const long long ntiles = (npix + 31) >> 5;
+    const int ne = c.n_energy;
+    double Ek[S5_SPEC_MAX_E / 32], acc[S5_SPEC_MAX_E / 32];
+    #pragma unroll
+    for (int j = 0; j < S5_SPEC_MAX_E / 32; j++) { int k = lane + 32 * j; Ek[j] = (k < ne) ? energies[k] : 1.0; acc[j] = 0.0; }
+
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1ULL);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((long long)t >= ntiles) break;
+        long long p = ((long long)t << 5) + lane;
+        SpecHit h;
+        h.amp3 = 0.0; h.ginv = 1.0; h.xs = 1.0;
+        bool hit = false;
+        if (p < npix) {
+            int lr = (int)(p / nx);
+            int ix = (int)(p - (long long)lr * nx);
+            int iy = s5_local_to_image_row(&c, lr);
+            unsigned status;
+            hit = spectrum_pixel(c, ix, iy, &h, &status);
+            atomicAdd(&s_cnt[status & 31], 1u);
+            atomicAdd(&s_cnt[32 + ((status >> 5) & 7)], 1u);
+        }
+        unsigned hits = __ballot_sync(0xffffffffu, hit);
+        for (unsigned m = hits; m; m &= m - 1) {
+            int src = __ffs(m) - 1;
+            SpecHit hs;
+            hs.amp3 = __shfl_sync(0xffffffffu, h.amp3, src);
+            hs.ginv = __shfl_sync(0xffffffffu, h.ginv, src);
+            hs.xs = __shfl_sync(0xffffffffu, h.xs, src);
+            #pragma unroll
+            for (int j = 0; j < S5_SPEC_MAX_E / 32; j++)
+                if (lane + 32 * j < ne) acc[j] += spectrum_term(hs, Ek[j]);
+        }
+    }
+    #pragma unroll
+    for (int j = 0; j < S5_SPEC_MAX_E / 32; j++)
+        if (lane + 32 * j < ne && acc[j] != 0.0) atomicAdd(&s_spec[lane + 32 * j], acc[j]);
+    __syncthreads();
+    for (int k = threadIdx.x; k < ne; k += blockDim.x)
+        if (s_spec[k] != 0.0) atomicAdd(&spec[k], s_spec[k]);
+    flush_stats(s_cnt, 0, gstats);
+}
+
+/* ------------------------------------------------------------------ */
 /* FP64 DFMA-chain microbenchmark (roofline denominator)               */
 /* ------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed)

@@ -674,6 +674,35 @@ S5_HD S5_INL void trace_eqplane_pixel(const S5ImageConsts& c, int ix, int iy, Pi
     trace_eqplane_pixel_t<false>(c, ix, iy, o, nullptr);
 }
 
+/* mode SPECTRUM: what one disk hit contributes.  Returns false for pixels without a hit (or with T = 0 / g <= 0, which
+ * DiskRaytrace.spectrum skips, python/sim5diskraytrace.py:100,115).  The contribution to energy E_k is
+ *     amp * E_k^3 / expm1(xs * E_k)        (blackbody() of sim5radiation.c:73-76 at E_k/g, times g^3 dalpha dbeta)
+ * with the (1/g)^3 of the emitted energy and the g^3 of the intensity invariant kept as the reference has them. */
+struct SpecHit { double amp3, ginv, xs; };      /* amp3 = limb factor * BB1 * g^3 * dalpha dbeta ; ginv = 1/g ; xs = BB2 (hardening and T included) */
+S5_HD S5_INL bool spectrum_pixel(const S5ImageConsts& c, int ix, int iy, SpecHit* h, unsigned* status)
+{
+    PixelOut o;
+    trace_eqplane_pixel_t<false>(c, ix, iy, &o, nullptr);      /* c.mode == POLARIZED: g and mu_e from the Keplerian emitter frame */
+    *status = o.status;
+    unsigned cls = o.status & 31;
+    if (!(cls == SIM5_ST_HIT0 || cls == SIM5_ST_HIT1 || cls == SIM5_ST_HIT2)) return false;
+    double F = disk_nt_flux(c, o.r);
+    double T = sqrt(sqrt(F / 5.670400e-05));                   /* T_eff = (F / sigma_SB)^(1/4), python/sim5diskmodel.py:48 */
+    if (!(T > 0.0) || !(o.g > 0.0)) return false;
+    double limbf = (c.spec_limb && o.mue >= 0.0) ? 0.5 + 0.75 * o.mue : 1.0;
+    h->amp3 = limbf * c.bb1 * (o.g * o.g * o.g) * (c.da * c.db);
+    h->ginv = 1.0 / o.g;
+    h->xs = c.bb2 / T;
+    return true;
+}
+/* one (hit, energy) term: Iv = BB1 E^3 / expm1(BB2 E) at E = E_k / g, times g^3 dA -- with the per-hit factors hoisted
+ * (the reference-side driver divides and multiplies per term; the two agree to rounding, far inside the 1e-7 bar) */
+S5_HD S5_INL double spectrum_term(const SpecHit& h, double Ek)
+{
+    double E = Ek * h.ginv;
+    return h.amp3 * (E * E * E) * ff::rcp_ap(expm1(h.xs * E));
+}
+
 /* mode STEPWISE: raytrace() through the harness torus (SURVEY.md 8d cfg 4; oracle/ref_driver.c pixel_stepwise) */
 struct StepRay {           /* live state of one stepwise ray (the persistent kernel keeps this per lane) */
     double x[4], k[4];

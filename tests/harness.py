@@ -44,6 +44,8 @@ def load_ref():
                                         C.POINTER(abi.TraceStats)]
         lib.ref_trace_histogram.restype = C.c_double
         lib.ref_trace_histogram.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(C.c_double), C.c_int, C.c_int]
+        lib.ref_trace_spectrum.restype = C.c_double
+        lib.ref_trace_spectrum.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(C.c_double), C.c_int, C.c_int]
         lib.ref_r_ms.restype = C.c_double
         lib.ref_r_ms.argtypes = [C.c_double]
         lib.ref_r_bh.restype = C.c_double
@@ -61,6 +63,8 @@ def load_oracle():
                                         C.POINTER(abi.TraceStats)]
         lib.orc_trace_histogram.restype = C.c_double
         lib.orc_trace_histogram.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(C.c_double), C.c_int]
+        lib.orc_trace_spectrum.restype = C.c_double
+        lib.orc_trace_spectrum.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(C.c_double), C.c_int]
         _libs["oracle"] = lib
     return _libs["oracle"]
 
@@ -171,6 +175,8 @@ def load_hostsim():
         lib = C.CDLL(os.path.join(ROOT, "tests", "_build", "libhostsim.so"))
         lib.hs_trace_image.restype = C.c_double
         lib.hs_trace_image.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(abi.ImageOut), C.c_int]
+        lib.hs_trace_spectrum.restype = C.c_double
+        lib.hs_trace_spectrum.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(C.c_double), C.c_int]
         _libs["hostsim"] = lib
     return _libs["hostsim"]
 
@@ -179,6 +185,21 @@ def run_hostsim(p, nthreads=0):
     pl = Planes(p)
     dt = load_hostsim().hs_trace_image(C.byref(p), C.byref(pl.out), nthreads)
     return pl, None, dt
+
+
+def run_spectrum(which, p, nthreads=0):
+    """SPECTRUM mode through one of the CPU implementations: 'ref' (unmodified reference + driver), 'oracle' (C restatement),
+    'hostsim' (host instantiation of the device headers).  Returns (spectrum[n_energy], seconds)."""
+    spec = np.zeros(p.n_energy)
+    ptr = spec.ctypes.data_as(C.POINTER(C.c_double))
+    if which == "ref":
+        dt = load_ref().ref_trace_spectrum(C.byref(p), ptr, nthreads, 1)
+    elif which == "oracle":
+        dt = load_oracle().orc_trace_spectrum(C.byref(p), ptr, nthreads)
+    else:
+        dt = load_hostsim().hs_trace_spectrum(C.byref(p), ptr, nthreads)
+    assert dt >= 0, "%s spectrum failed (%r)" % (which, dt)
+    return spec, dt
 
 
 def golden(name):

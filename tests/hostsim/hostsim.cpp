@@ -9,6 +9,7 @@
 // links or loads it and has no CPU path.
 #include <omp.h>
 #include <stdio.h>
+#include <vector>
 #include "../../sim5_b200/csrc/pixel.cuh"
 
 using namespace s5;
@@ -111,6 +112,33 @@ void hs_fast_azimuth_coverage(const sim5_image_params* p, long* counts)
         }
     }
     counts[0] = n0; counts[1] = n1; counts[2] = n2; counts[3] = n3;
+}
+
+// mode SPECTRUM on the host instantiation: per-row partial sums added in row order (the kernel's atomics add in another order)
+double hs_trace_spectrum(const sim5_image_params* p, double* spec, int nthreads)
+{
+    sim5_image_params q = *p;
+    q.mode = SIM5_MODE_POLARIZED;
+    q.outputs = SIM5_OUT_R | SIM5_OUT_G | SIM5_OUT_MUE;
+    S5ImageConsts c;
+    s5_fill_image_consts(&q, &c);
+    int ne = p->n_energy;
+    std::vector<double> E(ne), part((size_t)ne * c.ny, 0.0);
+    for (int k = 0; k < ne; k++) E[k] = s5_spectrum_energy(p, k);
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+    double t0 = omp_get_wtime();
+    #pragma omp parallel for schedule(dynamic, 4)
+    for (int lr = 0; lr < c.nrows_local; lr++) {
+        int iy = s5_local_to_image_row(&c, lr);
+        double* h = part.data() + (size_t)iy * ne;
+        for (int ix = 0; ix < c.nx; ix++) {
+            SpecHit sh; unsigned status;
+            if (!spectrum_pixel(c, ix, iy, &sh, &status)) continue;
+            for (int k = 0; k < ne; k++) h[k] += spectrum_term(sh, E[k]);
+        }
+    }
+    for (int k = 0; k < ne; k++) { double s = 0.0; for (int iy = 0; iy < c.ny; iy++) s += part[(size_t)iy * ne + k]; spec[k] = s; }
+    return omp_get_wtime() - t0;
 }
 
 double hs_trace_image(const sim5_image_params* p, const sim5_image_out* out, int nthreads)

@@ -60,7 +60,7 @@ int main(void) {
 
 def test_default_params_agree_with_python_presets():
     L = api.lib()
-    for cfg in range(1, 6):
+    for cfg in range(1, 7):
         q = abi.ImageParams()
         assert L.sim5_default_params(cfg, C.byref(q)) == 0
         p = abi.default_params(cfg)

@@ -51,6 +51,13 @@ def main():
     pl, st, _ = H.run_ref(p)
     np.savez_compressed(os.path.join(OUT, "image_cfg2_50x37.npz"), **pl.arrays)
 
+    # ---- thermal spectrum (SPECTRUM preset shrunk), incl. a partial spectrum of an interleaved split
+    p = abi.default_params(6, 96)
+    spec, _ = H.run_spectrum("ref", p)
+    p.split_count, p.split_index, p.split_rows = 3, 1, 8
+    part, _ = H.run_spectrum("ref", p)
+    np.savez_compressed(os.path.join(OUT, "spectrum_cfg6_96.npz"), spectrum=spec, part_3_1_8=part, energies=np.array(abi.spectrum_energies(abi.default_params(6, 96))))
+
     # ---- histogram lattice (cfg 5 shrunk)
     p = abi.default_params(5, 48)
     p.n_spin, p.n_incl, p.n_bins = 3, 2, 32
