@@ -44,6 +44,9 @@ extern "C" {
 #define SIM5_MODE_SPECTRUM       4   /* observed thermal spectrum of the thin disk: sum over the image of the (limb-darkened, colour-corrected)
                                         black-body intensity of every disk hit -- DiskRaytrace.spectrum of the reference's Python layer
                                         (python/sim5diskraytrace.py:43-134) on the image grid, blackbody() of sim5radiation.c:56-78 */
+#define SIM5_MODE_SURFACE        5   /* image of a geometrically THICK disk: the ray is followed analytically (geodesic_P_int -> geodesic_follow
+                                        with the adaptive step of DiskRaytrace.__find_surface, python/sim5diskraytrace.py:214-336) until it meets the
+                                        surface H(R); g-factor and emission cosine from tetrad_surface (python/sim5diskraytrace.py:340-391) */
 
 /* output plane selector bits (all planes are row-major [ny][nx], index iy*nx+ix) */
 #define SIM5_OUT_R            0x001  /* radius of the disk hit                      (double) */
@@ -58,6 +61,9 @@ extern "C" {
 #define SIM5_OUT_STEPS        0x200  /* STEPWISE: number of raytrace() calls        (int32)  */
 #define SIM5_OUT_STATUS       0x400  /* classification / termination byte           (uint8)  */
 #define SIM5_OUT_QERR         0x800  /* STEPWISE: raytrace_error() at the end       (double) */
+#define SIM5_OUT_HEIGHT      0x1000  /* SURFACE: height r*cos(theta) of the hit     (double) */
+#define SIM5_OUT_DELAY       0x2000  /* EQPLANE/POLARIZED: geodesic_timedelay() between the disk hit and the sphere r = delay_r_ref (double) */
+#define SIM5_NPLANES             14
 
 /* flags */
 #define SIM5_FLAG_DEVICE_PTRS   0x1  /* pointers in sim5_image_out are device pointers (no staging, no D2H) */
@@ -92,6 +98,11 @@ extern "C" {
 #define SIM5_ST_ERRBREAK        10   /* rtd.error > 1e-2 */
 #define SIM5_ST_MAXSTEPS        11
 #define SIM5_ST_NOSTART         12   /* ray never reaches r_start (r_start < pericentre) or start position undefined */
+/* SURFACE terminations (HIT0 = the surface was found; HORIZON, ESCAPE = left 1.1 r0 four times, MAXSTEPS = step underflow are shared) */
+#define SIM5_ST_SURF_UNDER       7   /* the ray passed below the equatorial plane (m < 0) */
+#define SIM5_ST_SURF_EQPLANE    13   /* the ray reached the equatorial plane (H < 1e-4) before any surface: result = midplane crossing */
+#define SIM5_ST_SURF_BELOW      14   /* the start point of the search already lies below the surface */
+#define SIM5_ST_SURF_LOST       15   /* geodesic_follow() reported status 0 (horizon or end of the position integral) */
 /* init errors: 16 + GD_ERROR_* of geodesic_init_inf */
 #define SIM5_ST_INITERR         16
 #define SIM5_ST_CLASS(s)        ((s) & 0x1f)
@@ -169,6 +180,12 @@ typedef struct sim5_image_params {
      * [erg cm^-2 s^-1 keV^-1 srad^-1 x (GM/c^2)^2]; the caller multiplies by (GM/c^2 / D)^2 */
     int32_t  n_energy, spec_limb;
     double   e_min_kev, e_max_kev, spec_hardf;
+    /* SURFACE: harness-defined disk surface H(R) = surf_hr (R - surf_rin)^2 / R for R > surf_rin, 0 inside (dH/dR = surf_hr (1 - surf_rin^2/R^2)),
+     * R = r sin(theta); Keplerian rotation ell = ellK(R, a), no radial drift, Novikov-Thorne flux at R.  surf_hr = 0: flat disk
+     * (the `flat` branch of DiskRaytrace.geodesic).  surf_rin <= 0: r_ms(bh_spin) */
+    double   surf_hr, surf_rin;
+    /* SIM5_OUT_DELAY: radius of the sphere the travel time is measured to (> every disk radius in the image) */
+    double   delay_r_ref;
 } sim5_image_params;
 
 typedef struct sim5_image_out {
@@ -186,6 +203,8 @@ typedef struct sim5_image_out {
     uint8_t *status;
     double  *hist;               /* [n_spin][n_incl][n_bins] */
     double  *spectrum;           /* SPECTRUM: [n_energy], always a HOST array (it is 2 KB) */
+    double  *height;
+    double  *delay;
 } sim5_image_out;
 
 typedef struct sim5_trace_stats {
@@ -224,7 +243,8 @@ void* sim5_ipc_import(const void* handle64);
 int   sim5_ipc_release(void* imported_ptr);
 
 /* defaults: fills every field with the SURVEY.md 8(d) definition of BASELINE config `cfg` (1..5); 6 = the SPECTRUM preset
- * (the camera of config 2 at 2048^2, 128 energies 0.05..50 keV, hardening 1.7, limb darkening on) */
+ * (the camera of config 2 at 2048^2, 128 energies 0.05..50 keV, hardening 1.7, limb darkening on); 7 = the SURFACE preset (a = 0.9,
+ * i = 60 deg, 1024^2, rmax = 30, H/R -> 0.2, inner edge r_ms) */
 int  sim5_default_params(int cfg, sim5_image_params* p);
 
 /* THE batched entry: replaces the per-pixel loop of disk-image.c:53-105 */

@@ -41,7 +41,7 @@ static int gtype_code(int type, int have)
 }
 
 typedef struct pixel_result {
-    double r, phi, g, flux, chi, delta, mue, intensity, tau, qerr;
+    double r, phi, g, flux, chi, delta, mue, intensity, tau, qerr, height, delay;
     int steps;
     unsigned char status;
 } pixel_result;
@@ -195,6 +195,139 @@ static void pixel_stepwise(const sim5_image_params* p, double alpha, double beta
     o->status = (unsigned char)(st | gt);
 }
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * mode SURFACE: DiskRaytrace.geodesic / __find_surface / image of the reference's Python layer
+ * (python/sim5diskraytrace.py:214-336, 163-205, 340-391) spelled in C, every physics call the reference's own.
+ * The disk model (python: a dlopen'ed plug-in, src/sim5disk.c) is the harness surface of sim5_b200.h.
+ * ------------------------------------------------------------------------------------------------------------ */
+static double surf_rin(const sim5_image_params* p) { return (p->surf_rin > 0.0) ? p->surf_rin : r_ms(p->bh_spin); }
+static double surf_h(const sim5_image_params* p, double R)
+{
+    double rin = surf_rin(p);
+    return (R > rin) ? p->surf_hr * sqr(R - rin) / R : 0.0;
+}
+static double surf_dhdr(const sim5_image_params* p, double R)
+{
+    double rin = surf_rin(p);
+    return (R > rin) ? p->surf_hr * (1.0 - sqr(rin) / sqr(R)) : 0.0;
+}
+
+/* __find_surface (python/sim5diskraytrace.py:259-336); the recursion on `iteration` is the outer loop.
+ * Returns the termination class; on SIM5_ST_HIT0 / SIM5_ST_SURF_EQPLANE (P, r, m) is the result. */
+static int find_surface(const sim5_image_params* p, geodesic* gd, double* Po, double* ro, double* mo, int* nfollow)
+{
+    const double accuracy = 1e-2;
+    double disk_theta = atan(surf_h(p, 1e6) / 1e6);
+    double rbh = r_bh(p->bh_spin);
+    int iteration;
+    for (iteration = 0; ; iteration++) {
+        if (iteration > 3) return SIM5_ST_ESCAPE;
+        double r0 = fmax(fmax(200.0, 1.1 * gd->rp), (0.5 + iteration) * sqrt(sqr(gd->alpha) + sqr(gd->beta)) / cos(gd->incl + disk_theta));
+        double P1, r1, m1, R1, H1, Hd;
+        while (1) {
+            P1 = geodesic_P_int(gd, r0, 0);
+            r1 = geodesic_position_rad(gd, P1);
+            m1 = geodesic_position_pol(gd, P1);
+            R1 = r1 * sqrt(1. - m1 * m1);
+            H1 = r1 * m1;
+            Hd = surf_h(p, R1);
+            if ((Hd < H1) || (r0 > 5e6)) break;
+            r0 = 2.0 * r0;
+        }
+        if (!(Hd < H1)) return SIM5_ST_SURF_BELOW;          /* python: if (Hd >= H1) -- NaN compares false there and goes on; see below */
+        double P = P1, r = r1, m = m1;
+        int status = 0, restart = 0;
+        double step_factor = 1.0;
+        while (1) {
+            double step = fmax(accuracy / 2., fmin((H1 - Hd) / 2., 0.5 * (sqrt(r) - 0.99) * step_factor));
+            geodesic_follow(gd, step, &P, &r, &m, &status); (*nfollow)++;
+            if (!status) return SIM5_ST_SURF_LOST;
+            R1 = r * sqrt(1. - m * m);
+            H1 = r * m;
+            Hd = surf_h(p, R1);
+            if (H1 <= Hd) {
+                if (step < accuracy) {
+                    geodesic_follow(gd, -step / 2., &P, &r, &m, &status); (*nfollow)++;
+                    *Po = P; *ro = r; *mo = m;
+                    return SIM5_ST_HIT0;
+                }
+                geodesic_follow(gd, -step, &P, &r, &m, &status); (*nfollow)++;
+                step_factor = step_factor / 5.;
+                continue;
+            }
+            if (H1 < 1e-4) {
+                *Po = geodesic_find_midplane_crossing(gd, 0);
+                *ro = geodesic_position_rad(gd, *Po);
+                *mo = geodesic_position_pol(gd, *Po);
+                return SIM5_ST_SURF_EQPLANE;
+            }
+            if (r < 1.05 * rbh) return SIM5_ST_HORIZON;
+            if (r > 1.1 * r0) { restart = 1; break; }
+            if (m < 0.0) return SIM5_ST_SURF_UNDER;
+            if (step < accuracy / 2.) break;
+        }
+        if (!restart) return SIM5_ST_MAXSTEPS;
+    }
+}
+
+static void pixel_surface(const sim5_image_params* p, double alpha, double beta, pixel_result* o)
+{
+    geodesic gd;
+    int error = 0;
+    memset(o, 0, sizeof(*o));
+    double a = p->bh_spin;
+
+    geodesic_init_inf(p->incl, a, alpha, beta, &gd, &error);
+    if (error) {
+        int have = (error == GD_ERROR_TYPE_RR_DOUBLE);
+        o->status = (unsigned char)((SIM5_ST_INITERR + error) | (gtype_code(gd.type, have) << 5));
+        return;
+    }
+    int gt = gtype_code(gd.type, 1) << 5;
+    double P, r, m;
+    int cls, nfollow = 0;
+    if (surf_h(p, 1e5) == 0.0) {                        /* flat=(self.disk.h(1e5)==0.0), python/sim5diskraytrace.py:170,240-243 */
+        P = geodesic_find_midplane_crossing(&gd, 0);
+        r = geodesic_position_rad(&gd, P);
+        m = 0.0;
+        cls = SIM5_ST_SURF_EQPLANE;
+    } else {
+        cls = find_surface(p, &gd, &P, &r, &m, &nfollow);
+    }
+    o->steps = nfollow;
+    if (cls != SIM5_ST_HIT0 && cls != SIM5_ST_SURF_EQPLANE) { o->status = (unsigned char)(cls | gt); return; }
+    if (isnan(r)) { o->status = (unsigned char)(SIM5_ST_MISS | gt); return; }
+    o->status = (unsigned char)(cls | gt);
+
+    double k[4];
+    photon_momentum(a, r, m, gd.l, gd.q, gd.Rpc - P, 1.0, k);
+    double R = r * sqrt(1. - m * m);
+    o->r = r;
+    o->height = r * m;
+    double F = disk_nt_flux(R);
+    if (F == 0.0) return;                                /* image(): if (F == 0.0): continue */
+
+    sim5metric M;
+    sim5tetrad t;
+    double U[4], N[4];
+    double e0[4] = {1.0, 0.0, 0.0, 0.0};
+    double e2[4] = {0.0, 0.0, 1.0, 0.0};
+    kerr_metric(a, r, m, &M);                            /* __tetrad, :340-349; disk.l = Keplerian, disk.vr = 0 */
+    tetrad_surface(&M, Omega_from_ell(ellK(R, a), &M), 0.0, (m > 0.0) ? surf_dhdr(p, R) : 0.0, &t);
+    on2bl(e0, U, &t);
+    on2bl(e2, N, &t);
+    double g = (k[0] * M.g00 + k[3] * M.g03) / dotprod(k, U, &M);      /* __gfactor, :353-362 */
+    if (!(g > 0.0)) g = 0.0;
+    double mue = dotprod(k, N, &M) / dotprod(k, U, &M);                 /* __emission_angle, :378-391 */
+    if (mue < 0.0 && mue > -1e-2) mue = 1e-3;
+    double limb = 0.5 + 0.75 * mue;
+    if (!(g > 0.0)) return;                              /* image(): invalid g -> continue */
+    o->g = g;
+    o->mue = mue;
+    o->flux = F * pow(g, 4.) * limb;
+}
+
 static int silence_stderr(void)
 {
     fflush(stderr);
@@ -253,8 +386,9 @@ double ref_trace_image(const sim5_image_params* p, const sim5_image_out* out, in
             double alpha = (((double)(ix)+.5)/(double)(nx)-0.5)*2.0*rmax;
             double beta  = (((double)(iy)+.5)/(double)(ny)-0.5)*2.0*rmax * ((double)ny/(double)nx);
             pixel_result o;
-            if (p->mode == SIM5_MODE_STEPWISE) pixel_stepwise(p, alpha, beta, &o);
-            else                               pixel_eqplane(p, rmin, alpha, beta, &o);
+            if (p->mode == SIM5_MODE_STEPWISE)     pixel_stepwise(p, alpha, beta, &o);
+            else if (p->mode == SIM5_MODE_SURFACE) pixel_surface(p, alpha, beta, &o);
+            else                                   pixel_eqplane(p, rmin, alpha, beta, &o);
             size_t i = (size_t)iy*(size_t)nx + (size_t)ix;
             if ((p->outputs & SIM5_OUT_R)         && out->r)         out->r[i] = o.r;
             if ((p->outputs & SIM5_OUT_PHI)       && out->phi)       out->phi[i] = o.phi;
@@ -266,6 +400,8 @@ double ref_trace_image(const sim5_image_params* p, const sim5_image_out* out, in
             if ((p->outputs & SIM5_OUT_INTENSITY) && out->intensity) out->intensity[i] = o.intensity;
             if ((p->outputs & SIM5_OUT_TAU)       && out->tau)       out->tau[i] = o.tau;
             if ((p->outputs & SIM5_OUT_QERR)      && out->qerr)      out->qerr[i] = o.qerr;
+            if ((p->outputs & SIM5_OUT_HEIGHT)    && out->height)    out->height[i] = o.height;
+            if ((p->outputs & SIM5_OUT_DELAY)     && out->delay)     out->delay[i] = o.delay;
             if ((p->outputs & SIM5_OUT_STEPS)     && out->steps)     out->steps[i] = o.steps;
             if ((p->outputs & SIM5_OUT_STATUS)    && out->status)    out->status[i] = o.status;
         }

@@ -876,6 +876,7 @@ double orc_trace_image(const sim5_image_params* p, const sim5_image_out* out, in
     if (!p || !out) return -1.0;
     if (p->mode == SIM5_MODE_HISTOGRAM) return -2.0;
     if (p->mode == SIM5_MODE_STEPWISE) return -3.0;        /* not restated here: checked against oracle/_ref + golden */
+    if (p->mode == SIM5_MODE_SURFACE) return -3.0;         /* likewise (the surface finder is a caller-side loop over the reference API: oracle/ref_driver.c) */
     int nx = p->nx, ny = p->ny, rb = p->row_begin, re = p->row_end;
     if (rb == 0 && re == 0) re = ny;
     double rmin = (p->r_emit_min > 0.0) ? p->r_emit_min : orc_r_ms(p->bh_spin);

@@ -7,16 +7,18 @@ import ctypes as C
 import math
 
 # modes
-MODE_EQPLANE, MODE_POLARIZED, MODE_STEPWISE, MODE_HISTOGRAM, MODE_SPECTRUM = 0, 1, 2, 3, 4
+MODE_EQPLANE, MODE_POLARIZED, MODE_STEPWISE, MODE_HISTOGRAM, MODE_SPECTRUM, MODE_SURFACE = 0, 1, 2, 3, 4, 5
 # outputs
 OUT_R, OUT_PHI, OUT_G, OUT_FLUX = 0x001, 0x002, 0x004, 0x008
 OUT_CHI, OUT_DELTA, OUT_MUE = 0x010, 0x020, 0x040
 OUT_INTENSITY, OUT_TAU, OUT_STEPS, OUT_STATUS, OUT_QERR = 0x080, 0x100, 0x200, 0x400, 0x800
+OUT_HEIGHT, OUT_DELAY = 0x1000, 0x2000
 # flags
 FLAG_DEVICE_PTRS, FLAG_NO_REFILL, FLAG_ASYNC, FLAG_SINGLE_PASS, FLAG_NO_OVERLAP, FLAG_EXACT_AZIMUTH, FLAG_FULL_INDEX = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
 # status classes
 ST_HIT0, ST_HIT1, ST_MISS, ST_NOCROSS0, ST_NOCROSS1, ST_HIT2, ST_NOCROSS2 = 0, 1, 2, 3, 4, 5, 6
 ST_HORIZON, ST_ESCAPE, ST_ERRBREAK, ST_MAXSTEPS, ST_NOSTART = 8, 9, 10, 11, 12
+ST_SURF_UNDER, ST_SURF_EQPLANE, ST_SURF_BELOW, ST_SURF_LOST = 7, 13, 14, 15
 ST_INITERR = 16
 GT_NONE, GT_RR, GT_RC, GT_CC, GT_RR_DBL, GT_RR_BH = 0, 1, 2, 3, 4, 5
 
@@ -28,6 +30,7 @@ PLANES = (  # (field, output bit, ctype)
     ("flux", OUT_FLUX, C.c_double), ("chi", OUT_CHI, C.c_double), ("delta", OUT_DELTA, C.c_double),
     ("mue", OUT_MUE, C.c_double), ("intensity", OUT_INTENSITY, C.c_double), ("tau", OUT_TAU, C.c_double),
     ("qerr", OUT_QERR, C.c_double), ("steps", OUT_STEPS, C.c_int32), ("status", OUT_STATUS, C.c_uint8),
+    ("height", OUT_HEIGHT, C.c_double), ("delay", OUT_DELAY, C.c_double),
 )
 
 
@@ -49,6 +52,7 @@ class ImageParams(C.Structure):
         ("split_count", C.c_int32), ("split_index", C.c_int32), ("split_rows", C.c_int32), ("reserved2", C.c_int32),
         ("n_energy", C.c_int32), ("spec_limb", C.c_int32),
         ("e_min_kev", C.c_double), ("e_max_kev", C.c_double), ("spec_hardf", C.c_double),
+        ("surf_hr", C.c_double), ("surf_rin", C.c_double), ("delay_r_ref", C.c_double),
     ]
 
 
@@ -57,7 +61,7 @@ class ImageOut(C.Structure):
         ("r", C.c_void_p), ("phi", C.c_void_p), ("g", C.c_void_p), ("flux", C.c_void_p),
         ("chi", C.c_void_p), ("delta", C.c_void_p), ("mue", C.c_void_p), ("intensity", C.c_void_p),
         ("tau", C.c_void_p), ("qerr", C.c_void_p), ("steps", C.c_void_p), ("status", C.c_void_p),
-        ("hist", C.c_void_p), ("spectrum", C.c_void_p),
+        ("hist", C.c_void_p), ("spectrum", C.c_void_p), ("height", C.c_void_p), ("delay", C.c_void_p),
     ]
 
 
@@ -96,7 +100,7 @@ def spectrum_energies(p):
 
 
 def default_params(cfg, nx=None, ny=None):
-    """BASELINE.json configs 1..5 with the open parameters fixed as in SURVEY.md 8(d); 6 = the SPECTRUM preset."""
+    """BASELINE.json configs 1..5 with the open parameters fixed as in SURVEY.md 8(d); 6 = the SPECTRUM preset, 7 = the SURFACE preset."""
     p = ImageParams()
     p.struct_size = C.sizeof(ImageParams)
     p.max_order = 1
@@ -108,6 +112,7 @@ def default_params(cfg, nx=None, ny=None):
     p.spin_max, p.incl_min_deg, p.incl_max_deg = 0.998, 5.0, 85.0
     p.g_min, p.g_max, p.rmax_offset = 0.0, 2.0, 20.0
     p.n_energy, p.spec_limb, p.e_min_kev, p.e_max_kev, p.spec_hardf = 128, 1, 0.05, 50.0, 1.7
+    p.surf_hr, p.surf_rin, p.delay_r_ref = 0.2, 0.0, 1000.0
     if cfg == 1:
         p.mode, p.nx, p.ny = MODE_EQPLANE, 512, 512
         p.bh_spin, p.incl = 0.9, deg2rad(70.0)
@@ -138,8 +143,13 @@ def default_params(cfg, nx=None, ny=None):
         p.bh_spin, p.incl = 0.998, deg2rad(75.0)
         p.rmax = r_ms(p.bh_spin) + 20.0
         p.outputs = 0
+    elif cfg == 7:
+        p.mode, p.nx, p.ny = MODE_SURFACE, 1024, 1024
+        p.bh_spin, p.incl = 0.9, deg2rad(60.0)
+        p.rmax = 30.0
+        p.outputs = OUT_R | OUT_HEIGHT | OUT_G | OUT_MUE | OUT_FLUX | OUT_STEPS | OUT_STATUS
     else:
-        raise ValueError("cfg must be 1..6")
+        raise ValueError("cfg must be 1..7")
     p.torus_ell = ell_kepler(p.torus_rc, p.bh_spin)
     if nx is not None:
         p.nx = nx

@@ -63,7 +63,7 @@ struct Context {
     unsigned long long* d_counter = nullptr;
     DevStats* d_stats = nullptr;
     DevStats* h_stats = nullptr;          /* pinned */
-    Plane planes[12];
+    Plane planes[SIM5_NPLANES];
     Plane hist;
     Plane azq_redo;
     Plane azq_f, azq_key;                 /* azimuth work-item queue (phase A -> phase B) */
@@ -170,9 +170,10 @@ int persistent_grid(K kernel, int threads)
     return g_ctx.sm_count * per_sm;
 }
 
-const struct { unsigned bit; size_t elem; } kPlaneInfo[12] = {
+const struct { unsigned bit; size_t elem; } kPlaneInfo[SIM5_NPLANES] = {
     {SIM5_OUT_R, 8}, {SIM5_OUT_PHI, 8}, {SIM5_OUT_G, 8}, {SIM5_OUT_FLUX, 8}, {SIM5_OUT_CHI, 8}, {SIM5_OUT_DELTA, 8},
     {SIM5_OUT_MUE, 8}, {SIM5_OUT_INTENSITY, 8}, {SIM5_OUT_TAU, 8}, {SIM5_OUT_QERR, 8}, {SIM5_OUT_STEPS, 4}, {SIM5_OUT_STATUS, 1},
+    {SIM5_OUT_HEIGHT, 8}, {SIM5_OUT_DELAY, 8},
 };
 void* host_plane(const sim5_image_out* o, int i)
 {
@@ -180,6 +181,7 @@ void* host_plane(const sim5_image_out* o, int i)
         case 0: return o->r; case 1: return o->phi; case 2: return o->g; case 3: return o->flux;
         case 4: return o->chi; case 5: return o->delta; case 6: return o->mue; case 7: return o->intensity;
         case 8: return o->tau; case 9: return o->qerr; case 10: return o->steps; case 11: return o->status;
+        case 12: return o->height; case 13: return o->delay;
     }
     return nullptr;
 }
@@ -190,6 +192,7 @@ void set_dev_plane(DevOut* d, int i, void* p)
         case 3: d->flux = (double*)p; break; case 4: d->chi = (double*)p; break; case 5: d->delta = (double*)p; break;
         case 6: d->mue = (double*)p; break; case 7: d->intensity = (double*)p; break; case 8: d->tau = (double*)p; break;
         case 9: d->qerr = (double*)p; break; case 10: d->steps = (int*)p; break; case 11: d->status = (unsigned char*)p; break;
+        case 12: d->height = (double*)p; break; case 13: d->delay = (double*)p; break;
     }
 }
 
@@ -428,7 +431,7 @@ extern "C" int sim5_device_to_host(void* dst, const void* src, size_t bytes)
 /* the open parameters of the five BASELINE configs */
 extern "C" int sim5_default_params(int cfg, sim5_image_params* p)
 {
-    if (!p || cfg < 1 || cfg > 6) return SIM5_ERR_BAD_PARAM;
+    if (!p || cfg < 1 || cfg > 7) return SIM5_ERR_BAD_PARAM;
     memset(p, 0, sizeof(*p));
     p->struct_size = (int32_t)sizeof(*p);
     p->max_order = 1;
@@ -439,6 +442,7 @@ extern "C" int sim5_default_params(int cfg, sim5_image_params* p)
     p->spin_max = 0.998; p->incl_min_deg = 5.0; p->incl_max_deg = 85.0;
     p->g_min = 0.0; p->g_max = 2.0; p->rmax_offset = 20.0;
     p->n_energy = 128; p->spec_limb = 1; p->e_min_kev = 0.05; p->e_max_kev = 50.0; p->spec_hardf = 1.7;
+    p->surf_hr = 0.2; p->surf_rin = 0.0; p->delay_r_ref = 1000.0;
     switch (cfg) {
         case 1: p->mode = SIM5_MODE_EQPLANE; p->nx = p->ny = 512; p->bh_spin = 0.9; p->incl = 70.0 / 180.0 * M_PI;
                 p->rmax = s5_host_r_ms(p->bh_spin) + 8.0; p->outputs = SIM5_OUT_R | SIM5_OUT_G | SIM5_OUT_FLUX | SIM5_OUT_STATUS; break;
@@ -453,6 +457,8 @@ extern "C" int sim5_default_params(int cfg, sim5_image_params* p)
                 p->rmax = 0.0; p->outputs = 0; break;
         case 6: p->mode = SIM5_MODE_SPECTRUM; p->nx = p->ny = 2048; p->bh_spin = 0.998; p->incl = 75.0 / 180.0 * M_PI;
                 p->rmax = s5_host_r_ms(p->bh_spin) + 20.0; p->outputs = 0; break;
+        case 7: p->mode = SIM5_MODE_SURFACE; p->nx = p->ny = 1024; p->bh_spin = 0.9; p->incl = 60.0 / 180.0 * M_PI;
+                p->rmax = 30.0; p->outputs = SIM5_OUT_R | SIM5_OUT_HEIGHT | SIM5_OUT_G | SIM5_OUT_MUE | SIM5_OUT_FLUX | SIM5_OUT_STEPS | SIM5_OUT_STATUS; break;
     }
     {   /* ellK(torus_rc, a), sim5kerr.c:1050-1071 */
         double r = p->torus_rc, a = p->bh_spin;
@@ -469,7 +475,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     if (!p || !out) { set_error("null params/out"); return SIM5_ERR_BAD_PARAM; }
     if (p->struct_size != (int32_t)sizeof(sim5_image_params)) { set_error("sim5_image_params.struct_size mismatch"); return SIM5_ERR_BAD_PARAM; }
     if (p->nx <= 0 || p->ny <= 0) { set_error("empty image"); return SIM5_ERR_BAD_PARAM; }
-    if (p->mode < SIM5_MODE_EQPLANE || p->mode > SIM5_MODE_SPECTRUM) { set_error("unknown mode"); return SIM5_ERR_BAD_PARAM; }
+    if (p->mode < SIM5_MODE_EQPLANE || p->mode > SIM5_MODE_SURFACE) { set_error("unknown mode"); return SIM5_ERR_BAD_PARAM; }
     std::lock_guard<std::mutex> lk(g_ctx.mu);
     int rc = ensure_init(p->device);
     if (rc) return rc;
@@ -482,7 +488,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     if (rb < 0 || re > p->ny || rb > re) { set_error("bad row range"); return SIM5_ERR_BAD_PARAM; }
     if (p->max_order < 0 || p->max_order > 2) { set_error("max_order must be 0..2"); return SIM5_ERR_BAD_PARAM; }
     if (p->mode == SIM5_MODE_STEPWISE && (p->max_steps < 1 || !(p->precision_factor > 0))) { set_error("bad stepper parameters"); return SIM5_ERR_BAD_PARAM; }
-    for (int i = 0; i < 12; i++)
+    for (int i = 0; i < SIM5_NPLANES; i++)
         if ((p->outputs & kPlaneInfo[i].bit) && !host_plane(out, i)) { set_error("selected output plane is NULL"); return SIM5_ERR_NO_OUTPUT; }
 
     int split = p->split_count > 1 ? p->split_count : 1;
@@ -498,7 +504,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     DevOut d;
     memset(&d, 0, sizeof d);
     d.compact = (!devptr || (split > 1 && !(p->flags & SIM5_FLAG_FULL_INDEX))) ? 1 : 0;
-    for (int i = 0; i < 12; i++) {
+    for (int i = 0; i < SIM5_NPLANES; i++) {
         if (!(p->outputs & kPlaneInfo[i].bit)) continue;
         if (devptr) { set_dev_plane(&d, i, host_plane(out, i)); continue; }
         rc = reserve(c.planes[i], (npix ? npix : 1) * kPlaneInfo[i].elem);
@@ -509,7 +515,8 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     S5ImageConsts consts;                  /* travels by value as a kernel parameter: no H2D copy, async-safe */
     s5_fill_image_consts(p, &consts);
     /* two-phase azimuth: phase A queues the disk hits, phase B integrates phi per geodesic type */
-    bool two_phase = (p->mode != SIM5_MODE_STEPWISE) && (p->outputs & SIM5_OUT_PHI) && !(p->flags & SIM5_FLAG_SINGLE_PASS) && npix > 0;
+    bool lanes = (p->mode == SIM5_MODE_STEPWISE || p->mode == SIM5_MODE_SURFACE);
+    bool two_phase = !lanes && (p->outputs & SIM5_OUT_PHI) && !(p->flags & SIM5_FLAG_SINGLE_PASS) && npix > 0;
 
     /* Host planes: the rows are traced in CHUNKS so the device->host copy of chunk k (copy stream, copy engine) runs
      * under the kernels of chunk k+1; only the last chunk's copy is exposed.  Device planes: one chunk. */
@@ -548,15 +555,18 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
             cc.row_begin = consts.row_begin + (lr0 / srows) * split * srows;
             cc.nrows_local = lrows;
             cc.row_end = cc.row_begin + lrows * split;
-            for (int i = 0; i < 12; i++) {
+            for (int i = 0; i < SIM5_NPLANES; i++) {
                 if (!(p->outputs & kPlaneInfo[i].bit)) continue;
                 set_dev_plane(&dd, i, (char*)c.planes[i].p + pix0 * kPlaneInfo[i].elem);
             }
         }
         CK(cudaMemsetAsync(c.d_counter, 0, 8 * sizeof(unsigned long long), c.stream));
         if (p->mode == SIM5_MODE_STEPWISE) {
-            grid = persistent_grid(s5::k_trace_stepwise, S5_CTA_THREADS);
-            s5::k_trace_stepwise<<<grid, S5_CTA_THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
+            grid = persistent_grid(s5::k_trace_lanes<s5::StepwiseProg>, S5_CTA_THREADS);
+            s5::k_trace_lanes<s5::StepwiseProg><<<grid, S5_CTA_THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
+        } else if (p->mode == SIM5_MODE_SURFACE) {
+            grid = persistent_grid(s5::k_trace_lanes<s5::SurfaceProg>, S5_CTA_THREADS);
+            s5::k_trace_lanes<s5::SurfaceProg><<<grid, S5_CTA_THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
         } else if (two_phase) {
             grid = persistent_grid(s5::k_trace_eqplane<true>, S5_EQ_THREADS);
             s5::k_trace_eqplane<true><<<grid, S5_EQ_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
@@ -612,7 +622,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         } else {
             CK(cudaEventRecord(c.ev2, c.stream));
         }
-        for (int i = 0; i < 12; i++) {
+        for (int i = 0; i < SIM5_NPLANES; i++) {
             if (!(p->outputs & kPlaneInfo[i].bit)) continue;
             size_t es = kPlaneInfo[i].elem;
             const char* src = (const char*)c.planes[i].p + pix0 * es;

@@ -46,6 +46,12 @@ struct S5ImageConsts {
     double bb1;          /* 2 h / c^2 / hardf^4 * kev2freq^4 */
     double bb2;          /* h kev2freq / (k_B hardf)  -- BB2 of blackbody() is bb2 / T */
     int n_energy, spec_limb;
+    /* surface finder (harness surface of sim5_b200.h; python/sim5diskraytrace.py:259-275) */
+    double surf_hr, surf_rin;
+    double surf_cos_it;  /* cos(incl + atan(H(1e6)/1e6)), host libm */
+    int surf_flat, pad2; /* H(1e5) == 0 */
+    /* SIM5_OUT_DELAY */
+    double delay_r_ref;
     /* Chandrasekhar table (harness, sim5_b200.h) */
     double chandra[SIM5_CHANDRA_N];
 };
@@ -147,6 +153,15 @@ static inline void s5_fill_image_consts(const sim5_image_params* p, S5ImageConst
         c->bb2 = (planck_h * kev2freq) / (boltzmann_k * hf);
         c->n_energy = p->n_energy;
         c->spec_limb = p->spec_limb;
+    }
+    {
+        c->surf_hr = p->surf_hr;
+        c->surf_rin = (p->surf_rin > 0.0) ? p->surf_rin : s5_host_r_ms(p->bh_spin);
+        double h6 = (1e6 > c->surf_rin) ? c->surf_hr * ((1e6 - c->surf_rin) * (1e6 - c->surf_rin)) / 1e6 : 0.0;
+        double h5 = (1e5 > c->surf_rin) ? c->surf_hr * ((1e5 - c->surf_rin) * (1e5 - c->surf_rin)) / 1e5 : 0.0;
+        c->surf_cos_it = cos(p->incl + atan(h6 / 1e6));
+        c->surf_flat = (h5 == 0.0) ? 1 : 0;
+        c->delay_r_ref = p->delay_r_ref;
     }
     for (int i = 0; i < SIM5_CHANDRA_N; i++) c->chandra[i] = SIM5_CHANDRA_DELTA[i];
 }

@@ -22,7 +22,7 @@
 namespace s5 {
 
 struct DevOut {
-    double *r, *phi, *g, *flux, *chi, *delta, *mue, *intensity, *tau, *qerr;
+    double *r, *phi, *g, *flux, *chi, *delta, *mue, *intensity, *tau, *qerr, *height, *delay;
     int* steps;
     unsigned char* status;
     int compact;                  /* 1: plane index = local_row*nx + ix ; 0: full-image index iy*nx + ix */
@@ -80,6 +80,8 @@ __device__ __forceinline__ void store_pixel(const DevOut& out, unsigned outputs,
     if (outputs & SIM5_OUT_INTENSITY) out.intensity[i] = o.intensity;
     if (outputs & SIM5_OUT_TAU)       out.tau[i] = o.tau;
     if (outputs & SIM5_OUT_QERR)      out.qerr[i] = o.qerr;
+    if (outputs & SIM5_OUT_HEIGHT)    out.height[i] = o.height;
+    if (outputs & SIM5_OUT_DELAY)     out.delay[i] = o.delay;
     if (outputs & SIM5_OUT_STEPS)     out.steps[i] = o.steps;
     if (outputs & SIM5_OUT_STATUS)    out.status[i] = (unsigned char)o.status;
 }
@@ -273,13 +275,15 @@ k_azimuth_fast(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double*
 }
 
 /* ------------------------------------------------------------------ */
-/* mode STEPWISE : raytrace() stepping with warp-level lane refill     */
+/* modes STEPWISE and SURFACE : one live ray per lane, warp-level refill */
 /* ------------------------------------------------------------------ */
+/* PROG = StepwiseProg (a raytrace() call + the torus per step) or SurfaceProg (one pass of geodesic_follow's loop per step) */
 #define S5_STEPS_PER_ROUND 16
 #define S5_REFILL_MIN 4
 
+template <class PROG>
 __global__ void __launch_bounds__(S5_CTA_THREADS, S5_MIN_CTAS_STEP)
-k_trace_stepwise(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigned long long* __restrict__ ray_counter, DevStats* __restrict__ gstats)
+k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigned long long* __restrict__ ray_counter, DevStats* __restrict__ gstats)
 {
     __shared__ S5ImageConsts c;
     __shared__ unsigned int s_cnt[40];
@@ -293,7 +297,7 @@ k_trace_stepwise(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsi
     const long long npix = (long long)c.nrows_local * nx;
     const bool refill = !(c.flags & SIM5_FLAG_NO_REFILL);
 
-    StepRay s;
+    typename PROG::State s;
     long long mypix = -1;
     bool live = false;
     bool drained = false;          /* queue exhausted (warp-uniform) */
@@ -319,7 +323,7 @@ k_trace_stepwise(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsi
                     int iy = s5_local_to_image_row(&c, lr);
                     PixelOut o;
                     mypix = p;
-                    if (stepwise_start(c, ix, iy, &s, &o)) {
+                    if (PROG::start(c, ix, iy, &s, &o)) {
                         live = true;
                     } else {
                         size_t i = out.compact ? (size_t)p : (size_t)iy * (size_t)nx + (size_t)ix;
@@ -335,11 +339,10 @@ k_trace_stepwise(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsi
         #pragma unroll 1
         for (int it = 0; it < S5_STEPS_PER_ROUND; it++) {
             if (live) {
-                int cls = stepwise_step(c, &s);
+                int cls = PROG::step(c, &s);
                 if (cls) {
                     PixelOut o;
-                    o.r = o.phi = o.g = o.flux = o.chi = o.delta = o.mue = 0.0;
-                    stepwise_finish(c, &s, cls, &o);
+                    PROG::finish(c, &s, cls, &o);
                     int lr = (int)(mypix / nx);
                     int ix = (int)(mypix - (long long)lr * nx);
                     int iy = s5_local_to_image_row(&c, lr);

@@ -254,6 +254,8 @@ S5_HD S5_INL void on2bl(const double Vin[4], double Vout[4], const Tetrad* t)
 S5_HD S5_INL double r_bh(double a) { return 1. + sqrt(1. - sq(a)); }
 /* sim5kerr.c:1036-1046 */
 S5_HD S5_INL double OmegaK(double r, double a) { return 1. / (a + crm::cr_pow_1p5(r)); }
+/* Keplerian specific angular momentum (Komissarov 2008 form).  sim5kerr.c:1050-1071 */
+S5_HD S5_INL double ellK(double r, double a) { return (sq(r) - 2. * a * sqrt(r) + sq(a)) / (sqrt(r) * r - 2. * sqrt(r) + a); }
 /* sim5kerr.c:1101-1111 */
 S5_HD S5_INL double Omega_from_ell(double ell, const Metric* g) { return -(g->g03 + ell * g->g00) / (g->g33 + ell * g->g03); }
 /* sim5kerr.c:1114-1124 */

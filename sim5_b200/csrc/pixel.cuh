@@ -22,7 +22,7 @@
 namespace s5 {
 
 struct PixelOut {
-    double r, phi, g, flux, chi, delta, mue, intensity, tau, qerr;
+    double r, phi, g, flux, chi, delta, mue, intensity, tau, qerr, height, delay;
     int steps;
     unsigned status;
 };
@@ -624,7 +624,7 @@ S5_HD S5_INL bool trace_eqplane_pixel_t(const S5ImageConsts& c, int ix, int iy, 
     double alpha, beta;
     pixel_impact(c, ix, iy, &alpha, &beta);
     o->r = o->phi = o->g = o->flux = o->chi = o->delta = o->mue = 0.0;
-    o->intensity = o->tau = o->qerr = 0.0; o->steps = 0;
+    o->intensity = o->tau = o->qerr = o->height = o->delay = 0.0; o->steps = 0;
 
     Geodesic gd;
     int error = 0;
@@ -700,7 +700,10 @@ S5_HD S5_INL bool spectrum_pixel(const S5ImageConsts& c, int ix, int iy, SpecHit
 S5_HD S5_INL double spectrum_term(const SpecHit& h, double Ek)
 {
     double E = Ek * h.ginv;
-    return h.amp3 * (E * E * E) * ff::rcp_ap(expm1(h.xs * E));
+    double x = h.xs * E;
+    /* far Wien tail: expm1(x) == e^x to every bit and overflows at x > 709, where the approximate reciprocal has no inf -> 0 path */
+    double w = (x < 600.0) ? ff::rcp_ap(expm1(x)) : exp(-x);
+    return h.amp3 * (E * E * E) * w;
 }
 
 /* mode STEPWISE: raytrace() through the harness torus (SURVEY.md 8d cfg 4; oracle/ref_driver.c pixel_stepwise) */
@@ -717,7 +720,7 @@ S5_HD S5_INL bool stepwise_start(const S5ImageConsts& c, int ix, int iy, StepRay
     double alpha, beta;
     pixel_impact(c, ix, iy, &alpha, &beta);
     o->r = o->phi = o->g = o->flux = o->chi = o->delta = o->mue = 0.0;
-    o->intensity = o->tau = o->qerr = 0.0; o->steps = 0;
+    o->intensity = o->tau = o->qerr = o->height = o->delay = 0.0; o->steps = 0;
     Geodesic gd;
     int error = 0;
     gd.type = -1;
@@ -777,12 +780,186 @@ S5_HD S5_INL int stepwise_step(const S5ImageConsts& c, StepRay* s)
 S5_HD S5_INL void stepwise_finish(const S5ImageConsts& c, StepRay* s, int cls, PixelOut* o)
 {
     (void)c;
+    o->r = o->phi = o->g = o->flux = o->chi = o->delta = o->mue = o->height = o->delay = 0.0;
     o->intensity = s->I;
     o->tau = s->tau;
     o->steps = s->steps;
     o->qerr = raytrace_error(s->x, s->k, &s->rtd);
     o->status = (unsigned)cls | s->gt;
 }
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * mode SURFACE: the thick-disk surface finder of the reference's Python layer (DiskRaytrace.geodesic / __find_surface /
+ * image, python/sim5diskraytrace.py:214-336, 163-205, 340-391; reference-side spelling: oracle/ref_driver.c pixel_surface)
+ * as a per-lane state machine.  The unit of work is ONE pass of geodesic_follow's do-while body (sim5kerr-geod.c:907-921:
+ * a bounded advance of P, then r(P) and cos theta(P), two Jacobi sn/cn/dn evaluations), so the lanes of a warp stay
+ * together although every ray takes a different number of follow calls and of sub-steps inside each call
+ * (~400 sub-steps per ray from r0 >= 200 down to the disk); finished lanes are refilled by the persistent kernel.
+ * ------------------------------------------------------------------------------------------------------------------ */
+struct SurfRay {
+    Geodesic gd;
+    double P, r, m;             /* current position on the geodesic */
+    double H1, Hd;              /* height of the ray and of the surface at the last completed forward follow */
+    double r0, step_factor;
+    double step, rem;           /* argument of the running geodesic_follow call, and what is left of it */
+    int phase;                  /* running call: 0 forward probe, 1 step back by -step, 2 final step back by -step/2 */
+    int iteration, nfollow;
+    unsigned gt;
+};
+S5_HD S5_INL double surf_h(const S5ImageConsts& c, double R) { return (R > c.surf_rin) ? c.surf_hr * sq(R - c.surf_rin) / R : 0.0; }
+S5_HD S5_INL double surf_dhdr(const S5ImageConsts& c, double R) { return (R > c.surf_rin) ? c.surf_hr * (1.0 - sq(c.surf_rin) / sq(R)) : 0.0; }
+S5_HD S5_INL void surface_follow(SurfRay* s, double step, int phase) { s->step = (phase == 0) ? step : s->step; s->rem = step; s->phase = phase; s->nfollow++; }
+S5_HD S5_INL double surface_next_step(const SurfRay* s) { return fmax(1e-2 / 2., fmin((s->H1 - s->Hd) / 2., 0.5 * (sqrt(s->r) - 0.99) * s->step_factor)); }
+
+/* start (or restart with a larger r0) the search: python/sim5diskraytrace.py:259-289.  -1 = live, else the termination class (SIM5_ST_HIT0 is 0) */
+S5_HD S5_MID int surface_begin(const S5ImageConsts& c, SurfRay* s)
+{
+    if (s->iteration > 3) return SIM5_ST_ESCAPE;
+    const Geodesic* gd = &s->gd;
+    double r0 = fmax(fmax(200.0, 1.1 * gd->rp), (0.5 + (double)s->iteration) * sqrt(sq(gd->alpha) + sq(gd->beta)) / c.surf_cos_it);
+    double P1, r1, m1, H1, Hd;
+    for (;;) {
+        P1 = geodesic_P_int(gd, r0, 0);
+        r1 = geodesic_position_rad(gd, P1);
+        m1 = geodesic_position_pol(gd, P1);
+        double R1 = r1 * sqrt(1. - m1 * m1);
+        H1 = r1 * m1;
+        Hd = surf_h(c, R1);
+        if ((Hd < H1) || (r0 > 5e6)) break;
+        r0 = 2.0 * r0;
+    }
+    if (!(Hd < H1)) return SIM5_ST_SURF_BELOW;
+    s->r0 = r0; s->P = P1; s->r = r1; s->m = m1; s->H1 = H1; s->Hd = Hd;
+    s->step_factor = 1.0;
+    surface_follow(s, surface_next_step(s), 0);
+    return -1;
+}
+S5_HD S5_INL void surface_fail(PixelOut* o, unsigned status, int nfollow)
+{
+    o->r = o->phi = o->g = o->flux = o->chi = o->delta = o->mue = o->intensity = o->tau = o->qerr = o->height = o->delay = 0.0;
+    o->steps = nfollow;
+    o->status = status;
+}
+/* emission-side quantities at the surface point (P, r, m): DiskRaytrace.image + __tetrad/__gfactor/__emission_angle */
+S5_HD S5_MID void surface_finish(const S5ImageConsts& c, SurfRay* s, int cls, PixelOut* o)
+{
+    surface_fail(o, (unsigned)cls | s->gt, s->nfollow);
+    if (cls != SIM5_ST_HIT0 && cls != SIM5_ST_SURF_EQPLANE) return;
+    double r = s->r, m = s->m, a = c.a;
+    if (isnan(r)) { o->status = SIM5_ST_MISS | s->gt; return; }
+    double k[4];
+    photon_momentum(a, r, m, s->gd.l, s->gd.q, s->gd.Rpc - s->P, 1.0, k);
+    double R = r * sqrt(1. - m * m);
+    o->r = r;
+    o->height = r * m;
+    double F = disk_nt_flux(c, R);
+    if (F == 0.0) return;
+    Metric M;
+    Tetrad t;
+    double U[4], N[4];
+    const double e0[4] = {1.0, 0.0, 0.0, 0.0};
+    const double e2[4] = {0.0, 0.0, 1.0, 0.0};
+    kerr_metric(a, r, m, &M);
+    tetrad_surface(&M, Omega_from_ell(ellK(R, a), &M), 0.0, (m > 0.0) ? surf_dhdr(c, R) : 0.0, &t);
+    on2bl(e0, U, &t);
+    on2bl(e2, N, &t);
+    double g = (k[0] * M.g00 + k[3] * M.g03) / dotprod(k, U, &M);
+    if (!(g > 0.0)) g = 0.0;
+    double mue = dotprod(k, N, &M) / dotprod(k, U, &M);
+    if (mue < 0.0 && mue > -1e-2) mue = 1e-3;
+    double limb = 0.5 + 0.75 * mue;
+    if (!(g > 0.0)) return;
+    o->g = g;
+    o->mue = mue;
+    o->flux = F * crm::cr_pow_4(g) * limb;
+}
+/* returns true if the ray is live; otherwise *o is final */
+S5_HD S5_INL bool surface_start(const S5ImageConsts& c, int ix, int iy, SurfRay* s, PixelOut* o)
+{
+    double alpha, beta;
+    pixel_impact(c, ix, iy, &alpha, &beta);
+    int error = 0;
+    s->gd.type = -1;
+    s->nfollow = 0;
+    if (!geodesic_init_inf_sc(c.incl, c.sin_i, c.cos_i, c.a, alpha, beta, &s->gd, &error)) {
+        int gt = (error == GD_ERROR_TYPE_RR_DOUBLE) ? gtype_code(s->gd.type) : SIM5_GT_NONE;
+        surface_fail(o, (unsigned)((SIM5_ST_INITERR + error) | (gt << 5)), 0);
+        return false;
+    }
+    s->gt = (unsigned)gtype_code(s->gd.type) << 5;
+    if (c.surf_flat) {                                   /* flat disk: the order-0 equatorial crossing, nothing to follow */
+        s->P = geodesic_find_midplane_crossing(&s->gd, 0);
+        s->r = geodesic_position_rad(&s->gd, s->P);
+        s->m = 0.0;
+        surface_finish(c, s, SIM5_ST_SURF_EQPLANE, o);
+        return false;
+    }
+    s->iteration = 0;
+    int cls = surface_begin(c, s);
+    if (cls >= 0) { surface_finish(c, s, cls, o); return false; }
+    return true;
+}
+/* one pass of geodesic_follow's loop body; when that completes a follow call, the decision of __find_surface that follows
+ * it (python/sim5diskraytrace.py:296-331).  -1 while the ray is live, else the termination class */
+S5_HD S5_MID int surface_step(const S5ImageConsts& c, SurfRay* s)
+{
+    const Geodesic* gd = &s->gd;
+    bool ok = true, done = false;
+    {
+        const double MAXSTEP_FACTOR = 5e-2;
+        double truestep = s->rem / fabs(s->rem) * fmin(fabs(s->rem), MAXSTEP_FACTOR * sqrt(s->r));
+        s->P = s->P + truestep / (sq(s->r) + sq(gd->a * s->m));
+        s->r = geodesic_position_rad(gd, s->P);
+        s->m = geodesic_position_pol(gd, s->P);
+        if (s->r < 1.01 * r_bh(gd->a)) { ok = false; done = true; }
+        else if ((s->P < 0.0) || (s->P > 2. * gd->Rpc)) { ok = false; done = true; }
+        else { s->rem -= truestep; done = !(fabs(s->rem) > 1e-5); }
+    }
+    if (!done) return -1;
+    if (s->phase == 2) return SIM5_ST_HIT0;              /* the caller does not look at the status of the step back */
+    if (s->phase == 1) {
+        s->step_factor = s->step_factor / 5.;
+    } else {
+        const double accuracy = 1e-2;
+        if (!ok) return SIM5_ST_SURF_LOST;
+        double R1 = s->r * sqrt(1. - s->m * s->m);
+        s->H1 = s->r * s->m;
+        s->Hd = surf_h(c, R1);
+        if (s->H1 <= s->Hd) {
+            if (s->step < accuracy) surface_follow(s, -s->step / 2., 2);
+            else                    surface_follow(s, -s->step, 1);
+            return -1;
+        }
+        if (s->H1 < 1e-4) {
+            s->P = geodesic_find_midplane_crossing(gd, 0);
+            s->r = geodesic_position_rad(gd, s->P);
+            s->m = geodesic_position_pol(gd, s->P);
+            return SIM5_ST_SURF_EQPLANE;
+        }
+        if (s->r < 1.05 * c.r_bh) return SIM5_ST_HORIZON;
+        if (s->r > 1.1 * s->r0) { s->iteration++; return surface_begin(c, s); }
+        if (s->m < 0.0) return SIM5_ST_SURF_UNDER;
+        if (s->step < accuracy / 2.) return SIM5_ST_MAXSTEPS;
+    }
+    surface_follow(s, surface_next_step(s), 0);
+    return -1;
+}
+
+/* the two ray programs of the lane-refill kernel (kernels.cuh:k_trace_lanes) */
+struct StepwiseProg {
+    typedef StepRay State;
+    static S5_HD S5_INL bool start(const S5ImageConsts& c, int ix, int iy, State* s, PixelOut* o) { return stepwise_start(c, ix, iy, s, o); }
+    static S5_HD S5_INL int step(const S5ImageConsts& c, State* s) { return stepwise_step(c, s); }
+    static S5_HD S5_INL void finish(const S5ImageConsts& c, State* s, int cls, PixelOut* o) { stepwise_finish(c, s, cls, o); }
+};
+struct SurfaceProg {
+    typedef SurfRay State;
+    static S5_HD S5_INL bool start(const S5ImageConsts& c, int ix, int iy, State* s, PixelOut* o) { return surface_start(c, ix, iy, s, o); }
+    /* the kernel's protocol is "0 while live"; SIM5_ST_HIT0 is 0, so the class travels with bit 8 set */
+    static S5_HD S5_INL int step(const S5ImageConsts& c, State* s) { int r = surface_step(c, s); return r < 0 ? 0 : (r | 0x100); }
+    static S5_HD S5_INL void finish(const S5ImageConsts& c, State* s, int cls, PixelOut* o) { surface_finish(c, s, cls & 0xff, o); }
+};
 
 } /* namespace s5 */
 #endif

@@ -146,7 +146,7 @@ def err_summary(x, ref, floor=0.0):
 # tolerances of BASELINE.json's north_star: bit-exact classification / termination flags;
 # relative error <= 1e-9 on r, phi, g and <= 1e-7 on the polarization angle and flux.
 TOL = {"r": 1e-9, "phi": 1e-9, "g": 1e-9, "flux": 1e-7, "chi": 1e-7, "delta": 1e-7, "mue": 1e-9,
-       "intensity": 1e-7, "tau": 1e-7, "qerr": None}
+       "intensity": 1e-7, "tau": 1e-7, "qerr": None, "height": 1e-9, "delay": 1e-9}
 FLOOR = {"phi": 1.0, "chi": 1.0}          # |dphi| / max(|phi|, 1): phi ~ 1e-5 on the alpha ~ 0 column
 
 
@@ -209,6 +209,7 @@ def golden(name):
 GOLDEN_IMAGES = (  # (file, cfg, nx, ny, extra output bits)
     ("image_cfg1_64.npz", 1, 64, 64, 0), ("image_cfg2_64.npz", 2, 64, 64, 0), ("image_cfg2_50x37.npz", 2, 50, 37, 0),
     ("image_cfg3_64.npz", 3, 64, 64, abi.OUT_MUE), ("image_cfg4_16.npz", 4, 16, 16, abi.OUT_QERR),
+    ("image_cfg7_48.npz", 7, 48, 48, 0),
 )
 
 

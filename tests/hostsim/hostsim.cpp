@@ -159,6 +159,13 @@ double hs_trace_image(const sim5_image_params* p, const sim5_image_out* out, int
                     while ((cls = stepwise_step(c, &s)) == 0) {}
                     stepwise_finish(c, &s, cls, &o);
                 }
+            } else if (c.mode == SIM5_MODE_SURFACE) {
+                SurfRay s;
+                if (SurfaceProg::start(c, ix, iy, &s, &o)) {
+                    int cls;
+                    while ((cls = SurfaceProg::step(c, &s)) == 0) {}
+                    SurfaceProg::finish(c, &s, cls, &o);
+                }
             } else {
                 trace_eqplane_pixel(c, ix, iy, &o);
             }
@@ -173,6 +180,8 @@ double hs_trace_image(const sim5_image_params* p, const sim5_image_out* out, int
             if ((c.outputs & SIM5_OUT_INTENSITY) && out->intensity) out->intensity[i] = o.intensity;
             if ((c.outputs & SIM5_OUT_TAU) && out->tau) out->tau[i] = o.tau;
             if ((c.outputs & SIM5_OUT_QERR) && out->qerr) out->qerr[i] = o.qerr;
+            if ((c.outputs & SIM5_OUT_HEIGHT) && out->height) out->height[i] = o.height;
+            if ((c.outputs & SIM5_OUT_DELAY) && out->delay) out->delay[i] = o.delay;
             if ((c.outputs & SIM5_OUT_STEPS) && out->steps) out->steps[i] = o.steps;
             if ((c.outputs & SIM5_OUT_STATUS) && out->status) out->status[i] = (uint8_t)o.status;
         }

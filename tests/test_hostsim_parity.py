@@ -24,7 +24,7 @@ def test_images_against_golden(fname, cfg, nx, ny, extra):
 
 
 @pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("cfg,n", [(1, 160), (2, 160), (3, 128), (4, 24)])
+@pytest.mark.parametrize("cfg,n", [(1, 160), (2, 160), (3, 128), (4, 24), (7, 72)])
 def test_images_against_reference(cfg, n):
     p = abi.default_params(cfg, n)
     got, _, _ = H.run_hostsim(p)
@@ -34,8 +34,10 @@ def test_images_against_reference(cfg, n):
     if cfg in (1, 2, 3):
         assert st.class_count[abi.ST_HIT0] > 0 and st.class_count[abi.ST_MISS] > 0 and st.class_count[abi.ST_NOCROSS0] > 0
         assert st.gtype_count[abi.GT_RR] > 0 and st.gtype_count[abi.GT_RC] > 0
-    else:
+    elif cfg == 4:
         assert st.class_count[abi.ST_HORIZON] > 0 and st.class_count[abi.ST_ESCAPE] > 0
+    else:
+        assert st.class_count[abi.ST_HIT0] > 0 and st.class_count[abi.ST_HORIZON] > 0 and st.class_count[abi.ST_SURF_LOST] > 0
 
 
 @pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built")

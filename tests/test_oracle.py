@@ -17,7 +17,7 @@ pytestmark = pytest.mark.skipif(not H.have_oracle(), reason="oracle/libsim5oracl
 TIGHT = {k: 0.0 for k in ("r", "phi", "g", "flux", "chi", "delta", "mue")}      # max relative error allowed: none
 
 
-@pytest.mark.parametrize("fname,cfg,nx,ny,extra", [g for g in H.GOLDEN_IMAGES if g[1] != 4])
+@pytest.mark.parametrize("fname,cfg,nx,ny,extra", [g for g in H.GOLDEN_IMAGES if g[1] not in (4, 7)])
 def test_oracle_images_against_golden(fname, cfg, nx, ny, extra):
     p = H.golden_params(cfg, nx, ny, extra)
     got, st, _ = H.run_oracle(p)

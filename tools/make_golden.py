@@ -36,7 +36,7 @@ def main():
     rng = np.random.default_rng(20261017)
 
     # ---- images of the BASELINE configs at fixture size
-    for cfg, n in ((1, 64), (2, 64), (3, 64), (4, 16)):
+    for cfg, n in ((1, 64), (2, 64), (3, 64), (4, 16), (7, 48)):
         p = abi.default_params(cfg, n)
         if cfg == 4:
             p.outputs |= abi.OUT_QERR
@@ -50,6 +50,12 @@ def main():
     p = abi.default_params(2, 50, 37)
     pl, st, _ = H.run_ref(p)
     np.savez_compressed(os.path.join(OUT, "image_cfg2_50x37.npz"), **pl.arrays)
+
+    # the surface finder on a second disk: truncated at R = 8 (rays through the hole reach the equatorial plane), a = 0.5, i = 30 deg
+    p = abi.default_params(7, 40, 28)
+    p.bh_spin, p.incl, p.surf_rin, p.surf_hr, p.rmax = 0.5, abi.deg2rad(30.0), 8.0, 0.2, 12.0
+    pl, st, _ = H.run_ref(p)
+    np.savez_compressed(os.path.join(OUT, "image_surface_rin8_40x28.npz"), class_count=np.array(list(st.class_count)), **pl.arrays)
 
     # ---- thermal spectrum (SPECTRUM preset shrunk), incl. a partial spectrum of an interleaved split
     p = abi.default_params(6, 96)
