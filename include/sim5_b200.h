@@ -279,6 +279,15 @@ int sim5_batch_sncndn(int64_t n, const double* u, const double* m, double* sn, d
 /* unary/binary libm-compatible device functions (correctly-rounded double-double implementations):
  * op: 0 sin, 1 cos, 2 log, 3 atan2(y=a,x=b), 4 acos, 5 asin, 6 atan, 7 pow(a,1./3.), 8 pow(a,1.5), 9 pow(a,4.), 10 exp */
 int sim5_batch_libm(int op, int64_t n, const double* a, const double* b, double* out);
+/* the Byrd & Friedman integrals behind geodesic_timedelay (sim5elliptic.c:645-1139), n elements each; v[0..6] are the argument arrays
+ * (NULL = zeros).  op: 0 integral_C1(u,m)  1 C2(u,m)  2 C2_cos(cn,m)  3 Z2(a,b,u,m)  4 Rm1(a,u,m)  5 Rm2(a,u,m)  6 R2(a,u,m)
+ * 7 R_r0_re(a,b,c,d,X)  8 R_r0_re_inf(a,b,c,d)  9 R_r1_re(a,b,c,d,X)  10 R_r2_re(a,b,c,d,X)  11 T_m0(a2,b2,X)  12 T_m2(a2,b2,X)
+ * and with the complex pair c = v[2] + i v[3]:  13 R_r0_cc(a,b,c,X=v[4])  14 R_r0_cc_inf(a,b,c)  15 R_r1_cc(a,b,c,X1=v[4],X2=v[5])
+ * 16 R_r2_cc(a,b,c,X1,X2)  17 R_rp_cc2(a,b,c,p=v[6],X1,X2) */
+int sim5_batch_integral(int op, int64_t n, const double* const* v, double* out);
+/* geodesic_timedelay (sim5kerr-geod.c:559-731) between the radii ra[i] and rb[i] on the incoming branch of the geodesic with
+ * impact parameters (alpha[i], beta[i]) of an observer at inclination incl [rad] around a hole of spin a */
+int sim5_batch_timedelay(int64_t n, double incl, double a, const double* alpha, const double* beta, const double* ra, const double* rb, double* out);
 
 #ifdef __cplusplus
 }

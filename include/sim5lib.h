@@ -82,6 +82,7 @@ void on2bl(double Vin[4], double Vout[4], sim5tetrad* t);
 double r_bh(double a);
 double r_ms(double a);
 double OmegaK(double r, double a);
+double ellK(double r, double a);                                                  /* sim5kerr.c:1050 */
 double Omega_from_ell(double ell, sim5metric *m);
 double ell_from_Omega(double Omega, sim5metric *m);
 double gfactorK(double r, double a, double l);
@@ -117,6 +118,18 @@ double integral_R_rp_re(double a, double b, double c, double d, double p, double
 double integral_R_rp_re_inf(double a, double b, double c, double d, double p);
 double integral_R_rp_cc2_inf(double a, double b, sim5complex c, double p, double X1);
 double integral_T_mp(double a2, double b2, double p, double X);
+/* the integrals behind geodesic_timedelay that the reference exports (sim5elliptic.h:41-55; sim5elliptic.c:825-1139) */
+double integral_R_r0_re(double a, double b, double c, double d, double X);
+double integral_R_r0_re_inf(double a, double b, double c, double d);
+double integral_R_r0_cc(double a, double b, sim5complex c, double X);
+double integral_R_r0_cc_inf(double a, double b, sim5complex c);
+double integral_R_r1_re(double a, double b, double c, double d, double X);
+double integral_R_r1_cc(double a, double b, sim5complex c, double X1, double X2);
+double integral_R_r2_re(double a, double b, double c, double d, double X);
+double integral_R_r2_cc(double a, double b, sim5complex c, double X1, double X2);
+double integral_R_rp_cc2(double a, double b, sim5complex c, double p, double X1, double X2);
+double integral_T_m0(double a2, double b2, double X);
+double integral_T_m2(double a2, double b2, double X);
 
 /* ---- sim5kerr-geod.h:19-84 -------------------------------------------------------------------- */
 #define GEOD_TYPE_RR               40
@@ -171,6 +184,7 @@ double geodesic_dm_sign(geodesic *g, double P);
 void geodesic_momentum(geodesic *g, double P, double r, double m, double k[]);
 double geodesic_find_midplane_crossing(geodesic *g, int order);
 void geodesic_follow(geodesic *g, double step, double *P, double *r, double *m, int *status);
+double geodesic_timedelay(geodesic *g, double P1, double r1, double m1, double P2, double r2, double m2);   /* sim5kerr-geod.c:559 */
 
 /* ---- sim5raytrace.h:21-53 --------------------------------------------------------------------- */
 #define RTOPT_NONE              0

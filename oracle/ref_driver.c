@@ -84,6 +84,10 @@ static void pixel_eqplane(const sim5_image_params* p, double rmin, double alpha,
             o->status = (unsigned char)((order == 0 ? SIM5_ST_HIT0 : order == 1 ? SIM5_ST_HIT1 : SIM5_ST_HIT2) | gt);
             o->r = r;
             if (p->outputs & SIM5_OUT_PHI) o->phi = geodesic_position_azm(&gd, r, 0.0, P);
+            if (p->outputs & SIM5_OUT_DELAY) {       /* travel time between the sphere r = delay_r_ref and the disk hit */
+                double Pref = geodesic_P_int(&gd, p->delay_r_ref, 0);
+                o->delay = geodesic_timedelay(&gd, Pref, p->delay_r_ref, 0.0, P, r, 0.0);
+            }
             if (p->mode == SIM5_MODE_POLARIZED) {
                 double a = p->bh_spin;
                 double k[4], U[4], N[4], kl[4], fl[4], f[4];
@@ -597,3 +601,58 @@ void ref_batch_libm(int op, long n, const double* a, const double* b, double* o)
 }
 double ref_r_ms(double a) { return r_ms(a); }
 double ref_r_bh(double a) { return r_bh(a); }
+
+/* the integrals behind geodesic_timedelay, element-wise (op codes shared with sim5_batch_integral of the product):
+ * 0 C1(u,m) 1 C2(u,m) 2 C2_cos(c,m) 3 Z2(a,b,u,m) 4 Rm1(a,u,m) 5 Rm2(a,u,m) 6 R2(a,u,m) 7 R_r0_re(a,b,c,d,X) 8 R_r0_re_inf(a,b,c,d)
+ * 9 R_r1_re(a,b,c,d,X) 10 R_r2_re(a,b,c,d,X) 11 T_m0(a2,b2,X) 12 T_m2(a2,b2,X) 13 R_r0_cc(a,b,(c,d),X) 14 R_r0_cc_inf(a,b,(c,d))
+ * 15 R_r1_cc(a,b,(c,d),X1,X2) 16 R_r2_cc(..) 17 R_rp_cc2(a,b,(c,d),p,X1,X2) with X1 = v[4], X2 = v[5], p = v[6] */
+/* internal to sim5elliptic.c (no prototype in sim5elliptic.h); the unity build emits them as external symbols */
+double integral_C1(double u, double m);
+double integral_C2(double u, double m);
+double integral_C2_cos(double cn_u, double m);
+double integral_Z2(double a, double b, double u, double m);
+double integral_Rm1(double a, double u, double m);
+double integral_Rm2(double a, double u, double m);
+double integral_R2(double a, double u, double m);
+void ref_batch_integral(int op, long n, const double* v0, const double* v1, const double* v2, const double* v3, const double* v4,
+                        const double* v5, const double* v6, double* o)
+{
+    for (long i = 0; i < n; i++) {
+        sim5complex c = makeComplex(v2[i], v3[i]);
+        switch (op) {
+            case 0: o[i] = integral_C1(v0[i], v1[i]); break;
+            case 1: o[i] = integral_C2(v0[i], v1[i]); break;
+            case 2: o[i] = integral_C2_cos(v0[i], v1[i]); break;
+            case 3: o[i] = integral_Z2(v0[i], v1[i], v2[i], v3[i]); break;
+            case 4: o[i] = integral_Rm1(v0[i], v1[i], v2[i]); break;
+            case 5: o[i] = integral_Rm2(v0[i], v1[i], v2[i]); break;
+            case 6: o[i] = integral_R2(v0[i], v1[i], v2[i]); break;
+            case 7: o[i] = integral_R_r0_re(v0[i], v1[i], v2[i], v3[i], v4[i]); break;
+            case 8: o[i] = integral_R_r0_re_inf(v0[i], v1[i], v2[i], v3[i]); break;
+            case 9: o[i] = integral_R_r1_re(v0[i], v1[i], v2[i], v3[i], v4[i]); break;
+            case 10: o[i] = integral_R_r2_re(v0[i], v1[i], v2[i], v3[i], v4[i]); break;
+            case 11: o[i] = integral_T_m0(v0[i], v1[i], v2[i]); break;
+            case 12: o[i] = integral_T_m2(v0[i], v1[i], v2[i]); break;
+            case 13: o[i] = integral_R_r0_cc(v0[i], v1[i], c, v4[i]); break;
+            case 14: o[i] = integral_R_r0_cc_inf(v0[i], v1[i], c); break;
+            case 15: o[i] = integral_R_r1_cc(v0[i], v1[i], c, v4[i], v5[i]); break;
+            case 16: o[i] = integral_R_r2_cc(v0[i], v1[i], c, v4[i], v5[i]); break;
+            case 17: o[i] = integral_R_rp_cc2(v0[i], v1[i], c, v6[i], v4[i], v5[i]); break;
+            default: o[i] = NAN;
+        }
+    }
+}
+/* geodesic_timedelay between two radii on the way in (P = geodesic_P_int(r, 0)) of n geodesics from infinity */
+void ref_batch_timedelay(long n, double incl, double a, const double* alpha, const double* beta, const double* ra, const double* rb, double* o)
+{
+    int saved = silence_stderr();
+    for (long i = 0; i < n; i++) {
+        geodesic gd; int error = 0;
+        o[i] = NAN;
+        geodesic_init_inf(incl, a, alpha[i], beta[i], &gd, &error);
+        if (error) continue;
+        double Pa = geodesic_P_int(&gd, ra[i], 0), Pb = geodesic_P_int(&gd, rb[i], 0);
+        o[i] = geodesic_timedelay(&gd, Pa, 0.0, 0.0, Pb, 0.0, 0.0);     /* r = 0: radii and latitudes recomputed from P */
+    }
+    restore_stderr(saved);
+}

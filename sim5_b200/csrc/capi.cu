@@ -568,8 +568,13 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
             grid = persistent_grid(s5::k_trace_lanes<s5::SurfaceProg>, S5_CTA_THREADS);
             s5::k_trace_lanes<s5::SurfaceProg><<<grid, S5_CTA_THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
         } else if (two_phase) {
-            grid = persistent_grid(s5::k_trace_eqplane<true>, S5_EQ_THREADS);
-            s5::k_trace_eqplane<true><<<grid, S5_EQ_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+            if (p->outputs & SIM5_OUT_DELAY) {
+                grid = persistent_grid(s5::k_trace_eqplane<true, true>, S5_EQ_THREADS);
+                s5::k_trace_eqplane<true, true><<<grid, S5_EQ_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+            } else {
+                grid = persistent_grid(s5::k_trace_eqplane<true>, S5_EQ_THREADS);
+                s5::k_trace_eqplane<true><<<grid, S5_EQ_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+            }
             if (ch == 0) CK(cudaEventRecord(c.evp[0], c.stream));
             int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_AZ_THREADS);
             int g_rc = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RC>, S5_AZ_THREADS);
@@ -607,8 +612,13 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
             if (ch == 0) CK(cudaEventRecord(c.evp[2], c.stream));
             launches += 2;
         } else {
-            grid = persistent_grid(s5::k_trace_eqplane<false>, S5_EQ_THREADS);
-            s5::k_trace_eqplane<false><<<grid, S5_EQ_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+            if (p->outputs & SIM5_OUT_DELAY) {
+                grid = persistent_grid(s5::k_trace_eqplane<false, true>, S5_EQ_THREADS);
+                s5::k_trace_eqplane<false, true><<<grid, S5_EQ_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+            } else {
+                grid = persistent_grid(s5::k_trace_eqplane<false>, S5_EQ_THREADS);
+                s5::k_trace_eqplane<false><<<grid, S5_EQ_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+            }
         }
         launches += 1;
         CK(cudaGetLastError());
@@ -824,6 +834,31 @@ extern "C" int sim5_batch_libm(int op, int64_t n, const double* a, const double*
     BATCH_END();
 }
 
+extern "C" int sim5_batch_integral(int op, int64_t n, const double* const* v, double* out)
+{
+    BATCH_BEGIN();
+    if (!v) { set_error("null argument table"); return SIM5_ERR_BAD_PARAM; }
+    int rc;
+    for (int k = 0; k < 7; k++) {
+        if ((rc = stage_in(k, v[k], v[k] ? n : 0)) || (rc = stage_in(k, nullptr, n))) return rc;
+        if (!v[k]) CK(cudaMemsetAsync(g_ctx.batch[k], 0, (n ? n : 1) * sizeof(double), g_ctx.stream));
+    }
+    if ((rc = stage_in(7, nullptr, n))) return rc;
+    s5::k_batch_integral<<<batch_grid(n), 128, 0, g_ctx.stream>>>(op, n, B(0), B(1), B(2), B(3), B(4), B(5), B(6), B(7));
+    if ((rc = stage_out(7, out, n))) return rc;
+    BATCH_END();
+}
+extern "C" int sim5_batch_timedelay(int64_t n, double incl, double a, const double* alpha, const double* beta, const double* ra, const double* rb, double* out)
+{
+    BATCH_BEGIN();
+    int rc; if ((rc = stage_in(0, alpha, n)) || (rc = stage_in(1, beta, n)) || (rc = stage_in(2, ra, n)) || (rc = stage_in(4, rb, n)) || (rc = stage_in(3, nullptr, n))) return rc;
+    double si, ci;
+    sincos(incl, &si, &ci);
+    s5::k_batch_timedelay<<<batch_grid(n), 128, 0, g_ctx.stream>>>(n, incl, si, ci, a, B(0), B(1), B(2), B(4), B(3));
+    if ((rc = stage_out(3, out, n))) return rc;
+    BATCH_END();
+}
+
 /* ------------------------------------------------------------------ */
 /* scalar sim5lib.h API: one-thread device launches                    */
 /* ------------------------------------------------------------------ */
@@ -879,6 +914,22 @@ double call_d1(int op, double a0, double a1, double a2, double a3, double a4, do
             case 24: r = s5::r_bh(a0); break;
             case 25: r = s5::OmegaK(a0, a1); break;
             case 26: r = s5::gfactorK(a0, a1, a2); break;
+            case 27: r = s5::ellK(a0, a1); break;
+            case 28: r = s5::integral_C1(a0, a1); break;
+            case 29: r = s5::integral_C2(a0, a1); break;
+            case 30: r = s5::integral_C2_cos(a0, a1); break;
+            case 31: r = s5::integral_Z2(a0, a1, a2, a3); break;
+            case 32: r = s5::integral_Rm1(a0, a1, a2); break;
+            case 33: r = s5::integral_Rm2(a0, a1, a2); break;
+            case 34: r = s5::integral_R2(a0, a1, a2); break;
+            case 35: r = s5::integral_R_r0_re(a0, a1, a2, a3, a4); break;
+            case 36: r = s5::integral_R_r0_re_inf(a0, a1, a2, a3); break;
+            case 37: r = s5::integral_R_r1_re(a0, a1, a2, a3, a4); break;
+            case 38: r = s5::integral_R_r2_re(a0, a1, a2, a3, a4); break;
+            case 39: r = s5::integral_T_m0(a0, a1, a2); break;
+            case 40: r = s5::integral_T_m2(a0, a1, a2); break;
+            case 41: r = s5::integral_R0(a0, a1); break;
+            case 42: r = a0; break;                                      /* integral_C0, sim5elliptic.c:636-642 */
         }
         d->v[0] = r;
     });
@@ -901,12 +952,25 @@ DFUN4(integral_Z1, 19) DFUN3(integral_R1, 20)
 extern "C" double integral_R_rp_re(double a, double b, double c, double d, double p, double X) { return call_d1(21, a, b, c, d, p, X); }
 extern "C" double integral_R_rp_re_inf(double a, double b, double c, double d, double p) { return call_d1(22, a, b, c, d, p, 0); }
 DFUN4(integral_T_mp, 23)
-DFUN1(r_bh, 24) DFUN2(OmegaK, 25) DFUN3(gfactorK, 26)
+DFUN1(r_bh, 24) DFUN2(OmegaK, 25) DFUN3(gfactorK, 26) DFUN2(ellK, 27)
+extern "C" double integral_R_r0_re(double a, double b, double c, double d, double X) { return call_d1(35, a, b, c, d, X, 0); }
+DFUN4(integral_R_r0_re_inf, 36)
+extern "C" double integral_R_r1_re(double a, double b, double c, double d, double X) { return call_d1(37, a, b, c, d, X, 0); }
+extern "C" double integral_R_r2_re(double a, double b, double c, double d, double X) { return call_d1(38, a, b, c, d, X, 0); }
+DFUN3(integral_T_m0, 39) DFUN3(integral_T_m2, 40)
 
 /* r_ms is a per-image constant in every caller; it needs cbrt of the host libm to match the reference bit for bit */
 extern "C" double r_ms(double a) { return s5_host_r_ms(a); }
 
 struct c_complex { double re, im; };
+
+#define CCFUN(name, call, ...) extern "C" double name(__VA_ARGS__) \
+{ LOCK; if (!scalar_ready()) return kNaN; Scratch* d = D; bool ok = dev_call([=] __device__ () { d->v[0] = call; }); return ok ? H->v[0] : kNaN; }
+CCFUN(integral_R_r0_cc, s5::integral_R_r0_cc(a, b, c.re, c.im, X), double a, double b, c_complex c, double X)
+CCFUN(integral_R_r0_cc_inf, s5::integral_R_r0_cc_inf(a, b, c.re, c.im), double a, double b, c_complex c)
+CCFUN(integral_R_r1_cc, s5::integral_R_r1_cc(a, b, c.re, c.im, X1, X2), double a, double b, c_complex c, double X1, double X2)
+CCFUN(integral_R_r2_cc, s5::integral_R_r2_cc(a, b, c.re, c.im, X1, X2), double a, double b, c_complex c, double X1, double X2)
+CCFUN(integral_R_rp_cc2, s5::integral_R_rp_cc2(a, b, c.re, c.im, p, X1, X2), double a, double b, c_complex c, double p, double X1, double X2)
 
 extern "C" double integral_R_rp_cc2_inf(double a, double b, c_complex c, double p, double X1)
 {
@@ -1105,6 +1169,7 @@ extern "C" int geodesic_init_src(double a, double r, double m, double k[4], int 
     dev_call([=] __device__ () { d->v[0] = expr; }); return H->v[0]; }
 GEO_D(geodesic_P_int, s5::geodesic_P_int(&d->g, r, ppc), double r, int ppc)
 GEO_D(geodesic_position_rad, s5::geodesic_position_rad(&d->g, P), double P)
+GEO_D(geodesic_timedelay, s5::geodesic_timedelay(&d->g, P1, r1, m1, P2, r2, m2), double P1, double r1, double m1, double P2, double r2, double m2)
 GEO_D(geodesic_position_pol, s5::geodesic_position_pol(&d->g, P), double P)
 GEO_D(geodesic_position_pol_sign_k_theta, s5::geodesic_position_pol_sign_k_theta(&d->g, P), double P)
 GEO_D(geodesic_position_azm, s5::geodesic_position_azm(&d->g, r, m, P), double r, double m, double P)

@@ -815,5 +815,188 @@ S5_HD S5_MID double integral_T_mp(double a2, double b2, double p, double X)
         return 1. / sqrt(a2 + b2) / (p - b2) * (2. * elliptic_pi_complete(n, m) - elliptic_pi_cos(-X / sqrt(b2), n, m));
 }
 
+/* ---- the integrals behind geodesic_timedelay ------------------------------------------------------ */
+/* int cn u du = acos(dn)/sqrt(m), B&F 312.01.  sim5elliptic.c:645-653 */
+S5_HD S5_INL double integral_C1(double u, double m)
+{
+    double sn, cn, dn;
+    jacobi_sncndn(u, m, &sn, &cn, &dn);
+    return crm::cr_acos(dn) / sqrt(m);
+}
+/* int cn^2 u du, B&F 312.02.  sim5elliptic.c:656-673 */
+S5_HD S5_INL double integral_C2(double u, double m)
+{
+    double sn, cn, dn;
+    jacobi_sncndn(u, m, &sn, &cn, &dn);
+    return 1. / m * (elliptic_e_cos(cn, m) - (1. - m) * u);
+}
+S5_HD S5_INL double integral_C2_cos(double cn_u, double m)
+{
+    return 1. / m * (elliptic_e_cos(cn_u, m) - (1. - m) * elliptic_f_cos(cn_u, m));
+}
+/* int (1-b sn^2)^2/(1-a sn^2)^2 du, B&F 340.02.  sim5elliptic.c:693-715 */
+S5_HD S5_MID double integral_Z2(double a, double b, double u, double m)
+{
+    double sn, cn, dn;
+    jacobi_sncndn(u, m, &sn, &cn, &dn);
+    double V1 = elliptic_pi_cos(cn, a, m);
+    double V2 = 0.5 / ((a - 1.) * (m - a)) * (
+                    a * elliptic_e_cos(cn, m) + (m - a) * u +
+                    (2. * a * m + 2. * a - a * a - 3. * m) * V1 -
+                    (a * a * sn * cn * dn) / (1. - a * sn * sn)
+                );
+    double ab = a - b;
+    return 1. / sq(a) * (sq(b) * u + 2. * b * ab * V1 + ab * ab * V2);
+}
+/* int (1 + a cn u) du, B&F 341.00.  sim5elliptic.c:718-729 */
+S5_HD S5_INL double integral_Rm1(double a, double u, double m)
+{
+    return u + a / sqrt(m) * crm::cr_acos(jacobi_dn(u, m));
+}
+/* int (1 + a cn u)^2 du, B&F 341.01.  sim5elliptic.c:732-745 */
+S5_HD S5_MID double integral_Rm2(double a, double u, double m)
+{
+    double a2 = sq(a);
+    double sn, cn, dn;
+    jacobi_sncndn(u, m, &sn, &cn, &dn);
+    return 1 / m * ((m - a2 * (1. - m)) * u + a2 * elliptic_e_cos(cn, m) + 2 * a * sqrt(m) * crm::cr_acos(dn));
+}
+S5_HD S5_INL double integral_R0(double u, double m) { (void)m; return u; }
+/* int du/(1 + a cn u)^2, B&F 341.04.  sim5elliptic.c:795-815 */
+S5_HD S5_MID double integral_R2(double a, double u, double m)
+{
+    double a2 = sq(a);
+    double mma = (m + (1. - m) * a2);
+    double sn, cn, dn;
+    jacobi_sncndn(u, m, &sn, &cn, &dn);
+    return 1 / (a2 - 1.) / mma * (
+               (a2 * (2. * m - 1.) - 2. * m) * integral_R1(a, u, m) +
+               2. * m * integral_Rm1(a, u, m) -
+               m * integral_Rm2(a, u, m) +
+               a * a2 * sn * dn / (1. + a * cn)
+           );
+}
+/* int_a^X dx/sqrt((x-a)(x-b)(x-c)(x-d)), B&F 258.00.  sim5elliptic.c:825-838, 841-854 */
+S5_HD S5_INL double integral_R_r0_re(double a, double b, double c, double d, double X)
+{
+    double m4 = ((b - c) * (a - d)) / ((a - c) * (b - d));
+    double sn = sqrt(((b - d) * (X - a)) / ((a - d) * (X - b)));
+    return 2.0 / sqrt((a - c) * (b - d)) * jacobi_isn(sn, m4);
+}
+S5_HD S5_INL double integral_R_r0_re_inf(double a, double b, double c, double d)
+{
+    double m4 = ((b - c) * (a - d)) / ((a - c) * (b - d));
+    double sn = sqrt((b - d) / (a - d));
+    return 2.0 / sqrt((a - c) * (b - d)) * jacobi_isn(sn, m4);
+}
+/* the same with a complex pair c = u + iv, d = c*: B&F 260.00.  sim5elliptic.c:857-872, 875-889 */
+S5_HD S5_INL double integral_R_r0_cc(double a, double b, double cre, double cim, double X)
+{
+    double u = cre;
+    double v2 = sq(cim);
+    double A = sqrt(sq(a - u) + v2);
+    double B = sqrt(sq(b - u) + v2);
+    double m2 = (sq(A + B) - sq(a - b)) / (4. * A * B);
+    double cn = (X * (A - B) + a * B - b * A) / (X * (A + B) - a * B - b * A);
+    return 1. / sqrt(A * B) * jacobi_icn(cn, m2);
+}
+S5_HD S5_INL double integral_R_r0_cc_inf(double a, double b, double cre, double cim)
+{
+    double u = cre;
+    double v2 = sq(cim);
+    double A = sqrt(sq(a - u) + v2);
+    double B = sqrt(sq(b - u) + v2);
+    double m2 = (sq(A + B) - sq(a - b)) / (4. * A * B);
+    double cn = (A - B) / (A + B);
+    return 1. / sqrt(A * B) * jacobi_icn(cn, m2);
+}
+/* int_a^X x dx/sqrt(...), B&F 258.11.  sim5elliptic.c:892-905 */
+S5_HD S5_MID double integral_R_r1_re(double a, double b, double c, double d, double X)
+{
+    double m2 = ((b - c) * (a - d)) / ((a - c) * (b - d));
+    double sn = sqrt(((b - d) * (X - a)) / ((a - d) * (X - b)));
+    double u = jacobi_isn(sn, m2);
+    double a2 = (a - d) / (b - d);
+    double b2 = ((a - d) * b) / (a * (b - d));
+    double Z = integral_Z1(a2, b2, u, m2) - integral_Z1(a2, b2, 0, m2);
+    return a * 2.0 / sqrt((a - c) * (b - d)) * Z;
+}
+/* int_X1^X2 x dx/sqrt((x-a)(x-b)(x-c)(x-c*)), B&F 260.03.  sim5elliptic.c:908-931 */
+S5_HD S5_MID double integral_R_r1_cc(double a, double b, double cre, double cim, double X1, double X2)
+{
+    double u = cre;
+    double v2 = sq(cim);
+    double A = sqrt(sq(a - u) + v2);
+    double B = sqrt(sq(b - u) + v2);
+    double m = (sq(A + B) - sq(a - b)) / (4. * A * B);
+    double g = 1. / sqrt(A * B);
+    double alpha1 = (B * a + b * A) / (B * a - b * A);
+    double alpha2 = (B + A) / (B - A);
+    double u1 = elliptic_f_cos((X1 * (A - B) + a * B - b * A) / (X1 * (A + B) - a * B - b * A), m);
+    double u2 = elliptic_f_cos((X2 * (A - B) + a * B - b * A) / (X2 * (A + B) - a * B - b * A), m);
+    double t0 = alpha1 * (integral_R0(u2, m) - integral_R0(u1, m));
+    double t1 = (alpha2 - alpha1) * (integral_R1(alpha2, u2, m) - integral_R1(alpha2, u1, m));
+    return (B * a - b * A) / (B + A) * g * (t0 + t1);
+}
+/* int_a^X x^2 dx/sqrt(...), B&F 258.11.  sim5elliptic.c:954-967 */
+S5_HD S5_MID double integral_R_r2_re(double a, double b, double c, double d, double X)
+{
+    double m2 = ((b - c) * (a - d)) / ((a - c) * (b - d));
+    double sn = sqrt(((b - d) * (X - a)) / ((a - d) * (X - b)));
+    double u = jacobi_isn(sn, m2);
+    double a2 = (a - d) / (b - d);
+    double b2 = ((a - d) * b) / (a * (b - d));
+    double Z = integral_Z2(a2, b2, u, m2) - integral_Z2(a2, b2, 0, m2);
+    return sq(a) * 2.0 / sqrt((a - c) * (b - d)) * Z;
+}
+/* int_X1^X2 x^2 dx/sqrt((x-a)(x-b)(x-c)(x-c*)), B&F 260.03.  sim5elliptic.c:970-995; pow(., 2.) is an exact square in glibc's
+ * pow to the last bit of a correctly rounded product */
+S5_HD S5_MID double integral_R_r2_cc(double a, double b, double cre, double cim, double X1, double X2)
+{
+    double u = cre;
+    double v2 = sq(cim);
+    double A = sqrt(sq(a - u) + v2);
+    double B = sqrt(sq(b - u) + v2);
+    double m = (sq(A + B) - sq(a - b)) / (4. * A * B);
+    double g = 1. / sqrt(A * B);
+    double alpha1 = (B * a + b * A) / (B * a - b * A);
+    double alpha2 = (B + A) / (B - A);
+    double u1 = elliptic_f_cos((X1 * (A - B) + a * B - b * A) / (X1 * (A + B) - a * B - b * A), m);
+    double u2 = elliptic_f_cos((X2 * (A - B) + a * B - b * A) / (X2 * (A + B) - a * B - b * A), m);
+    double t0 = sq(alpha1) * (integral_R0(u2, m) - integral_R0(u1, m));
+    double t1 = 2. * alpha1 * (alpha2 - alpha1) * (integral_R1(alpha2, u2, m) - integral_R1(alpha2, u1, m));
+    double t2 = sq(alpha2 - alpha1) * (integral_R2(alpha2, u2, m) - integral_R2(alpha2, u1, m));
+    return sq((B * a - b * A) / (B + A)) * g * (t0 + t1 + t2);
+}
+/* int_X1^X2 dx/((x-p) sqrt((x-a)(x-b)(x-c)(x-c*))), B&F 260.04.  sim5elliptic.c:1047-1078 */
+S5_HD S5_MID double integral_R_rp_cc2(double a, double b, double cre, double cim, double p, double X1, double X2)
+{
+    double u = cre;
+    double v2 = sq(cim);
+    double A = sqrt(sq(a - u) + v2);
+    double B = sqrt(sq(b - u) + v2);
+    double m = (sq(A + B) - sq(a - b)) / (4. * A * B);
+    double g = 1. / sqrt(A * B);
+    double alpha1 = (B * a + b * A - p * A - p * B) / (B * a - b * A + p * A - p * B);
+    double alpha2 = (B + A) / (B - A);
+    double u1 = elliptic_f_cos((X1 * (A - B) + a * B - b * A) / (X1 * (A + B) - a * B - b * A), m);
+    double u2 = elliptic_f_cos((X2 * (A - B) + a * B - b * A) / (X2 * (A + B) - a * B - b * A), m);
+    double t0 = alpha2 * (integral_R0(u2, m) - integral_R0(u1, m));
+    double t1 = (alpha1 - alpha2) * (integral_R1(alpha1, u2, m) - integral_R1(alpha1, u1, m));
+    return (B - A) * g / (B * a + b * A - p * A - p * B) * (t0 + t1);
+}
+/* int_X^b dx/sqrt((a^2+x^2)(b^2-x^2)) and with x^2 in the numerator, B&F 213.00 / 213.06.  sim5elliptic.c:1119-1139 */
+S5_HD S5_INL double integral_T_m0(double a2, double b2, double X)
+{
+    double m = b2 / (a2 + b2);
+    return 1. / sqrt(a2 + b2) * jacobi_icn(X / sqrt(b2), m);
+}
+S5_HD S5_INL double integral_T_m2(double a2, double b2, double X)
+{
+    double m = b2 / (a2 + b2);
+    double cn = X / sqrt(b2);
+    return b2 / sqrt(a2 + b2) * (integral_C2_cos(cn, m) - integral_C2(0, m));
+}
+
 } /* namespace s5 */
 #endif

@@ -466,5 +466,54 @@ S5_HD S5_INL int geodesic_init_src(double a, double r, double m, const double k[
     return 1;
 }
 
+/* travel time between two positions on the geodesic (the radial integrals only: the reference's polar part is commented
+ * out).  sim5kerr-geod.c:559-731 */
+S5_HD S5_MID double geodesic_timedelay(const Geodesic* g, double P1, double r1, double m1, double P2, double r2, double m2)
+{
+    double time = 0.0;
+    if (P1 > P2) {
+        double tmp;
+        tmp = P2; P2 = P1; P1 = tmp;
+        tmp = r2; r2 = r1; r1 = tmp;
+        tmp = m2; m2 = m1; m1 = tmp;
+    }
+    if (r1 == 0) { r1 = geodesic_position_rad(g, P1); m1 = geodesic_position_pol(g, P1); }
+    if (r2 == 0) { r2 = geodesic_position_rad(g, P2); m2 = geodesic_position_pol(g, P2); }
+    (void)m1; (void)m2;
+    double a2 = sq(g->a);
+    double rp = 1. + sqrt(1. - a2);
+    double rm = 1. - sqrt(1. - a2);
+    double ra = g->r1.re, rb = g->r2.re, rc = g->r3.re, rd = g->r4.re;
+    double R0, R1, R2, RA, RB, A, B, s;
+    switch (g->type) {
+        case GEOD_TYPE_RR:
+            s = (((P1 > g->Rpc) && (P2 < g->Rpc)) || ((P1 < g->Rpc) && (P2 > g->Rpc))) ? +1 : -1;
+            R0 = integral_R_r0_re(ra, rb, rc, rd, r1) + s * integral_R_r0_re(ra, rb, rc, rd, r2);
+            R1 = integral_R_r1_re(ra, rb, rc, rd, r1) + s * integral_R_r1_re(ra, rb, rc, rd, r2);
+            R2 = integral_R_r2_re(ra, rb, rc, rd, r1) + s * integral_R_r2_re(ra, rb, rc, rd, r2);
+            RA = integral_R_rp_re(ra, rb, rc, rd, rp, r1) + s * integral_R_rp_re(ra, rb, rc, rd, rp, r2);
+            RB = integral_R_rp_re(ra, rb, rc, rd, rm, r1) + s * integral_R_rp_re(ra, rb, rc, rd, rm, r2);
+            A = (-g->a * g->l + 4.) * rp - 2. * a2;
+            B = (+g->a * g->l - 4.) * rm + 2. * a2;
+            time += 4. * fabs(R0) + 2. * fabs(R1) + fabs(R2) + (A * fabs(RA) + B * fabs(RB)) / sqrt(1. - a2);
+            break;
+        case GEOD_TYPE_RC: {
+            double cre = g->r3.re, cim = g->r3.im;
+            R0 = integral_R_r0_cc(ra, rb, cre, cim, r1) - integral_R_r0_cc(ra, rb, cre, cim, r2);
+            R1 = (r1 < r2) ? integral_R_r1_cc(ra, rb, cre, cim, r1, r2) : integral_R_r1_cc(ra, rb, cre, cim, r2, r1);
+            R2 = (r1 < r2) ? integral_R_r2_cc(ra, rb, cre, cim, r1, r2) : integral_R_r2_cc(ra, rb, cre, cim, r2, r1);
+            RA = (r1 < r2) ? integral_R_rp_cc2(ra, rb, cre, cim, rp, r1, r2) : integral_R_rp_cc2(ra, rb, cre, cim, rp, r2, r1);
+            RB = (r1 < r2) ? integral_R_rp_cc2(ra, rb, cre, cim, rm, r1, r2) : integral_R_rp_cc2(ra, rb, cre, cim, rm, r2, r1);
+            A = (-g->a * g->l + 4.) * rp - 2. * a2;
+            B = (+g->a * g->l - 4.) * rm + 2. * a2;
+            time += 4. * fabs(R0) + 2. * fabs(R1) + fabs(R2) + (A * fabs(RA) + B * fabs(RB)) / sqrt(1. - a2);
+            break;
+        }
+        default:                            /* RR_DBL, RR_BH, CC: not implemented in the reference either */
+            return NAN;
+    }
+    return time;
+}
+
 } /* namespace s5 */
 #endif

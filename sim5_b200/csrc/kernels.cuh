@@ -97,7 +97,7 @@ __device__ __forceinline__ void flush_stats(const unsigned int* s_cnt, unsigned 
 /* ------------------------------------------------------------------ */
 /* modes EQPLANE / POLARIZED : analytic geodesic per pixel             */
 /* ------------------------------------------------------------------ */
-template <bool DEFER>
+template <bool DEFER, bool DELAY = false>
 __global__ void __launch_bounds__(S5_EQ_THREADS, S5_MIN_CTAS_EQ)
 k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQueue q, unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
 {
@@ -138,7 +138,7 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
             int ix = (int)(p - (long long)lr * nx);
             int iy = s5_local_to_image_row(&c, lr);
             PixelOut o;
-            deferred = trace_eqplane_pixel_t<DEFER>(c, ix, iy, &o, &z);
+            deferred = trace_eqplane_pixel_t<DEFER, DELAY>(c, ix, iy, &o, &z);
             i = out.compact ? (size_t)p : (size_t)iy * (size_t)nx + (size_t)ix;
             store_pixel(out, c.outputs, i, o);
             atomicAdd(&s_cnt[o.status & 31], 1u);
@@ -589,6 +589,52 @@ __global__ void k_batch_libm(int op, long long n, const double* a, const double*
             default: v = NAN;
         }
         o[i] = v;
+    }
+}
+
+/* the integrals behind geodesic_timedelay (op codes: sim5_b200.h sim5_batch_integral) */
+__global__ void k_batch_integral(int op, long long n, const double* v0, const double* v1, const double* v2, const double* v3,
+                                 const double* v4, const double* v5, const double* v6, double* o)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double r;
+        switch (op) {
+            case 0: r = integral_C1(v0[i], v1[i]); break;
+            case 1: r = integral_C2(v0[i], v1[i]); break;
+            case 2: r = integral_C2_cos(v0[i], v1[i]); break;
+            case 3: r = integral_Z2(v0[i], v1[i], v2[i], v3[i]); break;
+            case 4: r = integral_Rm1(v0[i], v1[i], v2[i]); break;
+            case 5: r = integral_Rm2(v0[i], v1[i], v2[i]); break;
+            case 6: r = integral_R2(v0[i], v1[i], v2[i]); break;
+            case 7: r = integral_R_r0_re(v0[i], v1[i], v2[i], v3[i], v4[i]); break;
+            case 8: r = integral_R_r0_re_inf(v0[i], v1[i], v2[i], v3[i]); break;
+            case 9: r = integral_R_r1_re(v0[i], v1[i], v2[i], v3[i], v4[i]); break;
+            case 10: r = integral_R_r2_re(v0[i], v1[i], v2[i], v3[i], v4[i]); break;
+            case 11: r = integral_T_m0(v0[i], v1[i], v2[i]); break;
+            case 12: r = integral_T_m2(v0[i], v1[i], v2[i]); break;
+            case 13: r = integral_R_r0_cc(v0[i], v1[i], v2[i], v3[i], v4[i]); break;
+            case 14: r = integral_R_r0_cc_inf(v0[i], v1[i], v2[i], v3[i]); break;
+            case 15: r = integral_R_r1_cc(v0[i], v1[i], v2[i], v3[i], v4[i], v5[i]); break;
+            case 16: r = integral_R_r2_cc(v0[i], v1[i], v2[i], v3[i], v4[i], v5[i]); break;
+            case 17: r = integral_R_rp_cc2(v0[i], v1[i], v2[i], v3[i], v6[i], v4[i], v5[i]); break;
+            default: r = NAN;
+        }
+        o[i] = r;
+    }
+}
+/* geodesic_timedelay between two radii on the way in, for n geodesics from infinity (sin_i, cos_i: host libm, as every image call) */
+__global__ void k_batch_timedelay(long long n, double incl, double sin_i, double cos_i, double a, const double* alpha, const double* beta,
+                                  const double* ra, const double* rb, double* o)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Geodesic gd;
+        int error = 0;
+        double r = NAN;
+        if (geodesic_init_inf_sc(incl, sin_i, cos_i, a, alpha[i], beta[i], &gd, &error)) {
+            double Pa = geodesic_P_int(&gd, ra[i], 0), Pb = geodesic_P_int(&gd, rb[i], 0);
+            r = geodesic_timedelay(&gd, Pa, 0.0, 0.0, Pb, 0.0, 0.0);
+        }
+        o[i] = r;
     }
 }
 

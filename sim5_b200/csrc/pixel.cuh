@@ -618,7 +618,9 @@ S5_HD S5_MID void polarized_hit(const S5ImageConsts& c, const Geodesic* gd, doub
 /* modes EQPLANE and POLARIZED */
 /* DEFER: when the azimuth is requested, a hit fills *defer (returns true) instead of computing phi here
  * (the instantiation then carries no azimuth code at all) */
-template <bool DEFER>
+/* DELAY: the instantiation also evaluates geodesic_timedelay between the hit and the sphere r = delay_r_ref (SIM5_OUT_DELAY,
+ * SURVEY 8f N2); the default instantiation carries none of that code */
+template <bool DEFER, bool DELAY = false>
 S5_HD S5_INL bool trace_eqplane_pixel_t(const S5ImageConsts& c, int ix, int iy, PixelOut* o, AzIn* defer)
 {
     double alpha, beta;
@@ -655,6 +657,12 @@ S5_HD S5_INL bool trace_eqplane_pixel_t(const S5ImageConsts& c, int ix, int iy, 
                     o->phi = (c.flags & SIM5_FLAG_EXACT_AZIMUTH) ? azimuth_equatorial(&gd, k, r, P) : azimuth_equatorial_default(&gd, k, r, P);
                 }
             }
+            if (DELAY) {
+                if (c.outputs & SIM5_OUT_DELAY) {
+                    double Pref = geodesic_P_int(&gd, c.delay_r_ref, 0);
+                    o->delay = geodesic_timedelay(&gd, Pref, c.delay_r_ref, 0.0, P, r, 0.0);
+                }
+            }
             if (c.mode == SIM5_MODE_POLARIZED) {
                 polarized_hit(c, &gd, r, P, o);
             } else {
@@ -671,7 +679,8 @@ S5_HD S5_INL bool trace_eqplane_pixel_t(const S5ImageConsts& c, int ix, int iy, 
 }
 S5_HD S5_INL void trace_eqplane_pixel(const S5ImageConsts& c, int ix, int iy, PixelOut* o)
 {
-    trace_eqplane_pixel_t<false>(c, ix, iy, o, nullptr);
+    if (c.outputs & SIM5_OUT_DELAY) trace_eqplane_pixel_t<false, true>(c, ix, iy, o, nullptr);
+    else                            trace_eqplane_pixel_t<false>(c, ix, iy, o, nullptr);
 }
 
 /* mode SPECTRUM: what one disk hit contributes.  Returns false for pixels without a hit (or with T = 0 / g <= 0, which

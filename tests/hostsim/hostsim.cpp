@@ -49,6 +49,48 @@ void hs_batch_rf_hi(long n, const double* x, const double* y, const double* z, d
 void hs_batch_rj_hi(long n, const double* x, const double* y, const double* z, const double* p, double* o) { for (long i = 0; i < n; i++) o[i] = (hi_domain(x[i], y[i], z[i]) && hi_domain_p(p[i])) ? rj_hi(x[i], y[i], z[i], p[i]) : NAN; }
 void hs_batch_sncndn(long n, const double* u, const double* m, double* sn, double* cn, double* dn) { for (long i = 0; i < n; i++) jacobi_sncndn(u[i], m[i], &sn[i], &cn[i], &dn[i]); }
 
+void hs_batch_integral(int op, long n, const double* v0, const double* v1, const double* v2, const double* v3, const double* v4,
+                       const double* v5, const double* v6, double* o)
+{
+    for (long i = 0; i < n; i++) {
+        double r;
+        switch (op) {
+            case 0: r = integral_C1(v0[i], v1[i]); break;
+            case 1: r = integral_C2(v0[i], v1[i]); break;
+            case 2: r = integral_C2_cos(v0[i], v1[i]); break;
+            case 3: r = integral_Z2(v0[i], v1[i], v2[i], v3[i]); break;
+            case 4: r = integral_Rm1(v0[i], v1[i], v2[i]); break;
+            case 5: r = integral_Rm2(v0[i], v1[i], v2[i]); break;
+            case 6: r = integral_R2(v0[i], v1[i], v2[i]); break;
+            case 7: r = integral_R_r0_re(v0[i], v1[i], v2[i], v3[i], v4[i]); break;
+            case 8: r = integral_R_r0_re_inf(v0[i], v1[i], v2[i], v3[i]); break;
+            case 9: r = integral_R_r1_re(v0[i], v1[i], v2[i], v3[i], v4[i]); break;
+            case 10: r = integral_R_r2_re(v0[i], v1[i], v2[i], v3[i], v4[i]); break;
+            case 11: r = integral_T_m0(v0[i], v1[i], v2[i]); break;
+            case 12: r = integral_T_m2(v0[i], v1[i], v2[i]); break;
+            case 13: r = integral_R_r0_cc(v0[i], v1[i], v2[i], v3[i], v4[i]); break;
+            case 14: r = integral_R_r0_cc_inf(v0[i], v1[i], v2[i], v3[i]); break;
+            case 15: r = integral_R_r1_cc(v0[i], v1[i], v2[i], v3[i], v4[i], v5[i]); break;
+            case 16: r = integral_R_r2_cc(v0[i], v1[i], v2[i], v3[i], v4[i], v5[i]); break;
+            case 17: r = integral_R_rp_cc2(v0[i], v1[i], v2[i], v3[i], v6[i], v4[i], v5[i]); break;
+            default: r = NAN;
+        }
+        o[i] = r;
+    }
+}
+void hs_batch_timedelay(long n, double incl, double a, const double* alpha, const double* beta, const double* ra, const double* rb, double* o)
+{
+    double si, ci;
+    sincos(incl, &si, &ci);
+    for (long i = 0; i < n; i++) {
+        Geodesic gd; int error = 0;
+        o[i] = NAN;
+        if (!geodesic_init_inf_sc(incl, si, ci, a, alpha[i], beta[i], &gd, &error)) continue;
+        double Pa = geodesic_P_int(&gd, ra[i], 0), Pb = geodesic_P_int(&gd, rb[i], 0);
+        o[i] = geodesic_timedelay(&gd, Pa, 0.0, 0.0, Pb, 0.0, 0.0);
+    }
+}
+
 // geodesic_init_inf through the scalar-API path (cr_sincos of the inclination); g is the 240-byte reference struct
 int hs_geodesic_init_inf(double i, double a, double alpha, double beta, void* g, int* error)
 {

@@ -57,6 +57,22 @@ def main():
     pl, st, _ = H.run_ref(p)
     np.savez_compressed(os.path.join(OUT, "image_surface_rin8_40x28.npz"), class_count=np.array(list(st.class_count)), **pl.arrays)
 
+    # ---- geodesic_timedelay: the B&F integrals behind it, delays between two radii on random geodesics, the DELAY plane
+    import test_timedelay as TD
+    trng = np.random.default_rng(20261018)
+    out = {}
+    for name, v in TD.integral_args(trng, 400).items():
+        for k in range(7):
+            out["%s_v%d" % (name, k)] = v[k]
+        out[name] = TD.cpu_integral(ref, "ref_batch_integral", TD.OPS[name], v)
+    al, be, ra, rb = TD.delay_args(trng, 600)
+    out.update(alpha=al, beta=be, ra=ra, rb=rb, incl=abi.deg2rad(60.0), spin=0.9)
+    out["delay"] = TD.cpu_timedelay(ref, "ref_batch_timedelay", abi.deg2rad(60.0), 0.9, al, be, ra, rb)
+    p = TD.delay_params(48)
+    pl, st, _ = H.run_ref(p)
+    out.update(img_delay=pl["delay"], img_status=pl["status"])
+    np.savez_compressed(os.path.join(OUT, "timedelay.npz"), **out)
+
     # ---- thermal spectrum (SPECTRUM preset shrunk), incl. a partial spectrum of an interleaved split
     p = abi.default_params(6, 96)
     spec, _ = H.run_spectrum("ref", p)
