@@ -222,7 +222,7 @@ typedef struct sim5_trace_stats {
 /* lifecycle ------------------------------------------------------------- */
 int  sim5_gpu_init(int device);        /* create context/streams/scratch on `device`; idempotent */
 int  sim5_set_stream(void* cuda_stream); /* launch on the caller's cudaStream_t (e.g. torch's current stream); NULL = library stream */
-int  sim5_set_chunk_rays(int64_t rays); /* host-plane calls trace and copy back in chunks of about this many rays (copy of chunk k under the kernels of chunk k+1); <= 0 restores the default (2^20) */
+int  sim5_set_chunk_rays(int64_t rays); /* host-plane calls trace and copy back in chunks of about this many rays (copy of chunk k under the kernels of chunk k+1); <= 0 restores the default (2^21) */
 int  sim5_synchronize(void);            /* wait for everything enqueued by SIM5_FLAG_ASYNC calls */
 void sim5_gpu_shutdown(void);
 int  sim5_gpu_device_count(void);      /* 0 when no usable device */

@@ -29,7 +29,8 @@ using s5::AzQueue;
 namespace {
 
 #define S5_MAX_CHUNKS 32
-#define S5_CHUNK_RAYS (1 << 20)     /* rays per chunk of a host-plane call: ~1.1 ms of kernels, ~0.6 ms of PCIe */
+#define S5_CHUNK_RAYS (1 << 21)     /* rays per chunk of a host-plane call: ~1.1 ms of kernels, ~1.2 ms of PCIe.  4096^2 r/phi/g/flux/status end to end
+                                       (profiles/r01x_sweep.log, ms): 2^18 13.6, 2^19 13.6, 2^20 11.9, 2^21 11.4, 2^22 12.2, 2^23 14.4 */
 
 struct Scratch {                  /* mapped pinned memory shared by host and device for scalar calls */
     s5::Geodesic g;

@@ -47,10 +47,13 @@ struct AzQueue {
 
 #define S5_CTA_THREADS 128
 #ifndef S5_EQ_THREADS
-#define S5_EQ_THREADS 512          /* CTA size of the eq-plane trace kernels; r01p sweep: 512 x 1 CTA/SM 5.38 ms, 256 x 2 5.55, 128 x 4 5.68, 64 x 8 5.68 */
+#define S5_EQ_THREADS 512          /* CTA size of the eq-plane trace kernels */
 #endif
 #ifndef S5_MIN_CTAS_EQ
-#define S5_MIN_CTAS_EQ 1          /* resident CTAs per SM the eq-plane kernel is compiled for: 512 threads x 1 CTA = 128 registers per thread */
+#define S5_MIN_CTAS_EQ 2          /* resident CTAs per SM the eq-plane kernel is compiled for.  With the CTA-lockstep tile loop the kernel is bound by
+                                     dependent-issue latency, not by registers: profiles/r01x_sweep.log (phase A of cfg 2, ms): 512 x 1 (128 regs, 16
+                                     warps/SM) 5.33, 640 x 1 (96) 4.95, 768 x 1 (80) 4.80, 896 x 1 (72) 4.76, 1024 x 1 (64) 4.72, 384 x 3 (56) 4.84,
+                                     256 x 4 (64) 5.11, 512 x 2 (64 regs, 32 warps/SM, ~800 B of spills per thread served by L1) 4.63 */
 #endif
 #ifndef S5_MIN_CTAS_STEP
 #define S5_MIN_CTAS_STEP 1
@@ -282,7 +285,7 @@ k_azimuth_fast(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double*
 #define S5_REFILL_MIN 4
 
 template <class PROG>
-__global__ void __launch_bounds__(S5_CTA_THREADS, S5_MIN_CTAS_STEP)
+__global__ void __launch_bounds__(S5_CTA_THREADS, PROG::MIN_CTAS)
 k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigned long long* __restrict__ ray_counter, DevStats* __restrict__ gstats)
 {
     __shared__ S5ImageConsts c;
@@ -307,7 +310,7 @@ k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigne
         unsigned idle = __ballot_sync(0xffffffffu, !live);
         if (idle == 0xffffffffu && drained) break;
         /* refill finished lanes: always when the whole warp is idle; otherwise once enough lanes wait */
-        bool do_fill = !drained && (idle == 0xffffffffu || (refill && __popc(idle) >= S5_REFILL_MIN));
+        bool do_fill = !drained && (idle == 0xffffffffu || (refill && __popc(idle) >= PROG::REFILL_MIN));
         if (do_fill) {
             int nreq = __popc(idle);
             unsigned long long base = 0;

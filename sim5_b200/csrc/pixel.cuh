@@ -956,14 +956,34 @@ S5_HD S5_MID int surface_step(const S5ImageConsts& c, SurfRay* s)
 }
 
 /* the two ray programs of the lane-refill kernel (kernels.cuh:k_trace_lanes) */
+#ifndef S5_MIN_CTAS_STEP
+#define S5_MIN_CTAS_STEP 1
+#endif
 struct StepwiseProg {
     typedef StepRay State;
+    static const int REFILL_MIN = 4;              /* idle lanes of a warp that trigger a refill (S5_REFILL_MIN) */
+    static const int MIN_CTAS = S5_MIN_CTAS_STEP; /* resident 128-thread CTAs per SM the kernel is compiled for */
     static S5_HD S5_INL bool start(const S5ImageConsts& c, int ix, int iy, State* s, PixelOut* o) { return stepwise_start(c, ix, iy, s, o); }
     static S5_HD S5_INL int step(const S5ImageConsts& c, State* s) { return stepwise_step(c, s); }
     static S5_HD S5_INL void finish(const S5ImageConsts& c, State* s, int cls, PixelOut* o) { stepwise_finish(c, s, cls, o); }
 };
+/* profiles/r01x_sweep.log (1024^2 preset, ms): a ray's start (init_inf, P_int) costs ~30 sub-steps, so refilling a few idle lanes
+ * while the rest of the warp waits loses more than it gains -- refill at 4 / 8 / 16 / 24 idle lanes 61.9 / 60.1 / 57.9 / 56.4, only when
+ * the whole warp is idle 56.0 (neighbouring pixels take similar numbers of sub-steps).  Occupancy is what pays: 1 CTA/SM (226 regs)
+ * 56.0, 2: 56.7, 3 (168): 47.6, 4 (128): 44.1, 5 (96 regs, 20 warps/SM): 42.7, 6 (80): 44.2, 8 (64): 46.5 */
+#ifndef S5_SURF_REFILL_MIN
+#define S5_SURF_REFILL_MIN 32
+#endif
+#ifndef S5_SURF_MIN_CTAS
+#define S5_SURF_MIN_CTAS 5
+#endif
+#ifndef S5_MIN_CTAS_STEP
+#define S5_MIN_CTAS_STEP 1
+#endif
 struct SurfaceProg {
     typedef SurfRay State;
+    static const int REFILL_MIN = S5_SURF_REFILL_MIN;
+    static const int MIN_CTAS = S5_SURF_MIN_CTAS;
     static S5_HD S5_INL bool start(const S5ImageConsts& c, int ix, int iy, State* s, PixelOut* o) { return surface_start(c, ix, iy, s, o); }
     /* the kernel's protocol is "0 while live"; SIM5_ST_HIT0 is 0, so the class travels with bit 8 set */
     static S5_HD S5_INL int step(const S5ImageConsts& c, State* s) { int r = surface_step(c, s); return r < 0 ? 0 : (r | 0x100); }

@@ -33,6 +33,20 @@ p = abi.default_params(3); ms, st = t(p); res["cfg3_ms"] = round(ms,3); res["cfg
 p = abi.default_params(4, 512); ms, st = t(p, 1); res["cfg4_512_ms"] = round(ms,2); res["cfg4_steps_s"] = "%%.3e" %% (st.total_steps/ms*1e3)
 if os.environ.get("SWEEP_NOREFILL"):
     p.flags = abi.FLAG_NO_REFILL; ms, st = t(p, 1); res["cfg4_512_norefill_ms"] = round(ms,2)
+p = abi.default_params(7); ms, st = t(p, 2); res["cfg7_ms"] = round(ms,2)
+p.flags |= abi.FLAG_NO_REFILL; ms, st = t(p, 1); res["cfg7_norefill_ms"] = round(ms,2)
+if os.environ.get("SWEEP_CHUNKS"):
+    import time
+    L = api.lib()
+    p = abi.default_params(2)
+    planes = api.HostPlanes(p, pinned=True)
+    for lg in (18, 19, 20, 21, 22, 23):
+        L.sim5_set_chunk_rays(1 << lg)
+        best = 1e30
+        for _ in range(4):
+            t0 = time.perf_counter(); api.trace_image(p, planes); best = min(best, time.perf_counter() - t0)
+        res["e2e_chunk_2^%%d_ms" %% lg] = round(best * 1e3, 3)
+    L.sim5_set_chunk_rays(0)
 res.pop("_phases", None)
 print(json.dumps(res))
 ''' % (ROOT, ROOT)
