@@ -139,6 +139,8 @@ int ensure_init(int device)
     CK(cudaHostAlloc((void**)&c.h_stats, sizeof(DevStats), cudaHostAllocDefault));
     /* the stepper keeps ~100 doubles of live state per thread and calls non-inlined Carlson routines */
     cudaDeviceSetLimit(cudaLimitStackSize, 8192);
+    /* (cudaFuncAttributePreferredSharedMemoryCarveout = 0, i.e. all 256 KB to L1, was tried for the spilling kernels: phase A unchanged,
+     * SURFACE 42.6 -> 45.4 ms -- profiles/r01z_sweep.log -- so the driver's default carve-out stays) */
     c.ready = true;
     return SIM5_OK;
 }

@@ -55,6 +55,9 @@ struct AzQueue {
                                      warps/SM) 5.33, 640 x 1 (96) 4.95, 768 x 1 (80) 4.80, 896 x 1 (72) 4.76, 1024 x 1 (64) 4.72, 384 x 3 (56) 4.84,
                                      256 x 4 (64) 5.11, 512 x 2 (64 regs, 32 warps/SM, ~800 B of spills per thread served by L1) 4.63 */
 #endif
+#ifndef S5_EQ_TILES_PER_SYNC
+#define S5_EQ_TILES_PER_SYNC 1    /* tiles a warp traces between two CTA barriers of the lockstep tile loop */
+#endif
 #ifndef S5_MIN_CTAS_STEP
 #define S5_MIN_CTAS_STEP 1
 #endif
@@ -71,22 +74,30 @@ __device__ __forceinline__ void stage_consts(S5ImageConsts* dst, const S5ImageCo
     __syncthreads();
 }
 
+/* Output planes and queue items are written once and never read back by the writing kernel: streaming stores (st.global.cs,
+ * evict-first) keep them from displacing the kernels' register spills from L2 (64 registers per thread at 32 warps/SM: ~100 MB of
+ * local memory in flight next to 3 GB of output per image). */
+#if defined(S5_NO_STREAM_STORES)
+#define S5_ST(ptr, v) (*(ptr) = (v))
+#else
+#define S5_ST(ptr, v) __stcs((ptr), (v))
+#endif
 __device__ __forceinline__ void store_pixel(const DevOut& out, unsigned outputs, size_t i, const PixelOut& o)
 {
-    if (outputs & SIM5_OUT_R)         out.r[i] = o.r;
-    if (outputs & SIM5_OUT_PHI)       out.phi[i] = o.phi;
-    if (outputs & SIM5_OUT_G)         out.g[i] = o.g;
-    if (outputs & SIM5_OUT_FLUX)      out.flux[i] = o.flux;
-    if (outputs & SIM5_OUT_CHI)       out.chi[i] = o.chi;
-    if (outputs & SIM5_OUT_DELTA)     out.delta[i] = o.delta;
-    if (outputs & SIM5_OUT_MUE)       out.mue[i] = o.mue;
-    if (outputs & SIM5_OUT_INTENSITY) out.intensity[i] = o.intensity;
-    if (outputs & SIM5_OUT_TAU)       out.tau[i] = o.tau;
-    if (outputs & SIM5_OUT_QERR)      out.qerr[i] = o.qerr;
-    if (outputs & SIM5_OUT_HEIGHT)    out.height[i] = o.height;
-    if (outputs & SIM5_OUT_DELAY)     out.delay[i] = o.delay;
-    if (outputs & SIM5_OUT_STEPS)     out.steps[i] = o.steps;
-    if (outputs & SIM5_OUT_STATUS)    out.status[i] = (unsigned char)o.status;
+    if (outputs & SIM5_OUT_R)         S5_ST(&out.r[i], o.r);
+    if (outputs & SIM5_OUT_PHI)       S5_ST(&out.phi[i], o.phi);
+    if (outputs & SIM5_OUT_G)         S5_ST(&out.g[i], o.g);
+    if (outputs & SIM5_OUT_FLUX)      S5_ST(&out.flux[i], o.flux);
+    if (outputs & SIM5_OUT_CHI)       S5_ST(&out.chi[i], o.chi);
+    if (outputs & SIM5_OUT_DELTA)     S5_ST(&out.delta[i], o.delta);
+    if (outputs & SIM5_OUT_MUE)       S5_ST(&out.mue[i], o.mue);
+    if (outputs & SIM5_OUT_INTENSITY) S5_ST(&out.intensity[i], o.intensity);
+    if (outputs & SIM5_OUT_TAU)       S5_ST(&out.tau[i], o.tau);
+    if (outputs & SIM5_OUT_QERR)      S5_ST(&out.qerr[i], o.qerr);
+    if (outputs & SIM5_OUT_HEIGHT)    S5_ST(&out.height[i], o.height);
+    if (outputs & SIM5_OUT_DELAY)     S5_ST(&out.delay[i], o.delay);
+    if (outputs & SIM5_OUT_STEPS)     S5_ST(&out.steps[i], o.steps);
+    if (outputs & SIM5_OUT_STATUS)    S5_ST(&out.status[i], (unsigned char)o.status);
 }
 
 __device__ __forceinline__ void flush_stats(const unsigned int* s_cnt, unsigned long long s_steps, DevStats* gs)
@@ -120,22 +131,43 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
     for (;;) {
         unsigned long long t = 0;
 #if !defined(S5_EQ_FREERUN)
-        /* the CTA takes one tile per warp at a time and passes a barrier per batch, so its 16 warps walk the (183 KB) routine together and
-         * share instruction-cache lines: r01q sweep 5.33 vs 5.40 ms free-running (cfg 3: 2.67 vs 2.81 ms); -DS5_EQ_FREERUN restores per-warp pulls */
+        /* the CTA takes S5_EQ_TILES_PER_SYNC tiles per warp at a time and passes a barrier per batch, so its 16 warps walk the (183 KB)
+         * routine together and share instruction-cache lines: r01q sweep 5.33 vs 5.40 ms free-running (cfg 3: 2.67 vs 2.81 ms);
+         * -DS5_EQ_FREERUN restores per-warp pulls */
         __syncthreads();
-        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, (unsigned long long)(S5_EQ_THREADS / 32));
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, (unsigned long long)(S5_EQ_THREADS / 32 * S5_EQ_TILES_PER_SYNC));
         __syncthreads();
         if ((long long)s_tile >= ntiles) break;
-        t = s_tile + (threadIdx.x >> 5);
+      #pragma unroll 1
+      for (int sub = 0; sub < S5_EQ_TILES_PER_SYNC; sub++) {
+        t = s_tile + (unsigned long long)(sub * (S5_EQ_THREADS / 32)) + (threadIdx.x >> 5);
 #else
         if (lane == 0) t = atomicAdd(tile_counter, 1ULL);
         t = __shfl_sync(0xffffffffu, t, 0);
         if ((long long)t >= ntiles) break;
+      {
 #endif
         long long p = ((long long)t << 5) + lane;
         AzIn z;
         bool deferred = false;
         size_t i = 0;
+#if !defined(S5_EQ_FREERUN) && !defined(S5_EQ_NO_STAGE_SYNC)
+        {   /* every thread runs the routine (it has CTA barriers); threads past the end of the image trace its last pixel and drop the result */
+            const bool valid = (long long)t < ntiles && p < npix;
+            const long long pc = valid ? p : npix - 1;
+            int lr = (int)(pc / nx);
+            int ix = (int)(pc - (long long)lr * nx);
+            int iy = s5_local_to_image_row(&c, lr);
+            PixelOut o;
+            deferred = trace_eqplane_pixel_t<DEFER, DELAY, true>(c, ix, iy, &o, &z) && valid;
+            if (valid) {
+                i = out.compact ? (size_t)p : (size_t)iy * (size_t)nx + (size_t)ix;
+                store_pixel(out, c.outputs, i, o);
+                atomicAdd(&s_cnt[o.status & 31], 1u);
+                atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);
+            }
+        }
+#else
         if ((long long)t < ntiles && p < npix) {
             int lr = (int)(p / nx);
             int ix = (int)(p - (long long)lr * nx);
@@ -147,6 +179,7 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
             atomicAdd(&s_cnt[o.status & 31], 1u);
             atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);
         }
+#endif
         if (DEFER) {
             /* hand the azimuth of this tile's hits to phase B: one aggregated atomic per warp and geodesic type */
             bool is_rr = deferred && z.type == GEOD_TYPE_RR;
@@ -171,13 +204,14 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
             if (slot >= 0) {
                 double* f = q.f + slot;
                 const long long cap = q.cap;
-                f[0 * cap] = z.e0;  f[1 * cap] = z.e1;  f[2 * cap] = z.e2;   f[3 * cap] = z.e3;
-                f[4 * cap] = z.l;   f[5 * cap] = z.m2m; f[6 * cap] = z.m2p;  f[7 * cap] = z.mm;
-                f[8 * cap] = z.Tpp; f[9 * cap] = z.Tip; f[10 * cap] = z.Rpc; f[11 * cap] = z.beta;
-                f[12 * cap] = z.K_mm; f[13 * cap] = z.rf_u; f[14 * cap] = z.isn_inf; f[15 * cap] = z.r; f[16 * cap] = z.P;
-                q.key[slot] = (unsigned long long)i | ((unsigned long long)(z.nrr & 15) << 48) | ((unsigned long long)(z.rf_ok ? 1 : 0) << 56);
+                S5_ST(&f[0 * cap], z.e0);  S5_ST(&f[1 * cap], z.e1);  S5_ST(&f[2 * cap], z.e2);   S5_ST(&f[3 * cap], z.e3);
+                S5_ST(&f[4 * cap], z.l);   S5_ST(&f[5 * cap], z.m2m); S5_ST(&f[6 * cap], z.m2p);  S5_ST(&f[7 * cap], z.mm);
+                S5_ST(&f[8 * cap], z.Tpp); S5_ST(&f[9 * cap], z.Tip); S5_ST(&f[10 * cap], z.Rpc); S5_ST(&f[11 * cap], z.beta);
+                S5_ST(&f[12 * cap], z.K_mm); S5_ST(&f[13 * cap], z.rf_u); S5_ST(&f[14 * cap], z.isn_inf); S5_ST(&f[15 * cap], z.r); S5_ST(&f[16 * cap], z.P);
+                S5_ST(&q.key[slot], (unsigned long long)i | ((unsigned long long)(z.nrr & 15) << 48) | ((unsigned long long)(z.rf_ok ? 1 : 0) << 56));
             }
         }
+      }
     }
     flush_stats(s_cnt, 0, gstats);
 }

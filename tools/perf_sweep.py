@@ -29,6 +29,7 @@ p = abi.default_params(2); ms, st = t(p); res["cfg2_phi_ms"] = round(ms,3); res[
 if os.environ.get("SWEEP_EXACT"):
     p = abi.default_params(2); p.flags = abi.FLAG_EXACT_AZIMUTH; ms, st = t(p); res["cfg2_exact_ms"] = round(ms,3); res["cfg2_exact_phases_ms"] = res.pop("_phases")
 p = abi.default_params(2); p.outputs = abi.OUT_R|abi.OUT_G|abi.OUT_FLUX|abi.OUT_STATUS; ms, st = t(p); res["cfg2_nophi_ms"] = round(ms,3); res["cfg2_nophi_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
+p = abi.default_params(2); p.flags = abi.FLAG_SINGLE_PASS; ms, st = t(p); res["cfg2_single_pass_ms"] = round(ms,3); res.pop("_phases", None)
 p = abi.default_params(3); ms, st = t(p); res["cfg3_ms"] = round(ms,3); res["cfg3_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
 p = abi.default_params(4, 512); ms, st = t(p, 1); res["cfg4_512_ms"] = round(ms,2); res["cfg4_steps_s"] = "%%.3e" %% (st.total_steps/ms*1e3)
 if os.environ.get("SWEEP_NOREFILL"):
