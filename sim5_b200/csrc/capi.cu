@@ -139,6 +139,12 @@ int ensure_init(int device)
     CK(cudaHostAlloc((void**)&c.h_stats, sizeof(DevStats), cudaHostAllocDefault));
     /* the stepper keeps ~100 doubles of live state per thread and calls non-inlined Carlson routines */
     cudaDeviceSetLimit(cudaLimitStackSize, 8192);
+    if (S5_EQ_DYN_SMEM > 0) {
+        CK(cudaFuncSetAttribute(s5::k_trace_eqplane<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S5_EQ_DYN_SMEM));
+        CK(cudaFuncSetAttribute(s5::k_trace_eqplane<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S5_EQ_DYN_SMEM));
+        CK(cudaFuncSetAttribute(s5::k_trace_eqplane<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S5_EQ_DYN_SMEM));
+        CK(cudaFuncSetAttribute(s5::k_trace_eqplane<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S5_EQ_DYN_SMEM));
+    }
     /* (cudaFuncAttributePreferredSharedMemoryCarveout = 0, i.e. all 256 KB to L1, was tried for the spilling kernels: phase A unchanged,
      * SURFACE 42.6 -> 45.4 ms -- profiles/r01z_sweep.log -- so the driver's default carve-out stays) */
     c.ready = true;
@@ -166,10 +172,10 @@ int reserve_consts(size_t n)
 }
 
 template <class K>
-int persistent_grid(K kernel, int threads)
+int persistent_grid(K kernel, int threads, size_t dyn_smem = 0)
 {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     return g_ctx.sm_count * per_sm;
 }
 
@@ -532,11 +538,31 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     chunk_rows = ((chunk_rows + srows - 1) / srows) * srows;
     if (chunk_rows < srows) chunk_rows = srows;
     nchunks = nrows_local > 0 ? (nrows_local + chunk_rows - 1) / chunk_rows : 1;
+    /* chunk boundaries in local rows.  The first chunk's kernels and the last chunk's copy are the only exposed pieces of the
+     * pipeline, so with >= 4 chunks the first and the last are cut in half (one more chunk in total) */
+    int chunk_lr[S5_MAX_CHUNKS + 2];
+    {
+        int n = 0, lr = 0;
+        bool ramp = nchunks >= 4 && nchunks + 1 <= S5_MAX_CHUNKS && (chunk_rows / 2 / srows) * srows >= srows;
+        int half = ramp ? (chunk_rows / 2 / srows) * srows : chunk_rows;
+        chunk_lr[n++] = 0;
+        if (ramp) { lr = half; chunk_lr[n++] = lr; }
+        while (lr < nrows_local && n <= S5_MAX_CHUNKS) {
+            int left = nrows_local - lr;
+            int take = (ramp && left <= chunk_rows + half && left > half) ? left - half : (left < chunk_rows ? left : chunk_rows);
+            if (n == S5_MAX_CHUNKS) take = left;
+            lr += take; chunk_lr[n++] = lr;
+        }
+        nchunks = nrows_local > 0 ? n - 1 : 1;
+        if (nrows_local == 0) chunk_lr[1] = 0;
+    }
 
     AzQueue q;
     memset(&q, 0, sizeof q);
     if (two_phase) {
-        size_t qpix = (size_t)(nchunks > 1 ? chunk_rows : nrows_local) * (size_t)p->nx;
+        int max_rows = 0;
+        for (int ch = 0; ch < nchunks; ch++) if (chunk_lr[ch + 1] - chunk_lr[ch] > max_rows) max_rows = chunk_lr[ch + 1] - chunk_lr[ch];
+        size_t qpix = (size_t)max_rows * (size_t)p->nx;
         rc = reserve(c.azq_f, qpix * S5_AZ_NFIELDS * sizeof(double)); if (rc) return rc;
         rc = reserve(c.azq_key, qpix * sizeof(unsigned long long)); if (rc) return rc;
         rc = reserve(c.azq_redo, qpix * sizeof(unsigned)); if (rc) return rc;
@@ -548,8 +574,8 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     int grid = 0, launches = 0;
     CK(cudaEventRecord(c.ev1, c.stream));
     for (int ch = 0; ch < nchunks && npix > 0; ch++) {
-        int lr0 = ch * chunk_rows;
-        int lrows = nrows_local - lr0 < chunk_rows ? nrows_local - lr0 : chunk_rows;
+        int lr0 = chunk_lr[ch];
+        int lrows = chunk_lr[ch + 1] - lr0;
         size_t pix0 = (size_t)lr0 * (size_t)p->nx;
         S5ImageConsts cc = consts;
         DevOut dd = d;
@@ -572,11 +598,11 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
             s5::k_trace_lanes<s5::SurfaceProg><<<grid, S5_CTA_THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
         } else if (two_phase) {
             if (p->outputs & SIM5_OUT_DELAY) {
-                grid = persistent_grid(s5::k_trace_eqplane<true, true>, S5_EQ_THREADS);
-                s5::k_trace_eqplane<true, true><<<grid, S5_EQ_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+                grid = persistent_grid(s5::k_trace_eqplane<true, true>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
+                s5::k_trace_eqplane<true, true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
             } else {
-                grid = persistent_grid(s5::k_trace_eqplane<true>, S5_EQ_THREADS);
-                s5::k_trace_eqplane<true><<<grid, S5_EQ_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+                grid = persistent_grid(s5::k_trace_eqplane<true>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
+                s5::k_trace_eqplane<true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
             }
             if (ch == 0) CK(cudaEventRecord(c.evp[0], c.stream));
             int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_AZ_THREADS);
@@ -616,11 +642,11 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
             launches += 2;
         } else {
             if (p->outputs & SIM5_OUT_DELAY) {
-                grid = persistent_grid(s5::k_trace_eqplane<false, true>, S5_EQ_THREADS);
-                s5::k_trace_eqplane<false, true><<<grid, S5_EQ_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+                grid = persistent_grid(s5::k_trace_eqplane<false, true>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
+                s5::k_trace_eqplane<false, true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
             } else {
-                grid = persistent_grid(s5::k_trace_eqplane<false>, S5_EQ_THREADS);
-                s5::k_trace_eqplane<false><<<grid, S5_EQ_THREADS, 0, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+                grid = persistent_grid(s5::k_trace_eqplane<false>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
+                s5::k_trace_eqplane<false><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
             }
         }
         launches += 1;

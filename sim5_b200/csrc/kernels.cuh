@@ -55,6 +55,15 @@ struct AzQueue {
                                      warps/SM) 5.33, 640 x 1 (96) 4.95, 768 x 1 (80) 4.80, 896 x 1 (72) 4.76, 1024 x 1 (64) 4.72, 384 x 3 (56) 4.84,
                                      256 x 4 (64) 5.11, 512 x 2 (64 regs, 32 warps/SM, ~800 B of spills per thread served by L1) 4.63 */
 #endif
+#if !defined(S5_EQ_NO_SMEM_GD)
+#define S5_EQ_SMEM_GD 1           /* the ray's geodesic struct lives in a per-thread shared-memory slot (pixel.cuh SGD): spill stores of the
+                                     64-register build 1106 -> 482 B; cfg 2 without phi 4.14 -> 4.02 ms, cfg 3 2.50 -> 2.46 ms (profiles/r02d_sweep.log) */
+#endif
+#if defined(S5_EQ_SMEM_GD) && !defined(S5_EQ_FREERUN) && !defined(S5_EQ_NO_STAGE_SYNC)
+#define S5_EQ_DYN_SMEM ((size_t)S5_EQ_THREADS * 200 + 64)     /* per-thread geodesic slots (S5_GD_SLOT_BYTES) */
+#else
+#define S5_EQ_DYN_SMEM ((size_t)0)
+#endif
 #ifndef S5_EQ_TILES_PER_SYNC
 #define S5_EQ_TILES_PER_SYNC 1    /* tiles a warp traces between two CTA barriers of the lockstep tile loop */
 #endif
@@ -159,7 +168,13 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
             int ix = (int)(pc - (long long)lr * nx);
             int iy = s5_local_to_image_row(&c, lr);
             PixelOut o;
+#if defined(S5_EQ_SMEM_GD)
+            extern __shared__ double s_dyn[];
+            Geodesic* gslot = reinterpret_cast<Geodesic*>(reinterpret_cast<char*>(s_dyn) + (size_t)threadIdx.x * S5_GD_SLOT_BYTES);
+            deferred = trace_eqplane_pixel_t<DEFER, DELAY, true, true>(c, ix, iy, &o, &z, gslot) && valid;
+#else
             deferred = trace_eqplane_pixel_t<DEFER, DELAY, true>(c, ix, iy, &o, &z) && valid;
+#endif
             if (valid) {
                 i = out.compact ? (size_t)p : (size_t)iy * (size_t)nx + (size_t)ix;
                 store_pixel(out, c.outputs, i, o);

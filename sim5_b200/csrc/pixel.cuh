@@ -625,15 +625,20 @@ S5_HD S5_MID void polarized_hit(const S5ImageConsts& c, const Geodesic* gd, doub
  * is ~190 KB of SASS against a 32 KB L1.5 instruction cache, so it runs from L2; the barriers keep all warps of the CTA inside
  * the same stage, i.e. on the same instruction lines, and every line is fetched once per batch instead of once per warp.  The
  * retry of higher crossing orders (a few rays per thousand) runs without barriers.  Same calls in the same order: same bits. */
-template <bool DEFER, bool DELAY = false, bool SYNC = false>
-S5_HD S5_INL bool trace_eqplane_pixel_t(const S5ImageConsts& c, int ix, int iy, PixelOut* o, AzIn* defer)
+/* SGD: the geodesic lives in the caller's slot *gslot (a per-thread slice of shared memory, S5_GD_SLOT_BYTES apart: the first
+ * 200 bytes of the struct are all the routine touches) instead of in registers / local memory: the ~20 doubles of it that stay
+ * live from the roots to the emission stage then cost a conflict-free ld.shared instead of a register each or a spill */
+#define S5_GD_SLOT_BYTES 200      /* offsetof(Geodesic, k): 50 words per thread = conflict-free 64-bit accesses per half-warp */
+template <bool DEFER, bool DELAY = false, bool SYNC = false, bool SGD = false>
+S5_HD S5_INL bool trace_eqplane_pixel_t(const S5ImageConsts& c, int ix, int iy, PixelOut* o, AzIn* defer, Geodesic* gslot = nullptr)
 {
     double alpha, beta;
     pixel_impact(c, ix, iy, &alpha, &beta);
     o->r = o->phi = o->g = o->flux = o->chi = o->delta = o->mue = 0.0;
     o->intensity = o->tau = o->qerr = o->height = o->delay = 0.0; o->steps = 0;
 
-    Geodesic gd;
+    Geodesic gd_local;
+    Geodesic& gd = SGD ? *gslot : gd_local;
     int error = 0;
     RayCache k;
     gd.type = -1;
