@@ -144,6 +144,7 @@ int ensure_init(int device)
         CK(cudaFuncSetAttribute(s5::k_trace_eqplane<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S5_EQ_DYN_SMEM));
         CK(cudaFuncSetAttribute(s5::k_trace_eqplane<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S5_EQ_DYN_SMEM));
         CK(cudaFuncSetAttribute(s5::k_trace_eqplane<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S5_EQ_DYN_SMEM));
+        CK(cudaFuncSetAttribute(s5::k_trace_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S5_EQ_DYN_SMEM));
     }
     /* (cudaFuncAttributePreferredSharedMemoryCarveout = 0, i.e. all 256 KB to L1, was tried for the spilling kernels: phase A unchanged,
      * SURFACE 42.6 -> 45.4 ms -- profiles/r01z_sweep.log -- so the driver's default carve-out stays) */
@@ -245,9 +246,9 @@ int trace_histogram(const sim5_image_params* p, const sim5_image_out* out, sim5_
     CK(cudaMemsetAsync(d_hist + (size_t)lb * p->n_bins, 0, (size_t)(le - lb) * p->n_bins * sizeof(double), c.stream));
     CK(cudaMemsetAsync(c.d_counter, 0, sizeof(unsigned long long), c.stream));
     CK(cudaMemsetAsync(c.d_stats, 0, sizeof(DevStats), c.stream));
-    int grid = persistent_grid(s5::k_trace_histogram, S5_CTA_THREADS);
+    int grid = persistent_grid(s5::k_trace_histogram, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
     CK(cudaEventRecord(c.ev1, c.stream));
-    s5::k_trace_histogram<<<grid, S5_CTA_THREADS, 0, c.stream>>>(c.d_consts, lb, le, d_hist, c.d_counter, c.d_stats);
+    s5::k_trace_histogram<<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(c.d_consts, lb, le, d_hist, c.d_counter, c.d_stats);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c.ev2, c.stream));
     if (!devptr) CK(cudaMemcpyAsync(out->hist + (size_t)lb * p->n_bins, d_hist + (size_t)lb * p->n_bins, (size_t)(le - lb) * p->n_bins * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
@@ -262,7 +263,7 @@ int trace_histogram(const sim5_image_params* p, const sim5_image_out* out, sim5_
         float ms = 0;
         cudaEventElapsedTime(&ms, c.ev1, c.ev2); stats->kernel_ms = ms;
         cudaEventElapsedTime(&ms, c.ev0, c.ev3); stats->total_ms = ms;
-        stats->kernel_launches = 1; stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = S5_CTA_THREADS;
+        stats->kernel_launches = 1; stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = S5_EQ_THREADS;
     }
     return SIM5_OK;
 }
@@ -698,7 +699,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         cudaEventElapsedTime(&ms, c.ev1, c.ev2); stats->kernel_ms = ms;
         cudaEventElapsedTime(&ms, c.ev0, c.ev3); stats->total_ms = ms;
         stats->kernel_launches = launches;
-        stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = S5_CTA_THREADS;
+        stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = lanes ? S5_CTA_THREADS : S5_EQ_THREADS;
     }
     return SIM5_OK;
 }

@@ -61,8 +61,10 @@ struct AzQueue {
 #endif
 #if defined(S5_EQ_SMEM_GD) && !defined(S5_EQ_FREERUN) && !defined(S5_EQ_NO_STAGE_SYNC)
 #define S5_EQ_DYN_SMEM ((size_t)S5_EQ_THREADS * 200 + 64)     /* per-thread geodesic slots (S5_GD_SLOT_BYTES) */
+#define S5_EQ_DYN_SMEM_ON 1
 #else
 #define S5_EQ_DYN_SMEM ((size_t)0)
+#define S5_EQ_DYN_SMEM_ON 0
 #endif
 #ifndef S5_EQ_TILES_PER_SYNC
 #define S5_EQ_TILES_PER_SYNC 1    /* tiles a warp traces between two CTA barriers of the lockstep tile loop */
@@ -419,7 +421,10 @@ k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigne
 /* ------------------------------------------------------------------ */
 /* mode HISTOGRAM : g-factor transfer function over a (spin, incl) lattice */
 /* ------------------------------------------------------------------ */
-__global__ void __launch_bounds__(S5_CTA_THREADS, 4)       /* the histogram kernel keeps 128-thread CTAs (4 tiles of one image per CTA) */
+/* Same execution shape as k_trace_eqplane: CTAs of S5_EQ_THREADS threads in lockstep, one tile per warp and batch, the staged pixel
+ * routine with its CTA barriers and the geodesic in shared-memory slots (r02f sweep: the former 128-thread free-running kernel
+ * traced 2.5e9 rays/s, 2.8e9 at 64 registers).  A batch never straddles two lattice images, so the staged constants stay valid. */
+__global__ void __launch_bounds__(S5_EQ_THREADS, S5_MIN_CTAS_EQ)
 k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice image */, int img_begin, int img_end,
                   double* __restrict__ hist, unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
 {
@@ -431,12 +436,12 @@ k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice i
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
+    const int wpc = S5_EQ_THREADS / 32;                 /* tiles per batch */
     /* all images share nx, ny */
     const long long nx = gconsts[img_begin].nx;
     const long long npix = (long long)gconsts[img_begin].ny * nx;
     const long long tiles_per_img = (npix + 31) >> 5;
-    /* a CTA works on blocks of 4 consecutive tiles x 4 warps of ONE image so the staged constants stay valid */
-    const long long chunks_per_img = (tiles_per_img + 3) >> 2;
+    const long long chunks_per_img = (tiles_per_img + wpc - 1) / wpc;
     const long long nchunks = chunks_per_img * (long long)(img_end - img_begin);
     __shared__ unsigned long long s_chunk;
 
@@ -447,7 +452,7 @@ k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice i
         long long ch = (long long)s_chunk;
         if (ch >= nchunks) break;
         int img = img_begin + (int)(ch / chunks_per_img);
-        long long t = ((ch % chunks_per_img) << 2) + (threadIdx.x >> 5);
+        long long t = (ch % chunks_per_img) * wpc + (threadIdx.x >> 5);
         if (img != s_img) {
             __syncthreads();
             stage_consts(&c, gconsts + img);
@@ -458,17 +463,28 @@ k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice i
         bool hit = false;
         int bin = -1;
         double w = 0.0;
-        if (t < tiles_per_img && p < npix) {
-            int iy = (int)(p / nx);
-            int ix = (int)(p - (long long)iy * nx);
+        {
+            const bool valid = t < tiles_per_img && p < npix;
+            const long long pc = valid ? p : npix - 1;
+            int iy = (int)(pc / nx);
+            int ix = (int)(pc - (long long)iy * nx);
             PixelOut o;
-            trace_eqplane_pixel(c, ix, iy, &o);
-            atomicAdd(&s_cnt[o.status & 31], 1u);
-            atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);
-            unsigned cls = o.status & 31;
-            if (cls == SIM5_ST_HIT0 || cls == SIM5_ST_HIT1 || cls == SIM5_ST_HIT2) {
-                double tt = (o.g - c.g_min) / (c.g_max - c.g_min) * (double)c.n_bins;
-                if (tt >= 0.0 && tt < (double)c.n_bins) { hit = true; bin = (int)tt; w = o.flux * c.da * c.db; }
+            AzIn z;                                     /* never filled: the lattice images carry no phi (DEFER only keeps the azimuth code out) */
+#if S5_EQ_DYN_SMEM_ON
+            extern __shared__ double s_dyn[];
+            Geodesic* gslot = reinterpret_cast<Geodesic*>(reinterpret_cast<char*>(s_dyn) + (size_t)threadIdx.x * S5_GD_SLOT_BYTES);
+            trace_eqplane_pixel_t<true, false, true, true>(c, ix, iy, &o, &z, gslot);
+#else
+            trace_eqplane_pixel_t<true, false, true>(c, ix, iy, &o, &z);
+#endif
+            if (valid) {
+                atomicAdd(&s_cnt[o.status & 31], 1u);
+                atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);
+                unsigned cls = o.status & 31;
+                if (cls == SIM5_ST_HIT0 || cls == SIM5_ST_HIT1 || cls == SIM5_ST_HIT2) {
+                    double tt = (o.g - c.g_min) / (c.g_max - c.g_min) * (double)c.n_bins;
+                    if (tt >= 0.0 && tt < (double)c.n_bins) { hit = true; bin = (int)tt; w = o.flux * c.da * c.db; }
+                }
             }
         }
         /* warp-aggregated accumulation: one atomic per distinct bin in the warp */
@@ -496,7 +512,10 @@ k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice i
  * three per-hit numbers arrive by shuffle -- so every lane accumulates in registers and there is no per-term reduction.
  * Lanes flush once per kernel: shared-memory atomics per CTA, then one global atomic per CTA and energy. */
 #define S5_SPEC_MAX_E 256
-__global__ void __launch_bounds__(S5_CTA_THREADS, 3)      /* 168 registers: the 8 energies + 8 accumulators per lane live across the pixel routine */
+#ifndef S5_MIN_CTAS_SPEC
+#define S5_MIN_CTAS_SPEC 4
+#endif
+__global__ void __launch_bounds__(S5_CTA_THREADS, S5_MIN_CTAS_SPEC)      /* the 8 energies + 8 accumulators per lane live across the pixel routine; r02f sweep (ms): 3 CTAs/SM (168 regs) 5.41, 4 (128) 5.05, 5 5.50, 6 5.53 */
 k_trace_spectrum(const __grid_constant__ S5ImageConsts gconsts, const double* __restrict__ energies, double* __restrict__ spec,
                  unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
 {

@@ -747,7 +747,8 @@ struct SpecHit { double amp3, ginv, xs; };      /* amp3 = limb factor * BB1 * g^
 S5_HD S5_INL bool spectrum_pixel(const S5ImageConsts& c, int ix, int iy, SpecHit* h, unsigned* status)
 {
     PixelOut o;
-    trace_eqplane_pixel_t<false>(c, ix, iy, &o, nullptr);      /* c.mode == POLARIZED: g and mu_e from the Keplerian emitter frame */
+    AzIn z;                                                    /* never filled: no phi is requested (DEFER only keeps the azimuth code out of the kernel) */
+    trace_eqplane_pixel_t<true>(c, ix, iy, &o, &z);            /* c.mode == POLARIZED: g and mu_e from the Keplerian emitter frame */
     *status = o.status;
     unsigned cls = o.status & 31;
     if (!(cls == SIM5_ST_HIT0 || cls == SIM5_ST_HIT1 || cls == SIM5_ST_HIT2)) return false;

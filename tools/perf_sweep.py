@@ -23,7 +23,10 @@ def t(p, reps=3):
         _, st = api.trace_image(p, planes)
         if st.kernel_ms < best:
             best = st.kernel_ms
-            res["_phases"] = [round(v, 3) for v in api.last_phase_ms()[0]]
+            try:
+                res["_phases"] = [round(v, 3) for v in api.last_phase_ms()[0]]
+            except api.Sim5Error:
+                res["_phases"] = []
     return best, st
 p = abi.default_params(2); ms, st = t(p); res["cfg2_phi_ms"] = round(ms,3); res["cfg2_phases_ms"] = res.pop("_phases"); res["cfg2_phi_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
 if os.environ.get("SWEEP_EXACT"):
@@ -34,6 +37,8 @@ p = abi.default_params(3); ms, st = t(p); res["cfg3_ms"] = round(ms,3); res["cfg
 p = abi.default_params(4, 512); ms, st = t(p, 1); res["cfg4_512_ms"] = round(ms,2); res["cfg4_steps_s"] = "%%.3e" %% (st.total_steps/ms*1e3)
 if os.environ.get("SWEEP_NOREFILL"):
     p.flags = abi.FLAG_NO_REFILL; ms, st = t(p, 1); res["cfg4_512_norefill_ms"] = round(ms,2)
+p = abi.default_params(5, 512); p.n_spin, p.n_incl = 8, 4; ms, st = t(p, 2); res["cfg5_8x4x512_ms"] = round(ms,2); res["cfg5_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
+p = abi.default_params(6); ms, st = t(p, 2); res["cfg6_ms"] = round(ms,3)
 p = abi.default_params(7); ms, st = t(p, 2); res["cfg7_ms"] = round(ms,2)
 p.flags |= abi.FLAG_NO_REFILL; ms, st = t(p, 1); res["cfg7_norefill_ms"] = round(ms,2)
 if os.environ.get("SWEEP_CHUNKS"):
