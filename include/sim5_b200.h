@@ -256,6 +256,9 @@ int  sim5_trace_image(const sim5_image_params* p, const sim5_image_out* out, sim
  * ms[2] the bit-faithful redo passes (default; normally empty lists) or the bit-faithful RC kernel; items (may be NULL):
  * [0] RR and [1] RC disk hits integrated.  Returns the number of kernels the call launched (1, 3 or 4), <0 on error. */
 int  sim5_last_phase_ms(double* ms, int n, int64_t* items);
+/* the same times for the image call `back` calls ago (0 = most recent, the last 63 are kept): a caller that enqueues a train of
+ * SIM5_FLAG_ASYNC calls reads every call's per-kernel times afterwards instead of synchronising after each */
+int  sim5_phase_history(int back, double* ms, int n);
 
 /* FP64 DFMA-chain microbenchmark: returns measured TFLOP/s (2 flop per DFMA) of the device, <0 on error.
  * This is the roofline denominator for the compute-bound FP64 path (MEASURED_PEAKS.json has no FP64 entry). */

@@ -61,6 +61,8 @@ def lib():
         L.sim5_fp64_peak_tflops.restype = C.c_double
         L.sim5_last_phase_ms.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int64)]
         L.sim5_last_phase_ms.restype = C.c_int
+        L.sim5_phase_history.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
+        L.sim5_phase_history.restype = C.c_int
         dp = C.POINTER(C.c_double)
         L.sim5_batch_rf.argtypes = [C.c_int64, dp, dp, dp, dp]
         L.sim5_batch_rd.argtypes = [C.c_int64, dp, dp, dp, dp]
@@ -289,6 +291,15 @@ def last_phase_ms():
     if n < 0:
         raise Sim5Error("sim5_last_phase_ms failed: " + last_error())
     return [buf[i] for i in range(min(n, 3))], (items[0], items[1]), n
+
+
+def phase_history(back):
+    """Per-kernel device times (ms) of the image call `back` calls ago (0 = most recent) and the number of kernels it launched."""
+    buf = (C.c_double * 3)()
+    n = lib().sim5_phase_history(back, buf, 3)
+    if n < 0:
+        raise Sim5Error("sim5_phase_history failed: " + last_error())
+    return [buf[i] for i in range(min(n, 3))], n
 
 
 def write_text_dump(path, planes, p):

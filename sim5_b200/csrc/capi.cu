@@ -52,6 +52,12 @@ struct Context {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;      /* the RC azimuth chain runs on aux_stream beside the RR chain */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     cudaEvent_t evp[3] = {nullptr, nullptr, nullptr};   /* phase boundaries of the last image call: after phase A, after azimuth RR, after azimuth RC */
+    /* history of the phase events of the last S5_RING image calls ({ev1, evp[0..2], ev2} alias the current slot), so a caller that
+     * enqueues many SIM5_FLAG_ASYNC calls back to back can read every call's per-kernel times afterwards without a sync per call */
+#define S5_RING 64
+    cudaEvent_t ring[S5_RING][5] = {{nullptr}};
+    int ring_phases[S5_RING] = {0};
+    int ring_pos = 0;
     cudaEvent_t ev_chunk[S5_MAX_CHUNKS] = {nullptr};      /* chunk k traced -> its device->host copy may start */
     cudaEvent_t ev_copy_done = nullptr;
     long long chunk_rays = 0;             /* 0: S5_CHUNK_RAYS */
@@ -127,6 +133,10 @@ int ensure_init(int device)
     CK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     CK(cudaEventCreate(&c.ev0)); CK(cudaEventCreate(&c.ev1)); CK(cudaEventCreate(&c.ev2)); CK(cudaEventCreate(&c.ev3));
     for (int i = 0; i < 3; i++) CK(cudaEventCreate(&c.evp[i]));
+    c.ring[0][0] = c.ev1; c.ring[0][1] = c.evp[0]; c.ring[0][2] = c.evp[1]; c.ring[0][3] = c.evp[2]; c.ring[0][4] = c.ev2;
+    for (int k = 1; k < S5_RING; k++) for (int i = 0; i < 5; i++) CK(cudaEventCreate(&c.ring[k][i]));
+    c.ring_pos = 0;
+    for (int k = 0; k < S5_RING; k++) c.ring_phases[k] = 0;
     for (int i = 0; i < S5_MAX_CHUNKS; i++) CK(cudaEventCreateWithFlags(&c.ev_chunk[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.ev_copy_done, cudaEventDisableTiming));
     CK(cudaHostAlloc((void**)&c.h_scr, sizeof(Scratch), cudaHostAllocMapped));
@@ -347,8 +357,8 @@ extern "C" void sim5_gpu_shutdown(void)
     if (c.azq_redo.p) cudaFree(c.azq_redo.p); c.azq_redo = Plane();
     for (int i = 0; i < 8; i++) { if (c.batch[i]) cudaFree(c.batch[i]); c.batch[i] = nullptr; c.batch_bytes[i] = 0; }
     cudaFreeHost(c.h_scr); cudaFreeHost(c.h_consts); cudaFree(c.d_consts); cudaFree(c.d_counter); cudaFree(c.d_stats); cudaFreeHost(c.h_stats);
-    cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1); cudaEventDestroy(c.ev2); cudaEventDestroy(c.ev3);
-    for (int i = 0; i < 3; i++) cudaEventDestroy(c.evp[i]);
+    cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev3);
+    for (int k = 0; k < S5_RING; k++) for (int i = 0; i < 5; i++) cudaEventDestroy(c.ring[k][i]);
     for (int i = 0; i < S5_MAX_CHUNKS; i++) cudaEventDestroy(c.ev_chunk[i]);
     cudaEventDestroy(c.ev_copy_done);
     cudaStreamDestroy(c.own_stream); cudaStreamDestroy(c.copy_stream); cudaStreamDestroy(c.aux_stream);
@@ -570,6 +580,10 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         q.f = (double*)c.azq_f.p; q.key = (unsigned long long*)c.azq_key.p; q.count = c.d_counter + 4; q.cap = (long long)qpix;
         q.redo = (unsigned*)c.azq_redo.p;
     }
+    c.ring_pos = (c.ring_pos + 1) % S5_RING;
+    c.ev1 = c.ring[c.ring_pos][0]; c.evp[0] = c.ring[c.ring_pos][1]; c.evp[1] = c.ring[c.ring_pos][2]; c.evp[2] = c.ring[c.ring_pos][3];
+    c.ev2 = c.ring[c.ring_pos][4];
+    c.ring_phases[c.ring_pos] = 0;
     CK(cudaEventRecord(c.ev0, c.stream));
     CK(cudaMemsetAsync(c.d_stats, 0, sizeof(DevStats), c.stream));
     int grid = 0, launches = 0;
@@ -679,6 +693,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         }
     }
     c.phases = (nchunks == 1) ? launches : 0;      /* per-kernel times are defined for single-chunk calls only */
+    c.ring_phases[c.ring_pos] = c.phases;
     if (devptr || npix == 0) CK(cudaEventRecord(c.ev2, c.stream));
     if (async) return SIM5_OK;
     if (nchunks > 1) {
@@ -722,6 +737,24 @@ extern "C" int sim5_last_phase_ms(double* ms, int n, int64_t* items)
         items[0] = (int64_t)cnt[0]; items[1] = (int64_t)cnt[1];
     }
     return c.phases;
+}
+
+/* per-kernel times of the image call `back` calls ago (0 = the most recent; up to S5_RING - 1 calls are kept): same layout as
+ * sim5_last_phase_ms.  Waits for that call only.  Lets a caller time a train of SIM5_FLAG_ASYNC calls without a sync per call. */
+extern "C" int sim5_phase_history(int back, double* ms, int n)
+{
+    Context& c = g_ctx;
+    if (!c.ready || !ms || n < 1 || back < 0 || back >= S5_RING) { set_error("sim5_phase_history: bad arguments"); return SIM5_ERR_BAD_PARAM; }
+    int pos = ((c.ring_pos - back) % S5_RING + S5_RING) % S5_RING;
+    int phases = c.ring_phases[pos];
+    if (phases < 1) { set_error("sim5_phase_history: no image call recorded in that slot"); return SIM5_ERR_BAD_PARAM; }
+    cudaEvent_t* e = c.ring[pos];
+    CK(cudaEventSynchronize(e[4]));
+    float t = 0;
+    for (int i = 0; i < n; i++) ms[i] = 0.0;
+    if (phases == 1) { CK(cudaEventElapsedTime(&t, e[0], e[4])); ms[0] = t; return 1; }
+    for (int i = 0; i < 3 && i < n; i++) { CK(cudaEventElapsedTime(&t, e[i], e[i + 1])); ms[i] = t; }
+    return phases;
 }
 
 /* ------------------------------------------------------------------ */

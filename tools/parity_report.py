@@ -32,12 +32,16 @@ def main():
     args = ap.parse_args()
     assert H.have_ref(), "oracle/_ref/libsim5ref.so did not travel"
     api.init(0)
-    sizes = {1: 512, 2: 4096, 3: 2048, 4: 1024}
+    sizes = {1: 512, 2: 4096, 3: 2048, 4: 1024, 7: 1024, "2+delay": 1024}
     if args.quick:
         sizes = {k: max(v // 4, 64) for k, v in sizes.items()}
     report = {"checker": "oracle/_ref (unmodified reference, %d host threads)" % H.load_ref().ref_max_threads(), "configs": {}}
     for cfg, n in sizes.items():
-        p = abi.default_params(cfg, n)
+        if cfg == "2+delay":             # N2: the travel-time plane on the camera of config 2
+            p = abi.default_params(2, n)
+            p.outputs = abi.OUT_R | abi.OUT_DELAY | abi.OUT_STATUS
+        else:
+            p = abi.default_params(cfg, n)
         if cfg == 3:
             p.outputs |= abi.OUT_MUE
         if cfg == 4:
@@ -50,7 +54,7 @@ def main():
                  "status_mismatches": int(np.sum(got["status"] != ref["status"])),
                  "class_count_equal": list(st.class_count) == list(rst.class_count),
                  "gtype_count_equal": list(st.gtype_count) == list(rst.gtype_count), "planes": {}}
-        if cfg == 4:
+        if cfg in (4, 7):
             entry["step_count_mismatches"] = int(np.sum(got["steps"] != ref["steps"]))
             entry["total_steps"] = int(st.total_steps)
         for k in got.arrays:
@@ -60,8 +64,8 @@ def main():
             s["tol"] = H.TOL.get(k)
             s["within_tol"] = (s["tol"] is None) or (s["max"] <= s["tol"])
             entry["planes"][k] = s
-        report["configs"]["cfg%d" % cfg] = entry
-        print("cfg%d %s: status mismatches %d | %s" % (cfg, entry["size"], entry["status_mismatches"],
+        report["configs"]["cfg%s" % cfg] = entry
+        print("cfg%s %s: status mismatches %d | %s" % (cfg, entry["size"], entry["status_mismatches"],
               " ".join("%s max %.2e p99.9 %.2e exact %.4f" % (k, v["max"], v["p999"], v["exact"]) for k, v in entry["planes"].items())), flush=True)
 
     # cfg 5: sub-lattice of full-size images
@@ -90,6 +94,17 @@ def main():
         print("cfg5 image (spin %d, incl %d): max rel err per bin %.2e, max |d|/peak %.2e" % (js, ki, s["max"], worst), flush=True)
     report["configs"]["cfg5"] = {"size": "%dx%d x %d lattice images of 2048" % (p.nx, p.ny, len(picks)), "max_abs_over_peak": worst,
                                  "tol": 1e-7, "within_tol": worst <= 1e-7, "gpu_call_s": t_gpu, "cpu_ref_s": t_cpu}
+    # N3: the thermal spectrum of the preset (2048^2 x 128 energies)
+    p = abi.default_params(6)
+    if args.quick:
+        p.nx = p.ny = 512
+    hp = api.HostPlanes(p, pinned=False)
+    t0 = time.time(); api.trace_image(p, hp); t_gpu = time.time() - t0
+    ref, t_cpu = H.run_spectrum("ref", p)
+    s = H.err_summary(hp["spectrum"], ref)
+    print("spectrum %dx%d x %d energies: max rel err %.2e p99.9 %.2e" % (p.nx, p.ny, p.n_energy, s["max"], s["p999"]), flush=True)
+    report["configs"]["spectrum"] = {"size": "%dx%d x %d energies" % (p.nx, p.ny, p.n_energy), "planes": {"spectrum": dict(s, tol=1e-7, within_tol=s["max"] <= 1e-7)},
+                                     "gpu_call_s": t_gpu, "cpu_ref_s": t_cpu}
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as fh:
         json.dump(report, fh, indent=1)
