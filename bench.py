@@ -35,8 +35,9 @@ UNIT = "rays/s"
 F_ALG_PHI = 16.8e3        # flop per ray, (r, phi, g, F): SURVEY.md 8(d) non-redundant algorithm, / = 15, sqrt = 13 flop
 F_ALG_TRACE = 3.7e3       # of which phase A (roots, crossing, r, g, F): 3 rf + 1 sncndn + roots + glue, per ray
 F_ALG_AZ_RR = 13.1e3      # phase B per RR disk hit, the reference's non-redundant algorithm (bit-faithful kernels): 3 rf + 6 rj + 2 sncndn + glue
-F_ALG_AZ_FAST = 3.3e3     # phase B per RR disk hit, tolerance-mode algorithm (the default): 4 shared duplication sequences x 4.18 steps,
-                          # 23.5 R_C series, 6 R_J + 3 R_F tails, glue -- op count of tests/hostsim -DS5_COUNT_ITERS, DESIGN.md section 3
+F_ALG_AZ_FAST = 2.9e3     # phase B per RR disk hit, tolerance-mode algorithm (the default): 3 shared duplication sequences x 3.80 steps,
+                          # 18.4 R_C series, 5 R_J + 3 R_F tails, one AGM complete Pi, glue -- counted by tools/count_azimuth_ops.py on a host
+                          # build with -DS5_COUNT_ITERS; 3.3e3 before the complete Pi went from duplication to AGM
 BYTES_PER_RAY = 4 * 8 + 1
 SAMPLE_N = 1024           # CPU sample: the same camera at 1024x1024 (1/16 of the rays of the 4096^2 image)
 
@@ -344,7 +345,7 @@ def run_ours(args):
                          "step": {"achieved": achieved_step, "frac": achieved_step / peak_tf if peak_tf else None,
                                   "flop_per_ray": flop_step / (rays_step / world), "kernels_ms_total": kernel_ms,
                                   "reference_algorithm_equiv_tflops": F_ALG_PHI * (rays_step / world) / (kernel_ms * 1e-3) / 1e12,
-                                  "note": "achieved counts the flops of the algorithm actually run (tolerance-mode azimuth: 3.3 kflop per RR hit); "
+                                  "note": "achieved counts the flops of the algorithm actually run (tolerance-mode azimuth: 2.9 kflop per RR hit); "
                                           "reference_algorithm_equiv uses SURVEY.md 8(d)'s 16.8 kflop per ray of the reference's non-redundant algorithm"},
                          "hbm_written_bytes_per_launch": (rays_step // world) * BYTES_PER_RAY},
             "cpu_baseline": cpu,

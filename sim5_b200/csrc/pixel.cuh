@@ -357,8 +357,12 @@ S5_HD S5_MID double azimuth_fast_polar(const AzIn& z, bool* ok, float* mag)
     double pu = 1.0 + ns2;
     bool gp = (z.cos_i > 0.0) && (cu2 < 1.0) && (tm < 1.0) && !(tn == 1.0) && hi_domain(0.0, qc, 1.0) && hi_domain_p(pc) && hi_domain(cu2, qu, 1.0) && hi_domain_p(pu);
     if (!gp) { qc = pc = cu2 = qu = pu = 1.0; good = false; }
+#if defined(S5_POLAR_DUPLICATION)
     double rfK = (tm == z.mm) ? z.K_mm : rf_hi(0.0, qc, 1.0);
     double comp = rfK + tn * rj_hi(0.0, qc, 1.0, pc) * (1.0 / 3.0);
+#else
+    double comp = cel_pi_hi(qc, pc);                 /* complete Pi(tn | tm): AGM instead of a duplication sequence */
+#endif
     double Fu, Ju;
     rfj_hi<1, true>(cu2, qu, 1.0, &pu, &Fu, &Ju);
     double vu = ff::sqrt_ap0(1.0 - cu2) * (Fu - ns2 * Ju * (1.0 / 3.0));

@@ -47,6 +47,7 @@ void hs_batch_rc(long n, const double* x, const double* y, double* o) { for (lon
 void hs_batch_rj(long n, const double* x, const double* y, const double* z, const double* p, double* o) { for (long i = 0; i < n; i++) o[i] = rj(x[i], y[i], z[i], p[i]); }
 void hs_batch_rf_hi(long n, const double* x, const double* y, const double* z, double* o) { for (long i = 0; i < n; i++) o[i] = hi_domain(x[i], y[i], z[i]) ? rf_hi(x[i], y[i], z[i]) : NAN; }
 void hs_batch_rj_hi(long n, const double* x, const double* y, const double* z, const double* p, double* o) { for (long i = 0; i < n; i++) o[i] = (hi_domain(x[i], y[i], z[i]) && hi_domain_p(p[i])) ? rj_hi(x[i], y[i], z[i], p[i]) : NAN; }
+void hs_batch_cel_pi(long n, const double* qc, const double* pc, double* o) { for (long i = 0; i < n; i++) o[i] = cel_pi_hi(qc[i], pc[i]); }
 void hs_batch_sncndn(long n, const double* u, const double* m, double* sn, double* cn, double* dn) { for (long i = 0; i < n; i++) jacobi_sncndn(u[i], m[i], &sn[i], &cn[i], &dn[i]); }
 
 void hs_batch_integral(int op, long n, const double* v0, const double* v1, const double* v2, const double* v3, const double* v4,

@@ -56,6 +56,43 @@ def test_against_bit_faithful_restatement(hs):
     assert np.all(np.isnan(bad))
 
 
+def _pi_args(n, seed):
+    rng = np.random.default_rng(seed)
+    m = np.concatenate([rng.uniform(1e-6, 0.999999, n // 2), 1.0 - 10.0 ** rng.uniform(-9, -1, n // 2)])
+    nn = np.concatenate([-10.0 ** rng.uniform(-6, 5, n // 2), rng.uniform(-1.0, 0.999, n // 2)])
+    rng.shuffle(nn)
+    return m, nn
+
+
+def test_complete_pi_by_agm_against_mpmath(hs):
+    """cel_pi_hi (Bulirsch's AGM) against the mathematical value of the complete Pi(n | m), over the moduli and characteristics
+    the polar azimuth produces (n <= 0, down to -1e5) and beyond (0 < n < 1)."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    m, nn = _pi_args(2000, 5)
+    got = H.batch_call(hs, "hs_batch_cel_pi", [1.0 - m, 1.0 - nn])
+    worst = 0.0
+    for i in range(m.size):
+        t = mp.ellippi(mp.mpf(float(1.0 - (1.0 - nn[i]))), mp.mpf(float(1.0 - (1.0 - m[i]))))     # the doubles the routine saw
+        worst = max(worst, float(abs((mp.mpf(float(got[i])) - t) / t)))
+    assert worst < 2e-15, worst
+
+
+@pytest.mark.skipif(not H.have_oracle(), reason="oracle/libsim5oracle.so not built")
+def test_complete_pi_by_agm_against_carlson(hs):
+    """... and against R_F(0, qc, 1) + n R_J(0, qc, 1, pc) / 3 of the bit-faithful restatement (the way sim5elliptic.c:365-378
+    spells the complete Pi).  For n << -1 that sum cancels (R_F ~ -n R_J / 3) and the reference's own value loses digits, so the
+    comparison is relative to the size of its terms."""
+    lib = H.load_oracle()
+    m, nn = _pi_args(200000, 6)
+    qc, pc = 1.0 - m, 1.0 - nn
+    z0, one = np.zeros(m.size), np.ones(m.size)
+    f = H.batch_call(lib, "orc_batch_rf", [z0, qc, one])
+    j = nn * H.batch_call(lib, "orc_batch_rj", [z0, qc, one, pc]) / 3.0
+    got = H.batch_call(hs, "hs_batch_cel_pi", [qc, pc])
+    assert np.max(np.abs(got - (f + j)) / (np.abs(f) + np.abs(j))) < 4e-15
+
+
 @pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built")
 def test_default_and_exact_azimuth_against_reference():
     """phi of the default (tolerance-mode) path stays two orders of magnitude inside the 1e-9 bar; the exact flag restores
