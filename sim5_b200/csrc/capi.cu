@@ -606,11 +606,11 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         }
         CK(cudaMemsetAsync(c.d_counter, 0, 8 * sizeof(unsigned long long), c.stream));
         if (p->mode == SIM5_MODE_STEPWISE) {
-            grid = persistent_grid(s5::k_trace_lanes<s5::StepwiseProg>, S5_CTA_THREADS);
-            s5::k_trace_lanes<s5::StepwiseProg><<<grid, S5_CTA_THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
+            grid = persistent_grid(s5::k_trace_lanes<s5::StepwiseProg>, s5::StepwiseProg::THREADS);
+            s5::k_trace_lanes<s5::StepwiseProg><<<grid, s5::StepwiseProg::THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
         } else if (p->mode == SIM5_MODE_SURFACE) {
-            grid = persistent_grid(s5::k_trace_lanes<s5::SurfaceProg>, S5_CTA_THREADS);
-            s5::k_trace_lanes<s5::SurfaceProg><<<grid, S5_CTA_THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
+            grid = persistent_grid(s5::k_trace_lanes<s5::SurfaceProg>, s5::SurfaceProg::THREADS);
+            s5::k_trace_lanes<s5::SurfaceProg><<<grid, s5::SurfaceProg::THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
         } else if (two_phase) {
             if (p->outputs & SIM5_OUT_DELAY) {
                 grid = persistent_grid(s5::k_trace_eqplane<true, true>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
@@ -622,6 +622,10 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
             if (ch == 0) CK(cudaEventRecord(c.evp[0], c.stream));
             int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_AZ_THREADS);
             int g_rc = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RC>, S5_AZ_THREADS);
+            /* the redo passes are one latency-bound wave (~0.1 ms whatever the number of items).  Tried and dropped (profiles/r02y_redo_sweep.log):
+             * smaller CTAs (64 / 128 threads: more serial passes, 0.31 / 0.21 ms on an eighth of the image against 0.24) and an even deal of the
+             * items over all CTAs without barriers (0.14 / 0.22 ms against 0.10 / 0.24): the wave is bound by walking ~120 KB of code, not by the pipe */
+            const int redo_threads = S5_AZ_THREADS;
             if (p->flags & SIM5_FLAG_EXACT_AZIMUTH) {
                 s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 1, 0);
                 if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
@@ -639,15 +643,15 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                 s5::k_azimuth_fast<1><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
                 g_f = persistent_grid(s5::k_azimuth_fast<2>, S5_AZF_THREADS);
                 s5::k_azimuth_fast<2><<<g_f, S5_AZF_THREADS, 0, c.aux_stream>>>(cc, q, dd.phi);
-                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.aux_stream>>>(cc, q, dd.phi, c.d_counter + 2, 1);
+                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, c.d_counter + 2, 1);
                 CK(cudaEventRecord(c.ev_join, c.aux_stream));
                 launches += 1;
 #endif
                 if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
                 /* the redo list: items outside the fast routines' domain or flagged by the conditioning guard (~0.3 %) */
-                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 1, 1);
+                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, redo_threads, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 1, 1);
 #if defined(S5_AZF_MERGED)
-                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 2, 1);
+                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, redo_threads, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 2, 1);
 #else
                 CK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
 #endif
@@ -714,7 +718,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         cudaEventElapsedTime(&ms, c.ev1, c.ev2); stats->kernel_ms = ms;
         cudaEventElapsedTime(&ms, c.ev0, c.ev3); stats->total_ms = ms;
         stats->kernel_launches = launches;
-        stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = lanes ? S5_CTA_THREADS : S5_EQ_THREADS;
+        stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = (p->mode == SIM5_MODE_SURFACE) ? s5::SurfaceProg::THREADS : lanes ? S5_CTA_THREADS : S5_EQ_THREADS;
     }
     return SIM5_OK;
 }

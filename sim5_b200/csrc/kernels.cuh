@@ -70,7 +70,8 @@ struct AzQueue {
 #define S5_EQ_TILES_PER_SYNC 1    /* tiles a warp traces between two CTA barriers of the lockstep tile loop */
 #endif
 #ifndef S5_MIN_CTAS_STEP
-#define S5_MIN_CTAS_STEP 1
+#define S5_MIN_CTAS_STEP 3        /* stepwise lane kernel: 1 CTA/SM (186 regs, 8 warps/SM) 153.7 ms, 3 (168 regs, 12 warps) 139.5, 4 (128) 141.2, 5 (96) 156.6
+                                     (cfg 4 at 512^2, profiles/r02w_step_sweep.log) */
 #endif
 #ifndef S5_MIN_CTAS_AZ
 #define S5_MIN_CTAS_AZ 4
@@ -336,7 +337,7 @@ k_azimuth_fast(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double*
 #define S5_REFILL_MIN 4
 
 template <class PROG>
-__global__ void __launch_bounds__(S5_CTA_THREADS, PROG::MIN_CTAS)
+__global__ void __launch_bounds__(PROG::THREADS, PROG::MIN_CTAS)
 k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigned long long* __restrict__ ray_counter, DevStats* __restrict__ gstats)
 {
     __shared__ S5ImageConsts c;
@@ -357,6 +358,59 @@ k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigne
     bool drained = false;          /* queue exhausted (warp-uniform) */
     unsigned long long my_steps = 0;
 
+    if (PROG::BATCH > 0) {
+        /* CTA-batch variant: the CTA takes blockDim.x consecutive pixels, all lanes start together and the CTA passes a barrier every
+         * PROG::BATCH steps until its last ray has finished -- the warps then share instruction-cache lines (the step routine runs from
+         * L2 otherwise) at the price of waiting for the slowest ray of the batch.  For programs whose neighbouring rays take similar
+         * numbers of steps. */
+        __shared__ unsigned long long s_base;
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_base = atomicAdd(ray_counter, (unsigned long long)blockDim.x);
+            __syncthreads();
+            const long long base = (long long)s_base;
+            if (base >= npix) break;
+            const long long p = base + threadIdx.x;
+            live = false;
+            if (p < npix) {
+                int lr = (int)(p / nx);
+                int ix = (int)(p - (long long)lr * nx);
+                int iy = s5_local_to_image_row(&c, lr);
+                PixelOut o;
+                mypix = p;
+                if (PROG::start(c, ix, iy, &s, &o)) {
+                    live = true;
+                } else {
+                    size_t i = out.compact ? (size_t)p : (size_t)iy * (size_t)nx + (size_t)ix;
+                    store_pixel(out, c.outputs, i, o);
+                    atomicAdd(&s_cnt[o.status & 31], 1u);
+                    atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);
+                }
+            }
+            for (;;) {
+                #pragma unroll 1
+                for (int it = 0; it < (PROG::BATCH > 0 ? PROG::BATCH : 1); it++) {
+                    if (live) {
+                        int cls = PROG::step(c, &s);
+                        if (cls) {
+                            PixelOut o;
+                            PROG::finish(c, &s, cls, &o);
+                            int lr = (int)(mypix / nx);
+                            int ix = (int)(mypix - (long long)lr * nx);
+                            int iy = s5_local_to_image_row(&c, lr);
+                            size_t i = out.compact ? (size_t)mypix : (size_t)iy * (size_t)nx + (size_t)ix;
+                            store_pixel(out, c.outputs, i, o);
+                            atomicAdd(&s_cnt[o.status & 31], 1u);
+                            atomicAdd(&s_cnt[32 + ((o.status >> 5) & 7)], 1u);
+                            my_steps += (unsigned long long)o.steps;
+                            live = false;
+                        }
+                    }
+                }
+                if (!__syncthreads_or(live ? 1 : 0)) break;
+            }
+        }
+    } else
     for (;;) {
         unsigned idle = __ballot_sync(0xffffffffu, !live);
         if (idle == 0xffffffffu && drained) break;

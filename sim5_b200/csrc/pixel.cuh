@@ -1017,34 +1017,54 @@ S5_HD S5_MID int surface_step(const S5ImageConsts& c, SurfRay* s)
 }
 
 /* the two ray programs of the lane-refill kernel (kernels.cuh:k_trace_lanes) */
+#ifndef S5_STEP_THREADS
+#define S5_STEP_THREADS 128
+#endif
+#ifndef S5_STEP_BATCH
+#define S5_STEP_BATCH 0           /* 0: free-running warps with lane refill (steps per ray vary by an order of magnitude) */
+#endif
 #ifndef S5_MIN_CTAS_STEP
-#define S5_MIN_CTAS_STEP 1
+#define S5_MIN_CTAS_STEP 3
 #endif
 struct StepwiseProg {
     typedef StepRay State;
     static const int REFILL_MIN = 4;              /* idle lanes of a warp that trigger a refill (S5_REFILL_MIN) */
     static const int MIN_CTAS = S5_MIN_CTAS_STEP; /* resident 128-thread CTAs per SM the kernel is compiled for */
+    static const int THREADS = S5_STEP_THREADS;
+    static const int BATCH = S5_STEP_BATCH;
     static S5_HD S5_INL bool start(const S5ImageConsts& c, int ix, int iy, State* s, PixelOut* o) { return stepwise_start(c, ix, iy, s, o); }
     static S5_HD S5_INL int step(const S5ImageConsts& c, State* s) { return stepwise_step(c, s); }
     static S5_HD S5_INL void finish(const S5ImageConsts& c, State* s, int cls, PixelOut* o) { stepwise_finish(c, s, cls, o); }
 };
-/* profiles/r01x_sweep.log (1024^2 preset, ms): a ray's start (init_inf, P_int) costs ~30 sub-steps, so refilling a few idle lanes
- * while the rest of the warp waits loses more than it gains -- refill at 4 / 8 / 16 / 24 idle lanes 61.9 / 60.1 / 57.9 / 56.4, only when
- * the whole warp is idle 56.0 (neighbouring pixels take similar numbers of sub-steps).  Occupancy is what pays: 1 CTA/SM (226 regs)
- * 56.0, 2: 56.7, 3 (168): 47.6, 4 (128): 44.1, 5 (96 regs, 20 warps/SM): 42.7, 6 (80): 44.2, 8 (64): 46.5 */
+/* Launch shape of the SURFACE lane kernel (1024^2 preset, ms; profiles/r01x_sweep.log, r02z_surf_sweep.log).  Lane refill does not pay
+ * here: a ray's start (init_inf, P_int) costs ~30 sub-steps, so refilling a few idle lanes while the rest of the warp waits loses more
+ * than it gains -- refill at 4 / 8 / 16 / 24 idle lanes 61.9 / 60.1 / 57.9 / 56.4, only when the whole warp is idle 56.0 (neighbouring
+ * pixels take similar numbers of sub-steps).  Occupancy pays: 1 CTA/SM of 128 threads (226 regs) 56.0, 3 (168) 47.6, 4 (128) 44.1,
+ * 5 (96 regs, 20 warps/SM) 42.7, 6 (80) 44.2, 8 (64) 46.5.  And so does the plain CTA-batch loop (k_trace_lanes, PROG::BATCH: the CTA
+ * takes blockDim.x consecutive pixels, starts them together and steps until the last one is done -- no refill bookkeeping in the
+ * hot loop): 128 x 5 CTAs 34.0, 64 x 10 33.0, 32 x 20 33.7, 128 x 4 37.1, 128 x 6 36.6, 192 x 4 37.0, 256 x 3 37.9, 384 x 2 39.4, 512 x 1 45.5,
+ * 640 x 1 41.5 (the larger the batch, the longer it waits for its slowest ray). */
 #ifndef S5_SURF_REFILL_MIN
 #define S5_SURF_REFILL_MIN 32
 #endif
 #ifndef S5_SURF_MIN_CTAS
-#define S5_SURF_MIN_CTAS 5
+#define S5_SURF_MIN_CTAS 10
+#endif
+#ifndef S5_SURF_THREADS
+#define S5_SURF_THREADS 64
+#endif
+#ifndef S5_SURF_BATCH
+#define S5_SURF_BATCH 1           /* > 0: CTA-batch variant of the lane kernel with a barrier every S5_SURF_BATCH sub-steps; 0: warps with lane refill */
 #endif
 #ifndef S5_MIN_CTAS_STEP
-#define S5_MIN_CTAS_STEP 1
+#define S5_MIN_CTAS_STEP 3
 #endif
 struct SurfaceProg {
     typedef SurfRay State;
     static const int REFILL_MIN = S5_SURF_REFILL_MIN;
     static const int MIN_CTAS = S5_SURF_MIN_CTAS;
+    static const int THREADS = S5_SURF_THREADS;
+    static const int BATCH = S5_SURF_BATCH;
     static S5_HD S5_INL bool start(const S5ImageConsts& c, int ix, int iy, State* s, PixelOut* o) { return surface_start(c, ix, iy, s, o); }
     /* the kernel's protocol is "0 while live"; SIM5_ST_HIT0 is 0, so the class travels with bit 8 set */
     static S5_HD S5_INL int step(const S5ImageConsts& c, State* s) { int r = surface_step(c, s); return r < 0 ? 0 : (r | 0x100); }
