@@ -94,3 +94,27 @@ def test_gpu_against_second_golden_and_no_refill(gpu_api):
     got2, _ = gpu_api.trace_image(p, gpu_api.HostPlanes(p, pinned=True))
     for k in got.arrays:
         assert np.array_equal(got[k], got2[k], equal_nan=True), k
+
+
+@pytest.mark.gpu
+def test_gpu_row_ranges_and_split_compose(gpu_api):
+    """Row ranges and the interleaved multi-GPU split of a SURFACE image give exactly the rows of the full image."""
+    p = abi.default_params(7, 64)
+    full, _ = gpu_api.trace_image(p, gpu_api.HostPlanes(p, pinned=True))
+    part = gpu_api.HostPlanes(p, pinned=True)
+    for k in part.arrays:
+        part[k][...] = 0
+    for rb, re in ((0, 23), (23, 24), (24, 64)):
+        p.row_begin, p.row_end = rb, re
+        gpu_api.trace_image(p, part)
+    for k in full.arrays:
+        assert np.array_equal(full[k], part[k], equal_nan=True), k
+    p = abi.default_params(7, 64)
+    inter = gpu_api.HostPlanes(p, pinned=True)
+    for k in inter.arrays:
+        inter[k][...] = 0
+    for idx in range(2):
+        p.split_count, p.split_index, p.split_rows = 2, idx, 8
+        gpu_api.trace_image(p, inter)
+    for k in full.arrays:
+        assert np.array_equal(full[k], inter[k], equal_nan=True), k
