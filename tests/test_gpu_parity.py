@@ -315,3 +315,30 @@ def test_full_index_split_writes_into_one_image(gpu_api):
     L = gpu_api.lib()
     assert L.sim5_ipc_export(None, None) == abi.ERR_BAD_PARAM
     assert not L.sim5_ipc_import(None)
+
+
+def test_async_train_and_phase_history(gpu_api):
+    """A train of SIM5_FLAG_ASYNC calls enqueued back to back (what bench.py times): sim5_synchronize() completes them, the planes hold
+    the image of a synchronous call, and sim5_phase_history() returns the per-kernel times of each call of the train."""
+    p = abi.default_params(2, 256)
+    full, _ = _gpu_planes(gpu_api, p)
+    img = gpu_api.DevicePlanes(p)
+    L = gpu_api.lib()
+    try:
+        q = abi.default_params(2, 256)
+        q.flags = abi.FLAG_DEVICE_PTRS | abi.FLAG_ASYNC
+        st = abi.TraceStats()
+        for _ in range(5):
+            gpu_api.check(L.sim5_trace_image(C.byref(q), C.byref(img.out), C.byref(st)), "sim5_trace_image")
+        gpu_api.check(L.sim5_synchronize(), "sim5_synchronize")
+        for k in ("r", "phi", "g", "flux", "status"):
+            assert np.array_equal(img.to_host(k), full[k], equal_nan=True), k
+        for back in range(5):
+            ms, n = gpu_api.phase_history(back)
+            assert n >= 3 and len(ms) == 3 and ms[0] > 0 and ms[1] > 0 and ms[2] >= 0, (back, ms, n)
+        last, _, n_last = gpu_api.last_phase_ms()
+        assert last == gpu_api.phase_history(0)[0]
+        buf = (C.c_double * 3)()
+        assert L.sim5_phase_history(64, buf, 3) == abi.ERR_BAD_PARAM and L.sim5_phase_history(-1, buf, 3) == abi.ERR_BAD_PARAM
+    finally:
+        img.close()
