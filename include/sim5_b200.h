@@ -77,6 +77,10 @@ extern "C" {
 #define SIM5_FLAG_FULL_INDEX    0x40 /* with DEVICE_PTRS and split_count > 1: the planes are FULL-image planes (index iy*nx+ix) instead of this call's
                                         compact rows -- e.g. the peer-mapped planes of the rank that assembles the image (sim5_ipc_import), so
                                         every GPU stores its rows directly into the final image over NVLink and no gather is needed */
+#define SIM5_FLAG_DEFER_REDO    0x80 /* with DEVICE_PTRS | ASYNC, for a train of images traced back to back: the bit-faithful redo passes of the azimuth (one
+                                        latency-bound wave over ~0.3 % of the rays) are left running on the library's auxiliary stream while the NEXT
+                                        call's tracing kernel starts (two alternating work queues).  phi of a call is complete once sim5_join() has been
+                                        enqueued on / sim5_synchronize() has returned for the launch stream */
 #define SIM5_FLAG_ASYNC         0x4  /* with DEVICE_PTRS: enqueue on the library stream (sim5_set_stream) and return without
                                         synchronising; stats are not filled.  Pair with sim5_synchronize(). */
 
@@ -224,6 +228,7 @@ int  sim5_gpu_init(int device);        /* create context/streams/scratch on `dev
 int  sim5_set_stream(void* cuda_stream); /* launch on the caller's cudaStream_t (e.g. torch's current stream); NULL = library stream */
 int  sim5_set_chunk_rays(int64_t rays); /* host-plane calls trace and copy back in chunks of about this many rays (copy of chunk k under the kernels of chunk k+1); <= 0 restores the default (2^21) */
 int  sim5_synchronize(void);            /* wait for everything enqueued by SIM5_FLAG_ASYNC calls */
+int  sim5_join(void);                   /* make the launch stream wait (on the device, no host sync) for the deferred redo passes of earlier SIM5_FLAG_DEFER_REDO calls */
 void sim5_gpu_shutdown(void);
 int  sim5_gpu_device_count(void);      /* 0 when no usable device */
 const char* sim5_last_error(void);

@@ -35,6 +35,7 @@ def lib():
         L.sim5_set_stream.argtypes = [C.c_void_p]
         L.sim5_set_stream.restype = C.c_int
         L.sim5_synchronize.restype = C.c_int
+        L.sim5_join.restype = C.c_int
         L.sim5_set_chunk_rays.argtypes = [C.c_int64]
         L.sim5_set_chunk_rays.restype = C.c_int
         L.sim5_last_error.restype = C.c_char_p

@@ -28,6 +28,9 @@ using s5::AzQueue;
 /* ------------------------------------------------------------------ */
 namespace {
 
+#ifndef S5_DEFER_REDO_CTAS
+#define S5_DEFER_REDO_CTAS 32      /* grid of a deferred redo pass: it runs beside the next call's tracing kernel */
+#endif
 #define S5_MAX_CHUNKS 32
 #define S5_CHUNK_RAYS (1 << 21)     /* rays per chunk of a host-plane call: ~1.1 ms of kernels, ~1.2 ms of PCIe.  4096^2 r/phi/g/flux/status end to end
                                        (profiles/r01x_sweep.log, ms): 2^18 13.6, 2^19 13.6, 2^20 11.9, 2^21 11.4, 2^22 12.2, 2^23 14.4 */
@@ -74,6 +77,13 @@ struct Context {
     Plane hist;
     Plane azq_redo;
     Plane azq_f, azq_key;                 /* azimuth work-item queue (phase A -> phase B) */
+    /* SIM5_FLAG_DEFER_REDO: a second queue and two counter blocks of its own, so the redo passes of call k can run beside call k+1 */
+    Plane azq2_f, azq2_key, azq2_redo;
+    unsigned long long* d_counter2 = nullptr;             /* [2][8] */
+    cudaEvent_t ev_redo_done[2] = {nullptr, nullptr}, ev_fast_done = nullptr;
+    bool redo_pending[2] = {false, false};
+    int defer_buf = 0;
+    unsigned long long* last_counts = nullptr;           /* queue counts of the most recent image call (sim5_last_phase_ms) */
     void* batch[8] = {nullptr};
     size_t batch_bytes[8] = {0};
     std::string last_error;
@@ -145,6 +155,11 @@ int ensure_init(int device)
     CK(cudaHostAlloc((void**)&c.h_consts, sizeof(S5ImageConsts), cudaHostAllocDefault));
     CK(cudaMalloc((void**)&c.d_consts, sizeof(S5ImageConsts)));
     CK(cudaMalloc((void**)&c.d_counter, 8 * sizeof(unsigned long long)));   /* [0..2] tile counters, [4..5] queue counts */
+    CK(cudaMalloc((void**)&c.d_counter2, 16 * sizeof(unsigned long long)));
+    CK(cudaEventCreateWithFlags(&c.ev_redo_done[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c.ev_redo_done[1], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c.ev_fast_done, cudaEventDisableTiming));
+    c.redo_pending[0] = c.redo_pending[1] = false; c.defer_buf = 0; c.last_counts = c.d_counter + 4;
     CK(cudaMalloc((void**)&c.d_stats, sizeof(DevStats)));
     CK(cudaHostAlloc((void**)&c.h_stats, sizeof(DevStats), cudaHostAllocDefault));
     /* the stepper keeps ~100 doubles of live state per thread and calls non-inlined Carlson routines */
@@ -355,6 +370,12 @@ extern "C" void sim5_gpu_shutdown(void)
     if (c.azq_f.p) cudaFree(c.azq_f.p); c.azq_f = Plane();
     if (c.azq_key.p) cudaFree(c.azq_key.p); c.azq_key = Plane();
     if (c.azq_redo.p) cudaFree(c.azq_redo.p); c.azq_redo = Plane();
+    cudaStreamSynchronize(c.aux_stream);
+    if (c.azq2_f.p) cudaFree(c.azq2_f.p); c.azq2_f = Plane();
+    if (c.azq2_key.p) cudaFree(c.azq2_key.p); c.azq2_key = Plane();
+    if (c.azq2_redo.p) cudaFree(c.azq2_redo.p); c.azq2_redo = Plane();
+    cudaFree(c.d_counter2); c.d_counter2 = nullptr;
+    cudaEventDestroy(c.ev_redo_done[0]); cudaEventDestroy(c.ev_redo_done[1]); cudaEventDestroy(c.ev_fast_done);
     for (int i = 0; i < 8; i++) { if (c.batch[i]) cudaFree(c.batch[i]); c.batch[i] = nullptr; c.batch_bytes[i] = 0; }
     cudaFreeHost(c.h_scr); cudaFreeHost(c.h_consts); cudaFree(c.d_consts); cudaFree(c.d_counter); cudaFree(c.d_stats); cudaFreeHost(c.h_stats);
     cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev3);
@@ -380,10 +401,32 @@ extern "C" int sim5_set_chunk_rays(int64_t rays)
     return SIM5_OK;
 }
 
+namespace {
+/* the launch stream waits for the redo passes that SIM5_FLAG_DEFER_REDO calls left running on the auxiliary stream */
+int join_deferred(Context& c, int only_buf /* -1: all */)
+{
+    for (int b = 0; b < 2; b++) {
+        if (!c.redo_pending[b] || (only_buf >= 0 && b != only_buf)) continue;
+        CK(cudaStreamWaitEvent(c.stream, c.ev_redo_done[b], 0));
+        c.redo_pending[b] = false;
+    }
+    return SIM5_OK;
+}
+}
+
+extern "C" int sim5_join(void)
+{
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (!g_ctx.ready) return SIM5_OK;
+    return join_deferred(g_ctx, -1);
+}
+
 extern "C" int sim5_synchronize(void)
 {
     std::lock_guard<std::mutex> lk(g_ctx.mu);
     if (!g_ctx.ready) return SIM5_OK;
+    int rc = join_deferred(g_ctx, -1);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(g_ctx.stream));
     return SIM5_OK;
 }
@@ -580,6 +623,27 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         q.f = (double*)c.azq_f.p; q.key = (unsigned long long*)c.azq_key.p; q.count = c.d_counter + 4; q.cap = (long long)qpix;
         q.redo = (unsigned*)c.azq_redo.p;
     }
+    /* deferred redo passes: this call's queue and counters alternate between two sets; the set it takes must be free again (the call
+     * before the previous one), every other kind of call first waits for all of them */
+    const bool defer = two_phase && async && nchunks == 1 && (p->flags & SIM5_FLAG_DEFER_REDO) && !(p->flags & SIM5_FLAG_EXACT_AZIMUTH);
+    unsigned long long* cnt = c.d_counter;
+    if (defer) {
+        const int b = c.defer_buf;
+        c.defer_buf ^= 1;
+        rc = join_deferred(c, b); if (rc) return rc;
+        cnt = c.d_counter2 + 8 * b;
+        if (b == 1) {
+            size_t qpix = (size_t)q.cap;
+            rc = reserve(c.azq2_f, qpix * S5_AZ_NFIELDS * sizeof(double)); if (rc) return rc;
+            rc = reserve(c.azq2_key, qpix * sizeof(unsigned long long)); if (rc) return rc;
+            rc = reserve(c.azq2_redo, qpix * sizeof(unsigned)); if (rc) return rc;
+            q.f = (double*)c.azq2_f.p; q.key = (unsigned long long*)c.azq2_key.p; q.redo = (unsigned*)c.azq2_redo.p;
+        }
+        q.count = cnt + 4;
+    } else {
+        rc = join_deferred(c, -1); if (rc) return rc;
+    }
+    c.last_counts = cnt + 4;
     c.ring_pos = (c.ring_pos + 1) % S5_RING;
     c.ev1 = c.ring[c.ring_pos][0]; c.evp[0] = c.ring[c.ring_pos][1]; c.evp[1] = c.ring[c.ring_pos][2]; c.evp[2] = c.ring[c.ring_pos][3];
     c.ev2 = c.ring[c.ring_pos][4];
@@ -604,7 +668,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                 set_dev_plane(&dd, i, (char*)c.planes[i].p + pix0 * kPlaneInfo[i].elem);
             }
         }
-        CK(cudaMemsetAsync(c.d_counter, 0, 8 * sizeof(unsigned long long), c.stream));
+        CK(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), c.stream));
         if (p->mode == SIM5_MODE_STEPWISE) {
             grid = persistent_grid(s5::k_trace_lanes<s5::StepwiseProg>, s5::StepwiseProg::THREADS);
             s5::k_trace_lanes<s5::StepwiseProg><<<grid, s5::StepwiseProg::THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
@@ -614,10 +678,10 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         } else if (two_phase) {
             if (p->outputs & SIM5_OUT_DELAY) {
                 grid = persistent_grid(s5::k_trace_eqplane<true, true>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
-                s5::k_trace_eqplane<true, true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+                s5::k_trace_eqplane<true, true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, cnt, c.d_stats);
             } else {
                 grid = persistent_grid(s5::k_trace_eqplane<true>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
-                s5::k_trace_eqplane<true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+                s5::k_trace_eqplane<true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, cnt, c.d_stats);
             }
             if (ch == 0) CK(cudaEventRecord(c.evp[0], c.stream));
             int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_AZ_THREADS);
@@ -627,14 +691,10 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
              * items over all CTAs without barriers (0.14 / 0.22 ms against 0.10 / 0.24): the wave is bound by walking ~120 KB of code, not by the pipe */
             const int redo_threads = S5_AZ_THREADS;
             if (p->flags & SIM5_FLAG_EXACT_AZIMUTH) {
-                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 1, 0);
+                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, cnt + 1, 0);
                 if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
-                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 2, 0);
+                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, cnt + 2, 0);
             } else {
-#if defined(S5_AZF_MERGED)
-                int g_f = persistent_grid(s5::k_azimuth_fast<0>, S5_AZF_THREADS);
-                s5::k_azimuth_fast<0><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
-#else
                 /* RR chain on the launch stream, RC chain (3 % of the hits) on the auxiliary stream: the two bit-faithful redo
                  * passes are latency-bound single waves, so they run side by side instead of back to back */
                 CK(cudaEventRecord(c.ev_fork, c.stream));
@@ -643,19 +703,27 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                 s5::k_azimuth_fast<1><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
                 g_f = persistent_grid(s5::k_azimuth_fast<2>, S5_AZF_THREADS);
                 s5::k_azimuth_fast<2><<<g_f, S5_AZF_THREADS, 0, c.aux_stream>>>(cc, q, dd.phi);
-                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, c.d_counter + 2, 1);
-                CK(cudaEventRecord(c.ev_join, c.aux_stream));
-                launches += 1;
-#endif
-                if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
-                /* the redo list: items outside the fast routines' domain or flagged by the conditioning guard (~0.3 %) */
-                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, redo_threads, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 1, 1);
-#if defined(S5_AZF_MERGED)
-                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, redo_threads, 0, c.stream>>>(cc, q, dd.phi, c.d_counter + 2, 1);
-#else
-                CK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
-#endif
-                launches += 1;
+                if (defer) {
+                    /* both redo passes stay on the auxiliary stream, in a few CTAs (a 512-thread CTA of the bit-faithful kernel fills the register
+                     * file of its SM, and the next call's tracing kernel is about to want the SMs); nothing joins the launch stream here */
+                    const int gs_rc = g_rc < S5_DEFER_REDO_CTAS ? g_rc : S5_DEFER_REDO_CTAS, gs_rr = g_rr < S5_DEFER_REDO_CTAS ? g_rr : S5_DEFER_REDO_CTAS;
+                    CK(cudaEventRecord(c.ev_fast_done, c.stream));
+                    s5::k_azimuth<s5::GEOD_TYPE_RC><<<gs_rc, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, cnt + 2, 1);
+                    CK(cudaStreamWaitEvent(c.aux_stream, c.ev_fast_done, 0));
+                    s5::k_azimuth<s5::GEOD_TYPE_RR><<<gs_rr, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, cnt + 1, 1);
+                    const int b = (cnt == c.d_counter2) ? 0 : 1;
+                    CK(cudaEventRecord(c.ev_redo_done[b], c.aux_stream));
+                    c.redo_pending[b] = true;
+                    if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
+                } else {
+                    s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, cnt + 2, 1);
+                    CK(cudaEventRecord(c.ev_join, c.aux_stream));
+                    if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
+                    /* the redo list: items outside the fast routines' domain or flagged by the conditioning guard (~0.3 %) */
+                    s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, redo_threads, 0, c.stream>>>(cc, q, dd.phi, cnt + 1, 1);
+                    CK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
+                }
+                launches += 2;
             }
             if (ch == 0) CK(cudaEventRecord(c.evp[2], c.stream));
             launches += 2;
@@ -737,7 +805,7 @@ extern "C" int sim5_last_phase_ms(double* ms, int n, int64_t* items)
     for (int i = 0; i < 3 && i < n; i++) { CK(cudaEventElapsedTime(&t, seq[i], seq[i + 1])); ms[i] = t; }
     if (items) {
         unsigned long long cnt[2] = {0, 0};
-        CK(cudaMemcpy(cnt, c.d_counter + 4, sizeof cnt, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(cnt, c.last_counts, sizeof cnt, cudaMemcpyDeviceToHost));
         items[0] = (int64_t)cnt[0]; items[1] = (int64_t)cnt[1];
     }
     return c.phases;

@@ -340,5 +340,30 @@ def test_async_train_and_phase_history(gpu_api):
         assert last == gpu_api.phase_history(0)[0]
         buf = (C.c_double * 3)()
         assert L.sim5_phase_history(64, buf, 3) == abi.ERR_BAD_PARAM and L.sim5_phase_history(-1, buf, 3) == abi.ERR_BAD_PARAM
+        # SIM5_FLAG_DEFER_REDO: the redo passes of call k run beside call k+1 (two alternating queues); after sim5_synchronize() the
+        # planes hold the same image.  The planes are cleared first so that a lost redo pass would show.
+        for other in (abi.default_params(2, 256), abi.default_params(3, 192)):
+            ref_img, _ = _gpu_planes(gpu_api, other)
+            img2 = gpu_api.DevicePlanes(other, names=tuple(k for k in ("r", "phi", "g", "flux", "status") if k in ref_img.arrays))
+            try:
+                q = abi.ImageParams.from_buffer_copy(other)
+                q.outputs = 0
+                for name, bit, _ct in abi.PLANES:
+                    if name in img2.ptrs:
+                        q.outputs |= bit
+                q.flags = abi.FLAG_DEVICE_PTRS | abi.FLAG_ASYNC | abi.FLAG_DEFER_REDO
+                for _ in range(5):
+                    gpu_api.check(L.sim5_trace_image(C.byref(q), C.byref(img2.out), C.byref(st)), "sim5_trace_image")
+                gpu_api.check(L.sim5_synchronize(), "sim5_synchronize")
+                for k in img2.ptrs:
+                    assert np.array_equal(img2.to_host(k), ref_img[k], equal_nan=True), k
+                # a synchronous call right after a deferred train drains it first
+                gpu_api.check(L.sim5_trace_image(C.byref(q), C.byref(img2.out), C.byref(st)), "sim5_trace_image")
+                full2, _ = _gpu_planes(gpu_api, other)
+                for k in img2.ptrs:
+                    assert np.array_equal(full2[k], ref_img[k], equal_nan=True), k
+            finally:
+                gpu_api.check(L.sim5_synchronize(), "sim5_synchronize")
+                img2.close()
     finally:
         img.close()
