@@ -170,6 +170,7 @@ int ensure_init(int device)
         CK(cudaFuncSetAttribute(s5::k_trace_eqplane<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S5_EQ_DYN_SMEM));
         CK(cudaFuncSetAttribute(s5::k_trace_eqplane<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S5_EQ_DYN_SMEM));
         CK(cudaFuncSetAttribute(s5::k_trace_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S5_EQ_DYN_SMEM));
+        if (S5_SPEC_DYN_SMEM > 0) CK(cudaFuncSetAttribute(s5::k_trace_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S5_SPEC_DYN_SMEM));
     }
     /* (cudaFuncAttributePreferredSharedMemoryCarveout = 0, i.e. all 256 KB to L1, was tried for the spilling kernels: phase A unchanged,
      * SURFACE 42.6 -> 45.4 ms -- profiles/r01z_sweep.log -- so the driver's default carve-out stays) */
@@ -325,9 +326,9 @@ int trace_spectrum(const sim5_image_params* p, const sim5_image_out* out, sim5_t
     CK(cudaMemsetAsync(d_spec, 0, S5_SPEC_MAX_E * sizeof(double), c.stream));
     CK(cudaMemsetAsync(c.d_counter, 0, sizeof(unsigned long long), c.stream));
     CK(cudaMemsetAsync(c.d_stats, 0, sizeof(DevStats), c.stream));
-    int grid = persistent_grid(s5::k_trace_spectrum, S5_CTA_THREADS);
+    int grid = persistent_grid(s5::k_trace_spectrum, S5_SPEC_THREADS, S5_SPEC_DYN_SMEM);
     CK(cudaEventRecord(c.ev1, c.stream));
-    if (consts.nrows_local > 0) s5::k_trace_spectrum<<<grid, S5_CTA_THREADS, 0, c.stream>>>(consts, d_e, d_spec, c.d_counter, c.d_stats);
+    if (consts.nrows_local > 0) s5::k_trace_spectrum<<<grid, S5_SPEC_THREADS, S5_SPEC_DYN_SMEM, c.stream>>>(consts, d_e, d_spec, c.d_counter, c.d_stats);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c.ev2, c.stream));
     CK(cudaMemcpyAsync(out->spectrum, d_spec, ne * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
@@ -343,7 +344,7 @@ int trace_spectrum(const sim5_image_params* p, const sim5_image_out* out, sim5_t
         float ms = 0;
         cudaEventElapsedTime(&ms, c.ev1, c.ev2); stats->kernel_ms = ms;
         cudaEventElapsedTime(&ms, c.ev0, c.ev3); stats->total_ms = ms;
-        stats->kernel_launches = 1; stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = S5_CTA_THREADS;
+        stats->kernel_launches = 1; stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = S5_SPEC_THREADS;
     }
     return SIM5_OK;
 }

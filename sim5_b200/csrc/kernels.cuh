@@ -566,10 +566,19 @@ k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice i
  * three per-hit numbers arrive by shuffle -- so every lane accumulates in registers and there is no per-term reduction.
  * Lanes flush once per kernel: shared-memory atomics per CTA, then one global atomic per CTA and energy. */
 #define S5_SPEC_MAX_E 256
-#ifndef S5_MIN_CTAS_SPEC
-#define S5_MIN_CTAS_SPEC 4
+#if defined(S5_SPEC_FREERUN)
+#define S5_SPEC_THREADS S5_CTA_THREADS
+#define S5_SPEC_CTAS 4
+#define S5_SPEC_DYN_SMEM ((size_t)0)
+#else
+/* the same execution shape as k_trace_eqplane / k_trace_histogram: CTAs of S5_EQ_THREADS threads in lockstep, one tile per warp and
+ * batch, the staged pixel routine with the geodesic in shared-memory slots (the free-running 128-thread kernel was bound by
+ * instruction supply: stall_no_instruction 2.7 per issue, FP64 pipe 36 % active, profiles/r04b_ncu_modes_summary.csv) */
+#define S5_SPEC_THREADS S5_EQ_THREADS
+#define S5_SPEC_CTAS S5_MIN_CTAS_EQ
+#define S5_SPEC_DYN_SMEM S5_EQ_DYN_SMEM
 #endif
-__global__ void __launch_bounds__(S5_CTA_THREADS, S5_MIN_CTAS_SPEC)      /* the 8 energies + 8 accumulators per lane live across the pixel routine; r02f sweep (ms): 3 CTAs/SM (168 regs) 5.41, 4 (128) 5.05, 5 5.50, 6 5.53 */
+__global__ void __launch_bounds__(S5_SPEC_THREADS, S5_SPEC_CTAS)
 k_trace_spectrum(const __grid_constant__ S5ImageConsts gconsts, const double* __restrict__ energies, double* __restrict__ spec,
                  unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
 {
@@ -588,16 +597,45 @@ k_trace_spectrum(const __grid_constant__ S5ImageConsts gconsts, const double* __
     double Ek[S5_SPEC_MAX_E / 32], acc[S5_SPEC_MAX_E / 32];
     #pragma unroll
     for (int j = 0; j < S5_SPEC_MAX_E / 32; j++) { int k = lane + 32 * j; Ek[j] = (k < ne) ? energies[k] : 1.0; acc[j] = 0.0; }
-
+#if !defined(S5_SPEC_FREERUN)
+    __shared__ unsigned long long s_tile;
+#endif
     for (;;) {
         unsigned long long t = 0;
+        SpecHit h;
+        h.amp3 = 0.0; h.ginv = 1.0; h.xs = 1.0;
+        bool hit = false;
+#if !defined(S5_SPEC_FREERUN)
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, (unsigned long long)(S5_SPEC_THREADS / 32));
+        __syncthreads();
+        if ((long long)s_tile >= ntiles) break;
+        t = s_tile + (threadIdx.x >> 5);
+        {
+            long long p = ((long long)t << 5) + lane;
+            const bool valid = (long long)t < ntiles && p < npix;
+            const long long pc = valid ? p : npix - 1;
+            int lr = (int)(pc / nx);
+            int ix = (int)(pc - (long long)lr * nx);
+            int iy = s5_local_to_image_row(&c, lr);
+            unsigned status;
+#if S5_EQ_DYN_SMEM_ON
+            extern __shared__ double s_dyn[];
+            Geodesic* gslot = reinterpret_cast<Geodesic*>(reinterpret_cast<char*>(s_dyn) + (size_t)threadIdx.x * S5_GD_SLOT_BYTES);
+            hit = spectrum_pixel_t<true>(c, ix, iy, &h, &status, gslot) && valid;
+#else
+            hit = spectrum_pixel_t<false>(c, ix, iy, &h, &status, nullptr) && valid;
+#endif
+            if (valid) {
+                atomicAdd(&s_cnt[status & 31], 1u);
+                atomicAdd(&s_cnt[32 + ((status >> 5) & 7)], 1u);
+            }
+        }
+#else
         if (lane == 0) t = atomicAdd(tile_counter, 1ULL);
         t = __shfl_sync(0xffffffffu, t, 0);
         if ((long long)t >= ntiles) break;
         long long p = ((long long)t << 5) + lane;
-        SpecHit h;
-        h.amp3 = 0.0; h.ginv = 1.0; h.xs = 1.0;
-        bool hit = false;
         if (p < npix) {
             int lr = (int)(p / nx);
             int ix = (int)(p - (long long)lr * nx);
@@ -607,6 +645,7 @@ k_trace_spectrum(const __grid_constant__ S5ImageConsts gconsts, const double* __
             atomicAdd(&s_cnt[status & 31], 1u);
             atomicAdd(&s_cnt[32 + ((status >> 5) & 7)], 1u);
         }
+#endif
         unsigned hits = __ballot_sync(0xffffffffu, hit);
         for (unsigned m = hits; m; m &= m - 1) {
             int src = __ffs(m) - 1;

@@ -748,11 +748,14 @@ S5_HD S5_INL void trace_eqplane_pixel(const S5ImageConsts& c, int ix, int iy, Pi
  *     amp * E_k^3 / expm1(xs * E_k)        (blackbody() of sim5radiation.c:73-76 at E_k/g, times g^3 dalpha dbeta)
  * with the (1/g)^3 of the emitted energy and the g^3 of the intensity invariant kept as the reference has them. */
 struct SpecHit { double amp3, ginv, xs; };      /* amp3 = limb factor * BB1 * g^3 * dalpha dbeta ; ginv = 1/g ; xs = BB2 (hardening and T included) */
-S5_HD S5_INL bool spectrum_pixel(const S5ImageConsts& c, int ix, int iy, SpecHit* h, unsigned* status)
+/* SYNC: every thread of the CTA calls (lockstep kernels, see trace_eqplane_pixel_t); gslot = the thread's shared-memory geodesic slot */
+template <bool SYNC>
+S5_HD S5_INL bool spectrum_pixel_t(const S5ImageConsts& c, int ix, int iy, SpecHit* h, unsigned* status, Geodesic* gslot)
 {
     PixelOut o;
     AzIn z;                                                    /* never filled: no phi is requested (DEFER only keeps the azimuth code out of the kernel) */
-    trace_eqplane_pixel_t<true>(c, ix, iy, &o, &z);            /* c.mode == POLARIZED: g and mu_e from the Keplerian emitter frame */
+    if (SYNC) trace_eqplane_pixel_t<true, false, true, true>(c, ix, iy, &o, &z, gslot);
+    else      trace_eqplane_pixel_t<true>(c, ix, iy, &o, &z);  /* c.mode == POLARIZED: g and mu_e from the Keplerian emitter frame */
     *status = o.status;
     unsigned cls = o.status & 31;
     if (!(cls == SIM5_ST_HIT0 || cls == SIM5_ST_HIT1 || cls == SIM5_ST_HIT2)) return false;
@@ -764,6 +767,10 @@ S5_HD S5_INL bool spectrum_pixel(const S5ImageConsts& c, int ix, int iy, SpecHit
     h->ginv = 1.0 / o.g;
     h->xs = c.bb2 / T;
     return true;
+}
+S5_HD S5_INL bool spectrum_pixel(const S5ImageConsts& c, int ix, int iy, SpecHit* h, unsigned* status)
+{
+    return spectrum_pixel_t<false>(c, ix, iy, h, status, nullptr);
 }
 /* one (hit, energy) term: Iv = BB1 E^3 / expm1(BB2 E) at E = E_k / g, times g^3 dA -- with the per-hit factors hoisted
  * (the reference-side driver divides and multiplies per term; the two agree to rounding, far inside the 1e-7 bar) */
