@@ -95,12 +95,15 @@ def run_reference(args):
     import harness as H
     from sim5_b200 import abi
     p = workload_params(abi, SAMPLE_N)
+    # all the host threads this process may use -- stated explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     if H.have_ref():
-        kind, run = "reference", H.run_ref
-        cores = H.load_ref().ref_max_threads()
+        kind, run = "reference", (lambda q: H.run_ref(q, nthreads=cores))
     elif H.have_oracle():
-        kind, run = "port", H.run_oracle
-        cores = os.cpu_count()
+        kind, run = "port", (lambda q: H.run_oracle(q, nthreads=cores))
     else:
         print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref/libsim5ref.so nor oracle/libsim5oracle.so is built"}))
         return 0
