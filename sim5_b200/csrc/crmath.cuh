@@ -163,6 +163,7 @@ S5_HD S5_INL dd dd_sqr(dd a)
     p.l = fma_(add_(a.h, a.h), a.l, p.l);
     return fast_two_sum(p.h, p.l);
 }
+#if defined(S5_DD_DIV3)
 S5_HD S5_INL dd dd_div(dd a, dd b)
 {
     double q1 = a.h / b.h;
@@ -173,6 +174,17 @@ S5_HD S5_INL dd dd_div(dd a, dd b)
     dd q = fast_two_sum(q1, q2);
     return dd_add_d(q, q3);
 }
+#else
+/* a / b to ~2^-102 (two quotient digits; the third one of the long-division form above changes the result below 2^-104, far under
+ * the 2^-68 this library's error budget needs): one division, one double-double product and two double-double sums less per call */
+S5_HD S5_INL dd dd_div(dd a, dd b)
+{
+    double q1 = a.h / b.h;
+    dd r = dd_add(a, dd_neg(dd_mul_d(b, q1)));
+    double q2 = r.h / b.h;
+    return fast_two_sum(q1, q2);
+}
+#endif
 S5_HD S5_INL dd dd_div_dd_d(double a, double b)      /* a/b for plain doubles, as a dd */
 {
     double q = a / b;
