@@ -168,8 +168,12 @@ def run_ours(args):
     p.device = local
     rows = sdist.apply_split(p, rank, world) if world > 1 else n
     p.flags = abi.FLAG_DEVICE_PTRS | abi.FLAG_ASYNC | (abi.FLAG_EXACT_AZIMUTH if args.exact_azimuth else 0)
-    if not args.no_defer_redo:
-        p.flags |= abi.FLAG_DEFER_REDO      # a train of images: the redo wave of step k runs beside the tracing kernel of step k+1
+    # a train of images: the redo wave of step k can run beside the kernels of step k+1 (SIM5_FLAG_DEFER_REDO).  It pays when the wave is a
+    # large part of the step (multi-GPU split: 8 GPUs 1.24 -> 1.12 ms); on one GPU it is neutral to slightly negative (the wave's 32 CTAs
+    # take SMs from the 2.7 ms azimuth kernel: 7.30 vs 7.32-7.35 ms), so by default it is used for N > 1 only
+    defer = (world > 1) if args.defer_redo == "auto" else (args.defer_redo == "on")
+    if defer and not args.no_defer_redo:
+        p.flags |= abi.FLAG_DEFER_REDO
     names = ("r", "phi", "g", "flux")
     peer = world > 1 and args.gather == "peer"
     st = abi.TraceStats()
@@ -386,6 +390,7 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N>1: 'peer' = every rank stores its rows into rank 0's image over NVLink peer memory (default); "
                          "'nccl' = compact planes + torch.distributed gather + re-assembly on rank 0 (A/B)")
+    ap.add_argument("--defer-redo", default="auto", choices=["auto", "on", "off"], help="SIM5_FLAG_DEFER_REDO for the timed train (auto: only with more than one GPU)")
     ap.add_argument("--no-defer-redo", action="store_true", help="A/B: join the azimuth redo passes inside every step instead of letting them run beside the next step's tracing kernel")
     ap.add_argument("--exact-azimuth", action="store_true", help="A/B: bit-faithful azimuth kernels (SIM5_FLAG_EXACT_AZIMUTH) instead of the tolerance-mode default")
     args = ap.parse_args()

@@ -177,6 +177,7 @@ S5_HD S5_INL dd dd_div(dd a, dd b)
 #else
 /* a / b to ~2^-102 (two quotient digits; the third one of the long-division form above changes the result below 2^-104, far under
  * the 2^-68 this library's error budget needs): one division, one double-double product and two double-double sums less per call */
+#if defined(S5_DD_DIV_2DIV)
 S5_HD S5_INL dd dd_div(dd a, dd b)
 {
     double q1 = a.h / b.h;
@@ -184,6 +185,26 @@ S5_HD S5_INL dd dd_div(dd a, dd b)
     double q2 = r.h / b.h;
     return fast_two_sum(q1, q2);
 }
+#else
+/* both quotient digits from ONE correctly rounded reciprocal of b.h (the same bits on host and device): a digit that is off by an
+ * ulp only moves work into the next digit, the remainder is formed exactly either way */
+S5_HD S5_INL double rcp_(double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __drcp_rn(b);
+#else
+    return 1.0 / b;
+#endif
+}
+S5_HD S5_INL dd dd_div(dd a, dd b)
+{
+    double rb = rcp_(b.h);
+    double q1 = mul_(a.h, rb);
+    dd r = dd_add(a, dd_neg(dd_mul_d(b, q1)));
+    double q2 = mul_(r.h, rb);
+    return fast_two_sum(q1, q2);
+}
+#endif
 #endif
 S5_HD S5_INL dd dd_div_dd_d(double a, double b)      /* a/b for plain doubles, as a dd */
 {
