@@ -139,10 +139,13 @@ typedef struct sim5_image_params {
     uint32_t flags;              /* SIM5_FLAG_* */
     int32_t  nx, ny;             /* image size in pixels */
     int32_t  row_begin, row_end; /* rows [row_begin,row_end) traced by this call; 0,0 = all rows.
-                                    Planes are always addressed with the FULL image index iy*nx+ix
-                                    unless SIM5_FLAG_DEVICE_PTRS is set and row_base_is_zero != 0 */
+                                    HOST planes are always addressed with the FULL image index iy*nx+ix.  DEVICE planes
+                                    (SIM5_FLAG_DEVICE_PTRS) too, except in an interleaved split (split_count > 1) without
+                                    SIM5_FLAG_FULL_INDEX: those are COMPACT, [rows of this call][nx] (see split_count below) */
     int32_t  max_order;          /* highest crossing order tried (reference example: 1) */
-    int32_t  device;             /* CUDA device ordinal */
+    int32_t  device;             /* CUDA device ordinal; < 0 (what sim5_default_params sets): the calling thread's current context,
+                                    i.e. the device of its last sim5_gpu_init / explicit ordinal, else the process default.  Every
+                                    device has a context of its own; naming another device never tears one down */
     /* geometry -- pixel rule of disk-image.c:57-58:
      *   alpha = ((ix+.5)/nx-.5)*2*rmax ; beta = ((iy+.5)/ny-.5)*2*rmax*(ny/nx) */
     double   bh_spin;
@@ -167,7 +170,9 @@ typedef struct sim5_image_params {
     double   torus_k0;           /* absorption normalisation */
     /* HISTOGRAM */
     int32_t  n_spin, n_incl, n_bins;
-    int32_t  lattice_begin, lattice_end; /* images [begin,end) of the n_spin*n_incl lattice (multi-GPU split); 0,0 = all */
+    int32_t  lattice_begin, lattice_end; /* images [begin,end) of the n_spin*n_incl lattice; 0,0 = all.  With split_count > 1 the call traces
+                                            the images begin + split_index, begin + split_index + split_count, ... of that range and zeroes the bins of
+                                            the others, so the histograms of the split_count GPUs ADD UP to the lattice (one reduce at the end) */
     int32_t  reserved1;
     double   spin_max;           /* a_j = spin_max*j/(n_spin-1) */
     double   incl_min_deg, incl_max_deg; /* i_k = min + (max-min)*k/(n_incl-1) degrees */
@@ -224,12 +229,14 @@ typedef struct sim5_trace_stats {
 } sim5_trace_stats;
 
 /* lifecycle ------------------------------------------------------------- */
-int  sim5_gpu_init(int device);        /* create context/streams/scratch on `device`; idempotent */
+int  sim5_gpu_init(int device);        /* create context/streams/scratch on `device` (idempotent) and make it the calling thread's current
+                                          context; the first successful call also sets the process default.  Every entry point makes its
+                                          context's device current (cudaSetDevice) before it touches the CUDA runtime */
 int  sim5_set_stream(void* cuda_stream); /* launch on the caller's cudaStream_t (e.g. torch's current stream); NULL = library stream */
 int  sim5_set_chunk_rays(int64_t rays); /* host-plane calls trace and copy back in chunks of about this many rays (copy of chunk k under the kernels of chunk k+1); <= 0 restores the default (2^21) */
 int  sim5_synchronize(void);            /* wait for everything enqueued by SIM5_FLAG_ASYNC calls */
 int  sim5_join(void);                   /* make the launch stream wait (on the device, no host sync) for the deferred redo passes of earlier SIM5_FLAG_DEFER_REDO calls */
-void sim5_gpu_shutdown(void);
+void sim5_gpu_shutdown(void);          /* tears down the contexts of all devices */
 int  sim5_gpu_device_count(void);      /* 0 when no usable device */
 const char* sim5_last_error(void);
 const char* sim5_version(void);
@@ -240,7 +247,7 @@ void  sim5_host_free(void* p);
 /* device memory helpers for SIM5_FLAG_DEVICE_PTRS users (e.g. a torch tensor's data_ptr works too) */
 void* sim5_device_alloc(size_t bytes);
 void  sim5_device_free(void* p);
-int   sim5_device_to_host(void* dst, const void* src, size_t bytes);
+int   sim5_device_to_host(void* dst, const void* src, size_t bytes);   /* waits for the context's launch stream and deferred redo passes first */
 /* CUDA IPC for one-process-per-GPU jobs on one node: export a sim5_device_alloc'd plane as a 64-byte handle, import it in
  * another process (peer access over NVLink is enabled on first use), release the mapping before the owner frees the plane */
 int   sim5_ipc_export(const void* device_ptr, void* handle64);
@@ -254,6 +261,15 @@ int  sim5_default_params(int cfg, sim5_image_params* p);
 
 /* THE batched entry: replaces the per-pixel loop of disk-image.c:53-105 */
 int  sim5_trace_image(const sim5_image_params* p, const sim5_image_out* out, sim5_trace_stats* stats);
+
+/* The same call on `ndev` GPUs of the box (devices[] = distinct CUDA ordinals; p->device is ignored): one host thread per device
+ * drives that device's context.  Image rows are dealt out in interleaved 32-row blocks (split_rows overrides the 32), ragged row
+ * counts included; lattice images of HISTOGRAM mode one by one.  Host planes: every GPU copies its own rows into the caller's planes
+ * (pinned planes from sim5_host_alloc let the copies overlap the kernels).  SIM5_FLAG_DEVICE_PTRS: the planes live on devices[0] and
+ * the other GPUs store their rows into them over NVLink (peer access).  HISTOGRAM: devices[0] adds the partial lattices up with loads
+ * from its peers' memory, in a fixed order, before out->hist is written.  stats: counters summed over the devices, kernel_ms /
+ * total_ms of the slowest device.  SIM5_FLAG_ASYNC and SIM5_FLAG_DEFER_REDO do not apply. */
+int  sim5_trace_image_multi(const sim5_image_params* p, const sim5_image_out* out, sim5_trace_stats* stats, const int* devices, int ndev);
 
 /* device time in ms of each kernel of the most recent sim5_trace_image call (CUDA events on the launch stream; waits for
  * the call to finish, so it also works after SIM5_FLAG_ASYNC): ms[0] trace kernel (phase A), ms[1] azimuth of the RR

@@ -104,6 +104,7 @@ def default_params(cfg, nx=None, ny=None):
     """BASELINE.json configs 1..5 with the open parameters fixed as in SURVEY.md 8(d); 6 = the SPECTRUM preset, 7 = the SURFACE preset."""
     p = ImageParams()
     p.struct_size = C.sizeof(ImageParams)
+    p.device = -1                  # the calling thread's current context (api.init(device))
     p.max_order = 1
     p.disk_mass, p.disk_mdot, p.disk_alpha = 10.0, 0.1, 0.1
     p.precision_factor, p.r_start, p.step_max, p.max_steps = 0.01, 50.0, 1e9, 100000

@@ -6,6 +6,7 @@ There is no CPU path: if the CUDA library is missing or no device is usable, cal
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -58,6 +59,8 @@ def lib():
         L.sim5_default_params.restype = C.c_int
         L.sim5_trace_image.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(abi.ImageOut), C.POINTER(abi.TraceStats)]
         L.sim5_trace_image.restype = C.c_int
+        L.sim5_trace_image_multi.argtypes = [C.POINTER(abi.ImageParams), C.POINTER(abi.ImageOut), C.POINTER(abi.TraceStats), C.POINTER(C.c_int), C.c_int]
+        L.sim5_trace_image_multi.restype = C.c_int
         L.sim5_fp64_peak_tflops.argtypes = [C.c_int, C.c_int]
         L.sim5_fp64_peak_tflops.restype = C.c_double
         L.sim5_last_phase_ms.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int64)]
@@ -97,8 +100,17 @@ def last_error():
 _NP = {C.c_double: np.float64, C.c_int32: np.int32, C.c_uint8: np.uint8}
 
 
+def _free_pinned(ptr):
+    try:
+        lib().sim5_host_free(C.c_void_p(ptr))
+    except Exception:
+        pass
+
+
 class PinnedArray:
-    """numpy view over pinned host memory from sim5_host_alloc (freed with the object)."""
+    """numpy view over pinned host memory from sim5_host_alloc.  The memory belongs to the ctypes buffer every view is based on
+    (numpy keeps it alive through `.base`), and is freed when the LAST view goes away -- an array handed out by HostPlanes may
+    outlive the HostPlanes object."""
 
     def __init__(self, n, dtype):
         self.nbytes = int(n) * np.dtype(dtype).itemsize
@@ -106,15 +118,8 @@ class PinnedArray:
         if not self.ptr:
             raise Sim5Error("sim5_host_alloc failed: " + last_error())
         buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        weakref.finalize(buf, _free_pinned, self.ptr)
         self.array = np.frombuffer(buf, dtype=dtype, count=int(n))
-
-    def __del__(self):
-        try:
-            if self.ptr:
-                lib().sim5_host_free(self.ptr)
-                self.ptr = None
-        except Exception:
-            pass
 
 
 class HostPlanes:
@@ -163,11 +168,29 @@ def trace_image(p, planes=None, pinned=True):
 
 
 def trace_image_device(p, out_struct):
-    """Trace with caller-owned DEVICE planes (e.g. torch tensors' data_ptr()); nothing is copied to the host."""
-    p.flags |= abi.FLAG_DEVICE_PTRS
+    """Trace with caller-owned DEVICE planes (e.g. torch tensors' data_ptr()); nothing is copied to the host.
+    The caller's params are not modified.  Synchronous unless p.flags carries FLAG_ASYNC; after an ASYNC or DEFER_REDO call the
+    planes are complete once synchronize() has returned (DevicePlanes.to_host waits by itself)."""
+    q = abi.ImageParams.from_buffer_copy(p)
+    q.flags |= abi.FLAG_DEVICE_PTRS
     st = abi.TraceStats()
-    check(lib().sim5_trace_image(C.byref(p), C.byref(out_struct), C.byref(st)), "sim5_trace_image")
+    check(lib().sim5_trace_image(C.byref(q), C.byref(out_struct), C.byref(st)), "sim5_trace_image")
     return st
+
+
+def trace_image_multi(p, devices, planes=None, pinned=True):
+    """One call on several GPUs of the box (sim5_trace_image_multi): rows in interleaved 32-row blocks, lattice images one by one,
+    the histogram reduced on devices[0].  Returns (HostPlanes, TraceStats)."""
+    if planes is None:
+        planes = HostPlanes(p, pinned=pinned)
+    st = abi.TraceStats()
+    devs = (C.c_int * len(devices))(*devices)
+    check(lib().sim5_trace_image_multi(C.byref(p), C.byref(planes.out), C.byref(st), devs, len(devices)), "sim5_trace_image_multi")
+    return planes, st
+
+
+def synchronize():
+    check(lib().sim5_synchronize(), "sim5_synchronize")
 
 
 class DevicePlanes:

@@ -15,6 +15,8 @@
 #include <math.h>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "sim5_b200.h"
 #include "kernels.cuh"
@@ -93,7 +95,24 @@ struct Context {
     bool disk_set = false;
 };
 
-Context g_ctx;
+/* One context per CUDA device.  A host thread works on ONE of them at a time: the one it selected last (sim5_gpu_init(device), or
+ * sim5_image_params.device >= 0), else the process default (the device of the first sim5_gpu_init, else device 0).  Selecting another
+ * device never tears a context down: its stream, scratch planes and deferred work stay where they are.  sim5_trace_image_multi runs
+ * one worker thread per device, each on its own context. */
+#define S5_MAX_DEVICES 16
+Context g_pool[S5_MAX_DEVICES];
+int g_default_dev = 0;
+bool g_default_set = false;
+bool g_warned = false;
+thread_local Context* t_ctx = nullptr;
+inline Context& cur_ctx() { return t_ctx ? *t_ctx : g_pool[g_default_dev]; }
+#define g_ctx (cur_ctx())
+/* pick the context of `device` for this thread (device < 0: keep the current one) */
+inline Context& select_ctx(int device)
+{
+    if (device >= 0 && device < S5_MAX_DEVICES) t_ctx = &g_pool[device];
+    return cur_ctx();
+}
 
 void set_error(const std::string& s) { g_ctx.last_error = s; }
 
@@ -108,22 +127,25 @@ bool cuda_ok(cudaError_t e, const char* what)
 int no_device(const char* why)
 {
     set_error(std::string("no usable CUDA device (") + why + "); libsim5b200 has no CPU path");
-    if (!g_ctx.warned) {
+    if (!g_warned) {
         fprintf(stderr, "sim5_b200: %s\n", g_ctx.last_error.c_str());
-        g_ctx.warned = true;
+        g_warned = true;
     }
     return SIM5_ERR_NO_DEVICE;
 }
 
+/* Make the context of `device` (< 0: this thread's current one) ready and current for the CUDA runtime.  Called -- under the
+ * context's mutex -- at the top of every entry point, so kernels, events and allocations always go to the context's own device
+ * whatever the caller (or torch) made current in between. */
 int ensure_init(int device)
 {
-    Context& c = g_ctx;
-    if (c.ready && (device < 0 || device == c.device)) return SIM5_OK;
-    if (c.ready) sim5_gpu_shutdown();
+    if (device >= S5_MAX_DEVICES) { set_error("device ordinal out of range"); return SIM5_ERR_BAD_PARAM; }
+    Context& c = select_ctx(device);
+    if (c.ready) { CK(cudaSetDevice(c.device)); return SIM5_OK; }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return no_device(e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"); }
-    if (device < 0) device = 0;
+    device = (int)(&c - g_pool);
     if (device >= n) { set_error("device ordinal out of range"); return SIM5_ERR_BAD_PARAM; }
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -256,11 +278,20 @@ int trace_histogram(const sim5_image_params* p, const sim5_image_out* out, sim5_
     int lb = p->lattice_begin, le = p->lattice_end;
     if (lb == 0 && le == 0) le = nimg;
     if (lb < 0 || le > nimg || lb >= le) { set_error("bad lattice range"); return SIM5_ERR_BAD_PARAM; }
+    /* interleaved deal of the slice over split_count GPUs (one process or worker thread per GPU): this call traces the images
+     * lb + split_index, lb + split_index + split_count, ...; the bins of the other images of [lb,le) are zeroed, so the histograms of
+     * all GPUs add up to the lattice (ncclReduce / dist.reduce between processes, k_sum_peers inside sim5_trace_image_multi) */
+    const int split = p->split_count > 1 ? p->split_count : 1;
+    if (split > 1 && (p->split_index < 0 || p->split_index >= split)) { set_error("bad split_index"); return SIM5_ERR_BAD_PARAM; }
+    const int first = lb + (split > 1 ? p->split_index : 0);
+    const int n_own = first < le ? (le - first + split - 1) / split : 0;
     int rc = reserve_consts((size_t)nimg);
     if (rc) return rc;
-    for (int img = lb; img < le; img++) {
+    for (int k = 0; k < n_own; k++) {
+        int img = first + k * split;
         sim5_image_params q;
         lattice_params(p, img, &q);
+        q.split_count = 0; q.split_index = 0;
         s5_fill_image_consts(&q, &c.h_consts[img]);
     }
     size_t hbytes = (size_t)nimg * p->n_bins * sizeof(double);
@@ -274,7 +305,7 @@ int trace_histogram(const sim5_image_params* p, const sim5_image_out* out, sim5_
     CK(cudaMemsetAsync(c.d_stats, 0, sizeof(DevStats), c.stream));
     int grid = persistent_grid(s5::k_trace_histogram, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
     CK(cudaEventRecord(c.ev1, c.stream));
-    s5::k_trace_histogram<<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(c.d_consts, lb, le, d_hist, c.d_counter, c.d_stats);
+    if (n_own > 0) s5::k_trace_histogram<<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(c.d_consts, first, split, n_own, d_hist, c.d_counter, c.d_stats);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c.ev2, c.stream));
     if (!devptr) CK(cudaMemcpyAsync(out->hist + (size_t)lb * p->n_bins, d_hist + (size_t)lb * p->n_bins, (size_t)(le - lb) * p->n_bins * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
@@ -283,7 +314,7 @@ int trace_histogram(const sim5_image_params* p, const sim5_image_out* out, sim5_
     CK(cudaStreamSynchronize(c.stream));
     if (stats) {
         memset(stats, 0, sizeof(*stats));
-        stats->rays = (int64_t)(le - lb) * p->nx * p->ny;
+        stats->rays = (int64_t)n_own * p->nx * p->ny;
         for (int i = 0; i < 32; i++) stats->class_count[i] = (int64_t)c.h_stats->cls[i];
         for (int i = 0; i < 8; i++) stats->gtype_count[i] = (int64_t)c.h_stats->gtype[i];
         float ms = 0;
@@ -356,13 +387,17 @@ int trace_spectrum(const sim5_image_params* p, const sim5_image_out* out, sim5_t
 /* ------------------------------------------------------------------ */
 extern "C" int sim5_gpu_init(int device)
 {
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    return ensure_init(device);
+    if (device >= S5_MAX_DEVICES) { set_error("device ordinal out of range"); return SIM5_ERR_BAD_PARAM; }
+    Context& c = select_ctx(device);
+    std::lock_guard<std::mutex> lk(c.mu);
+    int rc = ensure_init(device);
+    if (rc == SIM5_OK && !g_default_set) { g_default_dev = c.device; g_default_set = true; }   /* threads that never select use this one */
+    return rc;
 }
 
-extern "C" void sim5_gpu_shutdown(void)
+namespace {
+void shutdown_ctx(Context& c)
 {
-    Context& c = g_ctx;
     if (!c.ready) return;
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
@@ -385,7 +420,22 @@ extern "C" void sim5_gpu_shutdown(void)
     cudaEventDestroy(c.ev_copy_done);
     cudaStreamDestroy(c.own_stream); cudaStreamDestroy(c.copy_stream); cudaStreamDestroy(c.aux_stream);
     cudaEventDestroy(c.ev_fork); cudaEventDestroy(c.ev_join);
+    c.stream = c.own_stream = c.copy_stream = c.aux_stream = nullptr;
+    c.redo_pending[0] = c.redo_pending[1] = false;
+    c.phases = 0;
     c.ready = false;
+}
+}
+
+/* tears down the contexts of ALL devices */
+extern "C" void sim5_gpu_shutdown(void)
+{
+    for (int d = 0; d < S5_MAX_DEVICES; d++) {
+        std::lock_guard<std::mutex> lk(g_pool[d].mu);
+        shutdown_ctx(g_pool[d]);
+    }
+    g_default_set = false; g_default_dev = 0;
+    t_ctx = nullptr;
 }
 
 extern "C" int sim5_set_stream(void* cuda_stream)
@@ -398,6 +448,7 @@ extern "C" int sim5_set_stream(void* cuda_stream)
 }
 extern "C" int sim5_set_chunk_rays(int64_t rays)
 {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
     g_ctx.chunk_rays = rays > 0 ? (long long)rays : 0;
     return SIM5_OK;
 }
@@ -444,6 +495,7 @@ extern "C" const char* sim5_version(void) { return "sim5_b200 0.1 (sm_100a, fp64
 
 extern "C" void* sim5_host_alloc(size_t bytes)
 {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
     if (ensure_init(-1) != SIM5_OK) return nullptr;
     void* p = nullptr;
     if (!cuda_ok(cudaHostAlloc(&p, bytes, cudaHostAllocDefault), "cudaHostAlloc")) return nullptr;
@@ -452,6 +504,7 @@ extern "C" void* sim5_host_alloc(size_t bytes)
 extern "C" void sim5_host_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" void* sim5_device_alloc(size_t bytes)
 {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
     if (ensure_init(-1) != SIM5_OK) return nullptr;
     void* p = nullptr;
     if (!cuda_ok(cudaMalloc(&p, bytes), "cudaMalloc")) return nullptr;
@@ -485,10 +538,16 @@ extern "C" int sim5_ipc_release(void* imported_ptr)
     return SIM5_OK;
 }
 
+/* Ordered behind everything the library has enqueued for this context: the launch stream (which is cudaStreamNonBlocking, so a plain
+ * cudaMemcpy on the legacy stream would NOT wait for it) and the deferred redo passes of SIM5_FLAG_DEFER_REDO calls. */
 extern "C" int sim5_device_to_host(void* dst, const void* src, size_t bytes)
 {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
     if (ensure_init(-1) != SIM5_OK) return SIM5_ERR_NO_DEVICE;
-    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    int rc = join_deferred(g_ctx, -1);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CK(cudaStreamSynchronize(g_ctx.stream));
     return SIM5_OK;
 }
 
@@ -498,6 +557,7 @@ extern "C" int sim5_default_params(int cfg, sim5_image_params* p)
     if (!p || cfg < 1 || cfg > 7) return SIM5_ERR_BAD_PARAM;
     memset(p, 0, sizeof(*p));
     p->struct_size = (int32_t)sizeof(*p);
+    p->device = -1;                /* the calling thread's current context (sim5_gpu_init), never a silent move to device 0 */
     p->max_order = 1;
     p->disk_mass = 10.0; p->disk_mdot = 0.1; p->disk_alpha = 0.1;
     p->precision_factor = 0.01; p->r_start = 50.0; p->step_max = 1e9; p->max_steps = 100000;
@@ -540,10 +600,11 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     if (p->struct_size != (int32_t)sizeof(sim5_image_params)) { set_error("sim5_image_params.struct_size mismatch"); return SIM5_ERR_BAD_PARAM; }
     if (p->nx <= 0 || p->ny <= 0) { set_error("empty image"); return SIM5_ERR_BAD_PARAM; }
     if (p->mode < SIM5_MODE_EQPLANE || p->mode > SIM5_MODE_SURFACE) { set_error("unknown mode"); return SIM5_ERR_BAD_PARAM; }
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (p->device >= S5_MAX_DEVICES) { set_error("device ordinal out of range"); return SIM5_ERR_BAD_PARAM; }
+    Context& c = select_ctx(p->device);              /* device < 0: this thread's current context */
+    std::lock_guard<std::mutex> lk(c.mu);
     int rc = ensure_init(p->device);
     if (rc) return rc;
-    Context& c = g_ctx;
     if (p->mode == SIM5_MODE_HISTOGRAM) return trace_histogram(p, out, stats);
     if (p->mode == SIM5_MODE_SPECTRUM) return trace_spectrum(p, out, stats);
 
@@ -556,7 +617,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         if ((p->outputs & kPlaneInfo[i].bit) && !host_plane(out, i)) { set_error("selected output plane is NULL"); return SIM5_ERR_NO_OUTPUT; }
 
     int split = p->split_count > 1 ? p->split_count : 1;
-    int srows = p->split_rows > 0 ? p->split_rows : 1;
+    int srows = (split > 1 && p->split_rows > 0) ? p->split_rows : 1;     /* split_rows means nothing without a split: chunks may then cut at any row */
     if (split > 1) {
         if (p->split_index < 0 || p->split_index >= split) { set_error("bad split_index"); return SIM5_ERR_BAD_PARAM; }
         if ((re - rb) % (split * srows) != 0) { set_error("row range must be a multiple of split_count*split_rows"); return SIM5_ERR_BAD_PARAM; }
@@ -792,9 +853,191 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     return SIM5_OK;
 }
 
+/* ------------------------------------------------------------------ */
+/* one call, several GPUs of the box                                   */
+/* ------------------------------------------------------------------ */
+namespace {
+void add_stats(sim5_trace_stats* acc, const sim5_trace_stats& s, bool same_device)
+{
+    acc->rays += s.rays;
+    for (int i = 0; i < 32; i++) acc->class_count[i] += s.class_count[i];
+    for (int i = 0; i < 8; i++) acc->gtype_count[i] += s.gtype_count[i];
+    acc->total_steps += s.total_steps;
+    acc->kernel_launches += s.kernel_launches;
+    if (same_device) { acc->kernel_ms += s.kernel_ms; acc->total_ms += s.total_ms; }     /* calls of one device run back to back */
+    else { if (s.kernel_ms > acc->kernel_ms) acc->kernel_ms = s.kernel_ms; if (s.total_ms > acc->total_ms) acc->total_ms = s.total_ms; }
+    acc->sm_count += same_device ? 0 : s.sm_count;
+    if (s.grid_ctas > acc->grid_ctas) acc->grid_ctas = s.grid_ctas;
+    acc->cta_threads = s.cta_threads;
+}
+
+struct MultiJob {
+    int device = 0, index = 0, ndev = 1;
+    const sim5_image_params* p = nullptr;
+    const sim5_image_out* out = nullptr;
+    int dev0 = 0;
+    int rc = SIM5_OK;
+    std::string err;
+    sim5_trace_stats st;
+    double* d_hist = nullptr;            /* HISTOGRAM: this device's partial lattice */
+    double spec[S5_SPEC_MAX_E];          /* SPECTRUM: this device's partial sum */
+};
+
+/* the share of device job->index: runs on a thread of its own, on that device's context */
+void multi_worker(MultiJob* job)
+{
+    const sim5_image_params* p = job->p;
+    memset(&job->st, 0, sizeof job->st);
+    sim5_image_params q = *p;
+    q.device = job->device;
+    q.flags &= ~(uint32_t)(SIM5_FLAG_ASYNC | SIM5_FLAG_DEFER_REDO);
+    const bool devptr = (p->flags & SIM5_FLAG_DEVICE_PTRS) != 0;
+    auto fail = [&](int rc) { job->rc = rc; job->err = g_ctx.last_error; };
+    if (devptr && job->device != job->dev0 && p->mode != SIM5_MODE_HISTOGRAM && p->mode != SIM5_MODE_SPECTRUM) {
+        /* this GPU stores its rows straight into the planes of devices[0] over NVLink */
+        Context& c = select_ctx(job->device);
+        std::lock_guard<std::mutex> lk(c.mu);
+        int rc = ensure_init(job->device);
+        if (rc) return fail(rc);
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, job->device, job->dev0);
+        if (!can) { set_error("sim5_trace_image_multi: no peer access to the device that owns the planes"); return fail(SIM5_ERR_NOT_IMPL); }
+        cudaError_t e = cudaDeviceEnablePeerAccess(job->dev0, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cuda_ok(e, "cudaDeviceEnablePeerAccess"); return fail(SIM5_ERR_CUDA); }
+        cudaGetLastError();
+    }
+    if (p->mode == SIM5_MODE_HISTOGRAM) {
+        /* partial lattice in this device's own buffer; sim5_trace_image_multi adds the buffers up on devices[0] */
+        size_t hbytes = (size_t)p->n_spin * p->n_incl * p->n_bins * sizeof(double);
+        {
+            Context& c = select_ctx(job->device);
+            std::lock_guard<std::mutex> lk(c.mu);
+            int rc = ensure_init(job->device);
+            if (!rc) rc = reserve(c.azq_f, hbytes);
+            if (rc) return fail(rc);
+            job->d_hist = (double*)c.azq_f.p;
+        }
+        sim5_image_out o = *job->out;
+        o.hist = job->d_hist;
+        q.flags |= SIM5_FLAG_DEVICE_PTRS;
+        q.split_count = job->ndev; q.split_index = job->index;
+        int rc = sim5_trace_image(&q, &o, &job->st);
+        if (rc) fail(rc);
+        return;
+    }
+    int rb = p->row_begin, re = p->row_end;
+    if (rb == 0 && re == 0) re = p->ny;
+    /* interleaved row blocks: 32-row blocks while they divide evenly, single rows for what is left, the last < ndev rows to device 0 */
+    const int nd = job->ndev;
+    const int srows_a = p->split_rows > 0 ? p->split_rows : 32;
+    const int rows = re - rb;
+    const int n_a = rows / (nd * srows_a) * (nd * srows_a);
+    const int n_b = (rows - n_a) / nd * nd;
+    const int seg_begin[3] = {rb, rb + n_a, rb + n_a + n_b};
+    const int seg_end[3]   = {rb + n_a, rb + n_a + n_b, re};
+    const int seg_srows[3] = {srows_a, 1, 0};
+    sim5_image_out o = *job->out;
+    if (p->mode == SIM5_MODE_SPECTRUM) { for (int k = 0; k < S5_SPEC_MAX_E; k++) job->spec[k] = 0.0; }
+    for (int sgm = 0; sgm < 3; sgm++) {
+        if (seg_end[sgm] <= seg_begin[sgm]) continue;
+        if (sgm == 2 && job->index != 0) continue;
+        q.row_begin = seg_begin[sgm]; q.row_end = seg_end[sgm];
+        if (sgm < 2) { q.split_count = nd; q.split_index = job->index; q.split_rows = seg_srows[sgm]; if (devptr) q.flags |= SIM5_FLAG_FULL_INDEX; }
+        else         { q.split_count = 0; q.split_index = 0; q.split_rows = 0; }
+        sim5_trace_stats st;
+        memset(&st, 0, sizeof st);
+        double part[S5_SPEC_MAX_E];
+        if (p->mode == SIM5_MODE_SPECTRUM) o.spectrum = part;
+        int rc = sim5_trace_image(&q, &o, &st);
+        if (rc) return fail(rc);
+        if (p->mode == SIM5_MODE_SPECTRUM) for (int k = 0; k < p->n_energy; k++) job->spec[k] += part[k];
+        add_stats(&job->st, st, true);
+    }
+}
+}
+
+/* THE batched entry on several GPUs of one box: the same arguments as sim5_trace_image plus the device list.  One host thread per
+ * device drives that device's context; image rows are dealt out in interleaved 32-row blocks (the expensive rows around the shadow go
+ * to all GPUs), lattice images of HISTOGRAM mode one by one.  Host planes: every GPU copies its rows to the caller's planes itself
+ * (its own PCIe link; chunks under its kernels).  SIM5_FLAG_DEVICE_PTRS: the planes live on devices[0] and the other GPUs store into
+ * them over NVLink (peer access, SIM5_FLAG_FULL_INDEX).  HISTOGRAM: each GPU accumulates its images, devices[0] adds the partial
+ * lattices up with loads from its peers' memory (k_sum_peers, fixed order).  SPECTRUM: partial sums added on the host.  p->device is
+ * ignored; SIM5_FLAG_ASYNC / _DEFER_REDO do not apply.  stats: counters summed, times = the slowest device. */
+extern "C" int sim5_trace_image_multi(const sim5_image_params* p, const sim5_image_out* out, sim5_trace_stats* stats, const int* devices, int ndev)
+{
+    if (!p || !out || !devices || ndev < 1 || ndev > S5_MAX_DEVICES) { set_error("sim5_trace_image_multi: bad arguments"); return SIM5_ERR_BAD_PARAM; }
+    if (p->struct_size != (int32_t)sizeof(sim5_image_params)) { set_error("sim5_image_params.struct_size mismatch"); return SIM5_ERR_BAD_PARAM; }
+    const int navail = sim5_gpu_device_count();
+    if (navail <= 0) return no_device("device count is 0");
+    for (int i = 0; i < ndev; i++) {
+        if (devices[i] < 0 || devices[i] >= navail || devices[i] >= S5_MAX_DEVICES) { set_error("sim5_trace_image_multi: device ordinal out of range"); return SIM5_ERR_BAD_PARAM; }
+        for (int j = 0; j < i; j++) if (devices[j] == devices[i]) { set_error("sim5_trace_image_multi: a device is listed twice"); return SIM5_ERR_BAD_PARAM; }
+    }
+    if (p->mode == SIM5_MODE_SPECTRUM && (p->n_energy < 1 || p->n_energy > S5_SPEC_MAX_E)) { set_error("bad spectrum grid"); return SIM5_ERR_BAD_PARAM; }
+    if (p->mode == SIM5_MODE_HISTOGRAM && !out->hist) { set_error("HISTOGRAM mode needs out->hist"); return SIM5_ERR_NO_OUTPUT; }
+    Context* caller = &g_ctx;
+    std::vector<MultiJob> jobs((size_t)ndev);
+    std::vector<std::thread> th;
+    for (int i = 0; i < ndev; i++) {
+        jobs[i].device = devices[i]; jobs[i].index = i; jobs[i].ndev = ndev; jobs[i].p = p; jobs[i].out = out; jobs[i].dev0 = devices[0];
+    }
+    for (int i = 1; i < ndev; i++) th.emplace_back(multi_worker, &jobs[i]);
+    multi_worker(&jobs[0]);                                  /* the calling thread drives devices[0] */
+    for (auto& t : th) t.join();
+    int rc = SIM5_OK;
+    for (int i = 0; i < ndev; i++) if (jobs[i].rc != SIM5_OK && rc == SIM5_OK) { rc = jobs[i].rc; caller->last_error = jobs[i].err; }
+    if (rc == SIM5_OK && p->mode == SIM5_MODE_HISTOGRAM) {
+        /* reduce on devices[0]: loads from the peers' partial lattices (staged through a peer copy where there is no peer access) */
+        Context& c = select_ctx(devices[0]);
+        std::lock_guard<std::mutex> lk(c.mu);
+        rc = ensure_init(devices[0]);
+        const long long n = (long long)p->n_spin * p->n_incl * p->n_bins;
+        s5::PeerPtrs src;
+        for (int i = 0; i < 16; i++) src.p[i] = nullptr;
+        size_t staged = 0;
+        for (int i = 0; i < ndev && rc == SIM5_OK; i++) {
+            src.p[i] = jobs[i].d_hist;
+            if (i == 0) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[0], devices[i]);
+            cudaError_t e = can ? cudaDeviceEnablePeerAccess(devices[i], 0) : cudaErrorPeerAccessUnsupported;
+            if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); continue; }
+            cudaGetLastError();
+            rc = reserve(c.azq2_f, (size_t)(ndev - 1) * n * sizeof(double));
+            if (rc) break;
+            double* stage = (double*)c.azq2_f.p + staged * n;
+            staged++;
+            if (!cuda_ok(cudaMemcpyPeerAsync(stage, devices[0], jobs[i].d_hist, devices[i], n * sizeof(double), c.stream), "cudaMemcpyPeerAsync")) { rc = SIM5_ERR_CUDA; break; }
+            src.p[i] = stage;
+        }
+        if (rc == SIM5_OK) {
+            double* dst = jobs[0].d_hist;
+            s5::k_sum_peers<<<c.sm_count * 4, 256, 0, c.stream>>>(dst, src, ndev, n);
+            bool okc = cuda_ok(cudaGetLastError(), "k_sum_peers");
+            if (okc) okc = cuda_ok(cudaMemcpyAsync(out->hist, dst, n * sizeof(double), (p->flags & SIM5_FLAG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream), "histogram copy");
+            if (okc) okc = cuda_ok(cudaStreamSynchronize(c.stream), "histogram reduce");
+            if (!okc) rc = SIM5_ERR_CUDA;
+        }
+        if (rc != SIM5_OK) caller->last_error = c.last_error;
+    }
+    if (rc == SIM5_OK && p->mode == SIM5_MODE_SPECTRUM) {
+        if (!out->spectrum) { set_error("SPECTRUM mode needs out->spectrum"); return SIM5_ERR_NO_OUTPUT; }
+        for (int k = 0; k < p->n_energy; k++) { double s = 0.0; for (int i = 0; i < ndev; i++) s += jobs[i].spec[k]; out->spectrum[k] = s; }
+    }
+    t_ctx = caller;
+    cudaSetDevice(caller->ready ? caller->device : devices[0]);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (int i = 0; i < ndev; i++) add_stats(stats, jobs[i].st, false);
+    }
+    return rc;
+}
+
 extern "C" int sim5_last_phase_ms(double* ms, int n, int64_t* items)
 {
     Context& c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.ready) CK(cudaSetDevice(c.device));
     if (!c.ready || !ms || n < 1) { set_error("sim5_last_phase_ms: no context / no output"); return SIM5_ERR_BAD_PARAM; }
     if (c.phases < 1) { set_error("sim5_last_phase_ms: no image call recorded"); return SIM5_ERR_BAD_PARAM; }
     CK(cudaEventSynchronize(c.ev2));
@@ -817,6 +1060,8 @@ extern "C" int sim5_last_phase_ms(double* ms, int n, int64_t* items)
 extern "C" int sim5_phase_history(int back, double* ms, int n)
 {
     Context& c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.ready) CK(cudaSetDevice(c.device));
     if (!c.ready || !ms || n < 1 || back < 0 || back >= S5_RING) { set_error("sim5_phase_history: bad arguments"); return SIM5_ERR_BAD_PARAM; }
     int pos = ((c.ring_pos - back) % S5_RING + S5_RING) % S5_RING;
     int phases = c.ring_phases[pos];
@@ -835,9 +1080,10 @@ extern "C" int sim5_phase_history(int back, double* ms, int n)
 /* ------------------------------------------------------------------ */
 extern "C" double sim5_fp64_peak_tflops(int device, int iters)
 {
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (device >= S5_MAX_DEVICES) return -1.0;
+    Context& c = select_ctx(device);
+    std::lock_guard<std::mutex> lk(c.mu);
     if (ensure_init(device) != SIM5_OK) return -1.0;
-    Context& c = g_ctx;
     if (iters < 1) iters = 4096;
     int grid = c.sm_count * 8;
     if (reserve(c.planes[0], 4096) != SIM5_OK) return -1.0;

@@ -99,7 +99,7 @@ static inline void s5_fill_image_consts(const sim5_image_params* p, S5ImageConst
     if (c->row_begin == 0 && c->row_end == 0) c->row_end = p->ny;
     c->split_count = p->split_count > 1 ? p->split_count : 1;
     c->split_index = p->split_count > 1 ? p->split_index : 0;
-    c->split_rows  = p->split_rows > 0 ? p->split_rows : 1;
+    c->split_rows  = (p->split_count > 1 && p->split_rows > 0) ? p->split_rows : 1;
     c->nrows_local = (c->row_end - c->row_begin) / c->split_count;
     c->max_order = p->max_order;
     c->mode = p->mode;

@@ -478,8 +478,11 @@ k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigne
 /* Same execution shape as k_trace_eqplane: CTAs of S5_EQ_THREADS threads in lockstep, one tile per warp and batch, the staged pixel
  * routine with its CTA barriers and the geodesic in shared-memory slots (r02f sweep: the former 128-thread free-running kernel
  * traced 2.5e9 rays/s, 2.8e9 at 64 registers).  A batch never straddles two lattice images, so the staged constants stay valid. */
+/* The launch traces the n_img lattice images img_first, img_first + img_stride, ... (one GPU's share of an interleaved deal of the
+ * lattice over split_count GPUs: neighbouring images -- neighbouring inclinations of one spin -- cost about the same, so every GPU
+ * gets the same mix). */
 __global__ void __launch_bounds__(S5_EQ_THREADS, S5_MIN_CTAS_EQ)
-k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice image */, int img_begin, int img_end,
+k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice image */, int img_first, int img_stride, int n_img,
                   double* __restrict__ hist, unsigned long long* __restrict__ tile_counter, DevStats* __restrict__ gstats)
 {
     __shared__ S5ImageConsts c;
@@ -492,11 +495,11 @@ k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice i
     const int lane = threadIdx.x & 31;
     const int wpc = S5_EQ_THREADS / 32;                 /* tiles per batch */
     /* all images share nx, ny */
-    const long long nx = gconsts[img_begin].nx;
-    const long long npix = (long long)gconsts[img_begin].ny * nx;
+    const long long nx = gconsts[img_first].nx;
+    const long long npix = (long long)gconsts[img_first].ny * nx;
     const long long tiles_per_img = (npix + 31) >> 5;
     const long long chunks_per_img = (tiles_per_img + wpc - 1) / wpc;
-    const long long nchunks = chunks_per_img * (long long)(img_end - img_begin);
+    const long long nchunks = chunks_per_img * (long long)n_img;
     __shared__ unsigned long long s_chunk;
 
     for (;;) {
@@ -505,7 +508,7 @@ k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice i
         __syncthreads();
         long long ch = (long long)s_chunk;
         if (ch >= nchunks) break;
-        int img = img_begin + (int)(ch / chunks_per_img);
+        int img = img_first + img_stride * (int)(ch / chunks_per_img);
         long long t = (ch % chunks_per_img) * wpc + (threadIdx.x >> 5);
         if (img != s_img) {
             __syncthreads();
@@ -556,6 +559,19 @@ k_trace_histogram(const S5ImageConsts* __restrict__ gconsts /* one per lattice i
         }
     }
     flush_stats(s_cnt, 0, gstats);
+}
+
+/* Reduction of the lattice histograms of a multi-GPU call (sim5_trace_image_multi): the GPU that owns the result adds up the partial
+ * histograms of all GPUs with plain loads from their memory (peer access over NVLink / NVSwitch; 4 MB per GPU) in a FIXED order, so the
+ * reduced histogram does not depend on timing.  dst may alias src.p[0]. */
+struct PeerPtrs { const double* p[16]; };
+__global__ void __launch_bounds__(256) k_sum_peers(double* dst, PeerPtrs src, int nsrc, long long n)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double s = src.p[0][i];
+        for (int k = 1; k < nsrc; k++) s += src.p[k][i];
+        dst[i] = s;
+    }
 }
 
 /* ------------------------------------------------------------------ */
