@@ -244,6 +244,10 @@ const char* sim5_version(void);
 /* pinned host memory for output planes (so the D2H leg of the call can overlap tracing) */
 void* sim5_host_alloc(size_t bytes);
 void  sim5_host_free(void* p);
+/* page-lock / release caller-owned host memory (cudaHostRegister): e.g. one shared-memory image that the ranks of a one-process-per-GPU
+ * job all map, each copying its own rows into it over its own PCIe link */
+int   sim5_host_register(void* p, size_t bytes);
+int   sim5_host_unregister(void* p);
 /* device memory helpers for SIM5_FLAG_DEVICE_PTRS users (e.g. a torch tensor's data_ptr works too) */
 void* sim5_device_alloc(size_t bytes);
 void  sim5_device_free(void* p);

@@ -44,6 +44,10 @@ def lib():
         L.sim5_host_alloc.argtypes = [C.c_size_t]
         L.sim5_host_alloc.restype = C.c_void_p
         L.sim5_host_free.argtypes = [C.c_void_p]
+        L.sim5_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.sim5_host_register.restype = C.c_int
+        L.sim5_host_unregister.argtypes = [C.c_void_p]
+        L.sim5_host_unregister.restype = C.c_int
         L.sim5_device_alloc.argtypes = [C.c_size_t]
         L.sim5_device_alloc.restype = C.c_void_p
         L.sim5_device_free.argtypes = [C.c_void_p]

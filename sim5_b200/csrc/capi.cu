@@ -502,6 +502,23 @@ extern "C" void* sim5_host_alloc(size_t bytes)
     return p;
 }
 extern "C" void sim5_host_free(void* p) { if (p) cudaFreeHost(p); }
+/* page-lock caller-owned host memory (e.g. a shared-memory segment that several one-process-per-GPU ranks map: every rank registers it and
+ * copies its own rows into the one image), so that the device->host copies of a host-plane call run asynchronously under its kernels */
+extern "C" int sim5_host_register(void* p, size_t bytes)
+{
+    if (!p || !bytes) { set_error("sim5_host_register: null argument"); return SIM5_ERR_BAD_PARAM; }
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    int rc = ensure_init(-1);
+    if (rc) return rc;
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return SIM5_OK;
+}
+extern "C" int sim5_host_unregister(void* p)
+{
+    if (!p) return SIM5_OK;
+    CK(cudaHostUnregister(p));
+    return SIM5_OK;
+}
 extern "C" void* sim5_device_alloc(size_t bytes)
 {
     std::lock_guard<std::mutex> lk(g_ctx.mu);

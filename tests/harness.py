@@ -146,9 +146,11 @@ def err_summary(x, ref, floor=0.0):
 # tolerances of BASELINE.json's north_star: bit-exact classification / termination flags;
 # relative error <= 1e-9 on r, phi, g and <= 1e-7 on the polarization angle and flux.
 TOL = {"r": 1e-9, "phi": 1e-9, "g": 1e-9, "flux": 1e-7, "chi": 1e-7, "delta": 1e-7, "mue": 1e-9,
-       "intensity": 1e-7, "tau": 1e-7, "qerr": None, "height": 1e-9, "delay": 1e-9}
-FLOOR = {"phi": 1.0, "chi": 1.0, "height": 1.0}   # |dphi| / max(|phi|, 1): phi ~ 1e-5 on the alpha ~ 0 column; the height
-                                                   # r cos(theta) of a SURFACE hit passes through zero at the inner edge of the disk
+       "intensity": 1e-7, "tau": 1e-7, "qerr": 1e-9, "height": 1e-9, "delay": 1e-9}
+FLOOR = {"phi": 1.0, "chi": 1.0, "height": 1.0, "qerr": 1.0}
+# |dphi| / max(|phi|, 1): phi ~ 1e-5 on the alpha ~ 0 column; the height r cos(theta) of a SURFACE hit passes through
+# zero at the inner edge of the disk; qerr = raytrace_error() IS a relative error (the drift |Q - Q0| / Q0 of Carter's constant, 1e-10
+# ... 1e-3: a difference of two nearly equal numbers), so it is held to an ABSOLUTE 1e-9
 
 
 def assert_image_parity(got, ref, label="", tol=TOL):
