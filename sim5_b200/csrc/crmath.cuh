@@ -59,6 +59,29 @@ static __device__ const double crm_atantab_dev[65][2] = CRM_ATANTAB_INIT;
 #define CRM_ATANTAB(i, k) crm_atantab_host[i][k]
 #endif
 
+/* The polynomial coefficients and split constants as a constant-bank table: in SASS a 64-bit literal costs two UMOV / MOV per use
+ * (profiles/r04k: 5 percent of phase A's executed instructions were UMOV, and the kernels are instruction-issue bound), a c[bank][offset]
+ * operand of DFMA / DADD / DMUL costs nothing.  Same values: the table is initialised from the constexpr literals of crmath_tables.h. */
+#define CRM_KLIST(X) X(PI_H) X(PI_L) X(PI_2_H) X(PI_2_L) X(2_PI) X(PIO2_1) X(PIO2_2) X(PIO2_3) X(PIO2_4) X(LN2_HEAD) X(LN2_MID) X(LN2_TAIL) X(S1_H) X(S1_L) X(S2_H) X(S2_L) X(S3_H) X(S3_L) X(SQ0) X(SQ1) X(SQ2) X(SQ3) X(SQ4) X(SQ5) X(SQ6) X(SQ7) X(C2_H) X(C2_L) X(C3_H) X(C3_L) X(CQ0) X(CQ1) X(CQ2) X(CQ3) X(CQ4) X(CQ5) X(CQ6) X(CQ7) X(LP1) X(LP2) X(LP3) X(LP4) X(LP5) X(LP6) X(LP7) X(LP8) X(THIRD_H) X(THIRD_L) X(AT0) X(AT1) X(AT2) X(AT3) X(AT4) X(AT5)
+enum {
+#define X(n) KCI_##n,
+    CRM_KLIST(X)
+#undef X
+    KCI_COUNT
+};
+#if defined(__CUDACC__)
+static __constant__ double crm_kc_dev[KCI_COUNT] = {
+#define X(n) CRM_##n,
+    CRM_KLIST(X)
+#undef X
+};
+#endif
+#if defined(__CUDA_ARCH__) && !defined(S5_CRM_LITERALS)
+#define KC(n) crm_kc_dev[KCI_##n]
+#else
+#define KC(n) CRM_##n
+#endif
+
 /* ---- exact building blocks (never contracted, never reassociated) ---- */
 S5_HD S5_INL double fma_(double a, double b, double c)
 {
@@ -228,13 +251,13 @@ S5_HD S5_INL dd sin_kernel(dd r)                      /* |r| <= pi/4 (+eps) */
 {
     dd z = dd_sqr(r);
     double zh = z.h;
-    double q = CRM_SQ7;
-    q = fma_(q, zh, CRM_SQ6); q = fma_(q, zh, CRM_SQ5); q = fma_(q, zh, CRM_SQ4);
-    q = fma_(q, zh, CRM_SQ3); q = fma_(q, zh, CRM_SQ2); q = fma_(q, zh, CRM_SQ1);
-    q = fma_(q, zh, CRM_SQ0);
-    dd t = fast_two_sum(CRM_S3_H, fma_(zh, q, CRM_S3_L));
-    t = dd_add_fast(dd{CRM_S2_H, CRM_S2_L}, dd_mul(z, t));
-    t = dd_add_fast(dd{CRM_S1_H, CRM_S1_L}, dd_mul(z, t));
+    double q = KC(SQ7);
+    q = fma_(q, zh, KC(SQ6)); q = fma_(q, zh, KC(SQ5)); q = fma_(q, zh, KC(SQ4));
+    q = fma_(q, zh, KC(SQ3)); q = fma_(q, zh, KC(SQ2)); q = fma_(q, zh, KC(SQ1));
+    q = fma_(q, zh, KC(SQ0));
+    dd t = fast_two_sum(KC(S3_H), fma_(zh, q, KC(S3_L)));
+    t = dd_add_fast(dd{KC(S2_H), KC(S2_L)}, dd_mul(z, t));
+    t = dd_add_fast(dd{KC(S1_H), KC(S1_L)}, dd_mul(z, t));
     dd w = dd_mul(dd_mul(r, z), t);
     return dd_add_fast(r, w);
 }
@@ -242,12 +265,12 @@ S5_HD S5_INL dd cos_kernel(dd r)
 {
     dd z = dd_sqr(r);
     double zh = z.h;
-    double q = CRM_CQ7;
-    q = fma_(q, zh, CRM_CQ6); q = fma_(q, zh, CRM_CQ5); q = fma_(q, zh, CRM_CQ4);
-    q = fma_(q, zh, CRM_CQ3); q = fma_(q, zh, CRM_CQ2); q = fma_(q, zh, CRM_CQ1);
-    q = fma_(q, zh, CRM_CQ0);
-    dd t = fast_two_sum(CRM_C3_H, fma_(zh, q, CRM_C3_L));
-    t = dd_add_fast(dd{CRM_C2_H, CRM_C2_L}, dd_mul(z, t));
+    double q = KC(CQ7);
+    q = fma_(q, zh, KC(CQ6)); q = fma_(q, zh, KC(CQ5)); q = fma_(q, zh, KC(CQ4));
+    q = fma_(q, zh, KC(CQ3)); q = fma_(q, zh, KC(CQ2)); q = fma_(q, zh, KC(CQ1));
+    q = fma_(q, zh, KC(CQ0));
+    dd t = fast_two_sum(KC(C3_H), fma_(zh, q, KC(C3_L)));
+    t = dd_add_fast(dd{KC(C2_H), KC(C2_L)}, dd_mul(z, t));
     dd v = dd_mul(dd_sqr(z), t);
     dd u = fast_two_sum(1.0, -0.5 * z.h);
     u.l = add_(u.l, -0.5 * z.l);
@@ -258,11 +281,11 @@ S5_HD S5_INL dd cos_kernel(dd r)
 S5_HD S5_INL int reduce_pio2(double x, dd& r)
 {
     if (fabs(x) <= 0.78539816339744828) { r = dd{x, 0.0}; return 0; }
-    double k = rint(x * CRM_2_PI);
-    double a = fma_(-k, CRM_PIO2_1, x);               /* exact */
-    dd s = two_sum(a, -mul_(k, CRM_PIO2_2));          /* k*PIO2_2 exact */
-    s = dd_add_d(s, -mul_(k, CRM_PIO2_3));            /* exact product */
-    dd p4 = two_prod(k, CRM_PIO2_4);
+    double k = rint(x * KC(2_PI));
+    double a = fma_(-k, KC(PIO2_1), x);               /* exact */
+    dd s = two_sum(a, -mul_(k, KC(PIO2_2)));          /* k*PIO2_2 exact */
+    s = dd_add_d(s, -mul_(k, KC(PIO2_3)));            /* exact product */
+    dd p4 = two_prod(k, KC(PIO2_4));
     s = dd_add(s, dd_neg(p4));
     r = s;
     return (int)((long long)k & 3);
@@ -289,7 +312,25 @@ S5_HD S5_NOINL void cr_sincos(double x, double* sn, double* cs)
     }
 }
 S5_HD S5_INL double cr_sin(double x) { double s, c; cr_sincos(x, &s, &c); return s; }
-S5_HD S5_INL double cr_cos(double x) { double s, c; cr_sincos(x, &s, &c); return c; }
+/* cos alone evaluates ONE of the two kernels (the quadrant says which): the same value as the cosine of cr_sincos, half its work
+ * (the stepper calls it three times per raytrace() step, the radial roots once per ray) */
+S5_HD S5_NOINL double cr_cos(double x)
+{
+#if defined(S5_COS_VIA_SINCOS)
+    double s, c; cr_sincos(x, &s, &c); return c;
+#else
+    double ax = fabs(x);
+    if (!(ax < 1.0e6)) {
+        if (ax != ax || ax > 1.7976931348623157e308) return x - x;
+        return cos(x);
+    }
+    if (ax < 7.450580596923828e-09) return 1.0;
+    dd r;
+    int k = reduce_pio2(x, r);
+    double v = (k & 1) ? sin_kernel(r).h : cos_kernel(r).h;
+    return (k == 1 || k == 2) ? -v : v;          /* k = 0: +cos r, 1: -sin r, 2: -cos r, 3: +sin r */
+#endif
+}
 
 /* ================================================================== */
 /* log                                                                 */
@@ -310,22 +351,22 @@ S5_HD S5_NOINL double log_core(double x, double xl)
     double c = CRM_LOGTAB(i, 0), lch = CRM_LOGTAB(i, 1), lcl = CRM_LOGTAB(i, 2);
     double r = fma_(m, c, -1.0);                       /* exact, |r| < 2^-7 */
     dd r2 = two_prod(r, r);
-    double p = CRM_LP8;
-    p = fma_(p, r, CRM_LP7); p = fma_(p, r, CRM_LP6); p = fma_(p, r, CRM_LP5); p = fma_(p, r, CRM_LP4);
-    p = fma_(p, r, CRM_LP3); p = fma_(p, r, CRM_LP2); p = fma_(p, r, CRM_LP1);
+    double p = KC(LP8);
+    p = fma_(p, r, KC(LP7)); p = fma_(p, r, KC(LP6)); p = fma_(p, r, KC(LP5)); p = fma_(p, r, KC(LP4));
+    p = fma_(p, r, KC(LP3)); p = fma_(p, r, KC(LP2)); p = fma_(p, r, KC(LP1));
     /* 1/3 + r*p with 1/3 in double-double so the r^3/3 term is good to ~2^-70 of the result */
-    double t3h = fma_(p, r, CRM_THIRD_H);
+    double t3h = fma_(p, r, KC(THIRD_H));
     double r3  = mul_(r, r2.h);
-    double t3  = fma_(r3, t3h, mul_(r3, CRM_THIRD_L));
+    double t3  = fma_(r3, t3h, mul_(r3, KC(THIRD_L)));
     if (xl != 0.0) t3 = add_(t3, (xl / scale) * c / (1.0 + r));   /* d/dr log1p(r) * dr */
     double ed = (double)e;
-    dd s1 = two_sum(mul_(ed, CRM_LN2_HEAD), lch);       /* e*HEAD exact (42-bit head) */
+    dd s1 = two_sum(mul_(ed, KC(LN2_HEAD)), lch);       /* e*HEAD exact (42-bit head) */
     dd s2 = two_sum(s1.h, r);
     dd s3 = two_sum(s2.h, -0.5 * r2.h);
     double low = add_(add_(s1.l, s2.l), s3.l);
-    low = add_(low, fma_(ed, CRM_LN2_MID, lcl));
+    low = add_(low, fma_(ed, KC(LN2_MID), lcl));
     low = add_(low, fma_(-0.5, r2.l, t3));
-    low = fma_(ed, CRM_LN2_TAIL, low);
+    low = fma_(ed, KC(LN2_TAIL), low);
     return add_(s3.h, low);
 }
 S5_HD S5_INL double cr_log(double x) { return log_core(x, 0.0); }
@@ -357,9 +398,9 @@ S5_HD S5_INL dd atan_kernel(dd x)                      /* 0 <= x <= 1 (+eps) */
         t = dd_div(num, den);
     }
     double th = t.h, z = mul_(th, th);
-    double p = CRM_AT5;
-    p = fma_(p, z, CRM_AT4); p = fma_(p, z, CRM_AT3); p = fma_(p, z, CRM_AT2);
-    p = fma_(p, z, CRM_AT1); p = fma_(p, z, CRM_AT0);
+    double p = KC(AT5);
+    p = fma_(p, z, KC(AT4)); p = fma_(p, z, KC(AT3)); p = fma_(p, z, KC(AT2));
+    p = fma_(p, z, KC(AT1)); p = fma_(p, z, KC(AT0));
     double w = mul_(mul_(th, z), p);
     if (j == 0) return fast_two_sum(t.h, add_(t.l, w));
     dd s = two_sum(CRM_ATANTAB(j, 0), t.h);
@@ -371,7 +412,7 @@ S5_HD S5_INL dd atan_ratio(dd num, dd den)
 {
     if (num.h > den.h || (num.h == den.h && num.l > den.l)) {
         dd a = atan_kernel(dd_div(den, num));
-        return dd_add(dd{CRM_PI_2_H, CRM_PI_2_L}, dd_neg(a));
+        return dd_add(dd{KC(PI_2_H), KC(PI_2_L)}, dd_neg(a));
     }
     return atan_kernel(dd_div(num, den));
 }
@@ -380,24 +421,24 @@ S5_HD S5_NOINL double cr_atan2(double y, double x)
     if (x != x || y != y) return x + y;
     double ay = fabs(y), ax = fabs(x);
     bool xneg = bits_of(x) < 0;
-    if (ay == 0.0) return xneg ? copysign(CRM_PI_H, y) : y;
-    if (ax == 0.0) return copysign(CRM_PI_2_H, y);
+    if (ay == 0.0) return xneg ? copysign(KC(PI_H), y) : y;
+    if (ax == 0.0) return copysign(KC(PI_2_H), y);
     const double INF = inf_();
     if (ax == INF || ay == INF) {
         double v;
         if (ax == INF && ay == INF) v = xneg ? 2.356194490192345 : 0.7853981633974483;
-        else if (ax == INF)         v = xneg ? CRM_PI_H : 0.0;
-        else                        v = CRM_PI_2_H;
+        else if (ax == INF)         v = xneg ? KC(PI_H) : 0.0;
+        else                        v = KC(PI_2_H);
         return copysign(v, y);
     }
     dd a;
     if (ay > ax) {
         a = atan_kernel(dd_div_dd_d(ax, ay));
-        a = dd_add(dd{CRM_PI_2_H, CRM_PI_2_L}, dd_neg(a));
+        a = dd_add(dd{KC(PI_2_H), KC(PI_2_L)}, dd_neg(a));
     } else {
         a = atan_kernel(dd_div_dd_d(ay, ax));
     }
-    if (xneg) a = dd_add(dd{CRM_PI_H, CRM_PI_L}, dd_neg(a));
+    if (xneg) a = dd_add(dd{KC(PI_H), KC(PI_L)}, dd_neg(a));
     return copysign(a.h, y);
 }
 S5_HD S5_NOINL double cr_atan(double x)
@@ -407,9 +448,9 @@ S5_HD S5_NOINL double cr_atan(double x)
     if (ax < 7.450580596923828e-09) return x;
     dd a;
     if (ax > 1.0) {
-        if (ax > 1.7976931348623157e308) return copysign(CRM_PI_2_H, x);
+        if (ax > 1.7976931348623157e308) return copysign(KC(PI_2_H), x);
         a = atan_kernel(dd_div_dd_d(1.0, ax));
-        a = dd_add(dd{CRM_PI_2_H, CRM_PI_2_L}, dd_neg(a));
+        a = dd_add(dd{KC(PI_2_H), KC(PI_2_L)}, dd_neg(a));
     } else {
         a = atan_kernel(dd{ax, 0.0});
     }
@@ -426,10 +467,10 @@ S5_HD S5_NOINL double cr_acos(double x)
 {
     double ax = fabs(x);
     if (!(ax <= 1.0)) return (x - x) / (x - x);
-    if (ax == 1.0) return x > 0.0 ? 0.0 : CRM_PI_H;
+    if (ax == 1.0) return x > 0.0 ? 0.0 : KC(PI_H);
     dd s = sqrt_1mx2(ax);
     dd a = atan_ratio(s, dd{ax, 0.0});
-    if (x < 0.0) a = dd_add(dd{CRM_PI_H, CRM_PI_L}, dd_neg(a));
+    if (x < 0.0) a = dd_add(dd{KC(PI_H), KC(PI_L)}, dd_neg(a));
     return a.h;
 }
 S5_HD S5_NOINL double cr_asin(double x)
@@ -437,7 +478,7 @@ S5_HD S5_NOINL double cr_asin(double x)
     double ax = fabs(x);
     if (!(ax <= 1.0)) return (x - x) / (x - x);
     if (ax < 7.450580596923828e-09) return x;
-    if (ax == 1.0) return copysign(CRM_PI_2_H, x);
+    if (ax == 1.0) return copysign(KC(PI_2_H), x);
     dd s = sqrt_1mx2(ax);
     dd a = atan_ratio(dd{ax, 0.0}, s);
     return copysign(a.h, x);

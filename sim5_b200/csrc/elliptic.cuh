@@ -204,11 +204,14 @@ S5_HD S5_INL double rf_core(double x, double y, double z)
         y = 0.25 * (y + lam);
         z = 0.25 * (z + lam);
         mu = THIRD * (x + y + z);
-        ff::Rcp rmu = ff::rcp_of(mu);
-        dx = ff::fdiv_nc(mu - x, rmu);
-        dy = ff::fdiv_nc(mu - y, rmu);
-        dz = ff::fdiv_nc(mu - z, rmu);
-        if (!(above_tol(dx) || above_tol(dy) || above_tol(dz))) break;     /* == !(max3(|dx|,|dy|,|dz|) > tol) */
+        const double ex = mu - x, ey = mu - y, ez = mu - z;
+        if (!ff::surely_above_tol(ff::imax_(ff::imax_(ff::hi_abs(ex), ff::hi_abs(ey)), ff::hi_abs(ez)), mu)) {
+            ff::Rcp rmu = ff::rcp_of(mu);
+            dx = ff::fdiv_nc(ex, rmu);
+            dy = ff::fdiv_nc(ey, rmu);
+            dz = ff::fdiv_nc(ez, rmu);
+            if (!(above_tol(dx) || above_tol(dy) || above_tol(dz))) break;     /* == !(max3(|dx|,|dy|,|dz|) > tol) */
+        }
         sx = ff::fsqrt_nc(x); sy = ff::fsqrt_nc(y); sz = ff::fsqrt_nc(z);
     }
     double e2 = dx * dy - dz * dz;
@@ -237,8 +240,11 @@ S5_HD S5_INL double rc_pos_core(double x, double y, double sx)
         x = 0.25 * (x + lam);
         y = 0.25 * (y + lam);
         mu = THIRD * (x + y + y);
-        s = ff::fdiv_nc(y - mu, mu);
-        if (!above_tol(s)) break;
+        const double ey = y - mu;
+        if (!ff::surely_above_tol(ff::hi_abs(ey), mu)) {
+            s = ff::fdiv_nc(ey, mu);
+            if (!above_tol(s)) break;
+        }
         sx = ff::fsqrt_nc(x); sy = ff::fsqrt_nc(y);
     }
     return ff::fdiv_nc(1.0 + s * s * (K1 + s * (K2 + s * (K3 + s * K4))), ff::fsqrt_nc(mu));      /* pre == 1: 1.0 * v == v */
@@ -259,8 +265,11 @@ S5_HD S5_INL double rc_neg_core(double x, double y)
         x = 0.25 * (x + lam);
         y = 0.25 * (y + lam);
         mu = THIRD * (x + y + y);
-        s = ff::fdiv_nc(y - mu, mu);
-        if (!above_tol(s)) break;
+        const double ey = y - mu;
+        if (!ff::surely_above_tol(ff::hi_abs(ey), mu)) {
+            s = ff::fdiv_nc(ey, mu);
+            if (!above_tol(s)) break;
+        }
         sx = ff::fsqrt_nc(x); sy = ff::fsqrt_nc(y);
     }
     return ff::fdiv_nc(pre * (1.0 + s * s * (K1 + s * (K2 + s * (K3 + s * K4)))), ff::fsqrt_nc(mu));
@@ -326,13 +335,16 @@ S5_HD S5_INL void rfj_shared_core(double x, double y, double z, const double* p,
         double s3 = x + y + z;
         if (WANT_RF && !fdone) {
             double mu = THIRD * s3;
+            const double ex = mu - x, ey = mu - y, ez = mu - z;
+            if (!ff::surely_above_tol(ff::imax_(ff::imax_(ff::hi_abs(ex), ff::hi_abs(ey)), ff::hi_abs(ez)), mu)) {
             ff::Rcp rmu = ff::rcp_of(mu);
-            double dx = ff::fdiv_nc(mu - x, rmu), dy = ff::fdiv_nc(mu - y, rmu), dz = ff::fdiv_nc(mu - z, rmu);
+            double dx = ff::fdiv_nc(ex, rmu), dy = ff::fdiv_nc(ey, rmu), dz = ff::fdiv_nc(ez, rmu);
             if (!(above_tol(dx) || above_tol(dy) || above_tol(dz))) {
                 double e2 = dx * dy - dz * dz;
                 double e3 = dx * dy * dz;
                 *rf_out = ff::fdiv_nc(1.0 + (F1 * e2 - F2 - F3 * e3) * e2 + F4 * e3, ff::fsqrt_nc(mu));
                 fdone = true;
+            }
             }
         }
         bool all = fdone;
@@ -340,11 +352,14 @@ S5_HD S5_INL void rfj_shared_core(double x, double y, double z, const double* p,
         for (int k = 0; k < NJ; k++) {
             if (SOLO || !jdone[k]) {
                 double mu = S5KC(KC_FIFTH) * (s3 + pt[k] + pt[k]);
-                ff::Rcp rmu = ff::rcp_of(mu);
-                double dx = ff::fdiv_nc(mu - x, rmu), dy = ff::fdiv_nc(mu - y, rmu), dz = ff::fdiv_nc(mu - z, rmu), dp = ff::fdiv_nc(mu - pt[k], rmu);
-                if (!(above_tol(dx) || above_tol(dy) || above_tol(dz) || above_tol(dp))) {
-                    rj_out[k] = rj_tail(acc[k], w, mu, dx, dy, dz, dp);
-                    jdone[k] = true;
+                const double ex = mu - x, ey = mu - y, ez = mu - z, ep = mu - pt[k];
+                if (!ff::surely_above_tol(ff::imax_(ff::imax_(ff::hi_abs(ex), ff::hi_abs(ey)), ff::imax_(ff::hi_abs(ez), ff::hi_abs(ep))), mu)) {
+                    ff::Rcp rmu = ff::rcp_of(mu);
+                    double dx = ff::fdiv_nc(ex, rmu), dy = ff::fdiv_nc(ey, rmu), dz = ff::fdiv_nc(ez, rmu), dp = ff::fdiv_nc(ep, rmu);
+                    if (!(above_tol(dx) || above_tol(dy) || above_tol(dz) || above_tol(dp))) {
+                        rj_out[k] = rj_tail(acc[k], w, mu, dx, dy, dz, dp);
+                        jdone[k] = true;
+                    }
                 }
             }
             all = all && jdone[k];
@@ -391,9 +406,12 @@ S5_HD S5_INL double rj_neg_core(double x, double y, double z, double p)
         zt = 0.25 * (zt + lam);
         pt = 0.25 * (pt + lam);
         mu = S5KC(KC_FIFTH) * (xt + yt + zt + pt + pt);
-        ff::Rcp rmu = ff::rcp_of(mu);
-        dx = ff::fdiv_nc(mu - xt, rmu); dy = ff::fdiv_nc(mu - yt, rmu); dz = ff::fdiv_nc(mu - zt, rmu); dp = ff::fdiv_nc(mu - pt, rmu);
-        if (!(above_tol(dx) || above_tol(dy) || above_tol(dz) || above_tol(dp))) break;
+        const double ex = mu - xt, ey = mu - yt, ez = mu - zt, ep = mu - pt;
+        if (!ff::surely_above_tol(ff::imax_(ff::imax_(ff::hi_abs(ex), ff::hi_abs(ey)), ff::imax_(ff::hi_abs(ez), ff::hi_abs(ep))), mu)) {
+            ff::Rcp rmu = ff::rcp_of(mu);
+            dx = ff::fdiv_nc(ex, rmu); dy = ff::fdiv_nc(ey, rmu); dz = ff::fdiv_nc(ez, rmu); dp = ff::fdiv_nc(ep, rmu);
+            if (!(above_tol(dx) || above_tol(dy) || above_tol(dz) || above_tol(dp))) break;
+        }
         sx = ff::fsqrt_nc(xt); sy = ff::fsqrt_nc(yt); sz = ff::fsqrt_nc(zt);
     }
     double res = rj_tail(acc, w, mu, dx, dy, dz, dp);
