@@ -34,6 +34,7 @@ namespace {
 #define S5_DEFER_REDO_CTAS 32      /* grid of a deferred redo pass: it runs beside the next call's tracing kernel */
 #endif
 #define S5_MAX_CHUNKS 32
+#define S5_BLK_WORDS (8 + sizeof(DevStats) / sizeof(unsigned long long))      /* counters + stats of one call, in 64-bit words */
 #define S5_CHUNK_RAYS (1 << 21)     /* rays per chunk of a host-plane call: ~1.1 ms of kernels, ~1.2 ms of PCIe.  4096^2 r/phi/g/flux/status end to end
                                        (profiles/r01x_sweep.log, ms): 2^18 13.6, 2^19 13.6, 2^20 11.9, 2^21 11.4, 2^22 12.2, 2^23 14.4 */
 
@@ -62,6 +63,8 @@ struct Context {
 #define S5_RING 64
     cudaEvent_t ring[S5_RING][5] = {{nullptr}};
     int ring_phases[S5_RING] = {0};
+    bool ring_defer[S5_RING] = {false};      /* the slot's call left its redo passes on the auxiliary stream: it ends at evp[1], no third phase */
+    bool last_defer = false;
     int ring_pos = 0;
     cudaEvent_t ev_chunk[S5_MAX_CHUNKS] = {nullptr};      /* chunk k traced -> its device->host copy may start */
     cudaEvent_t ev_copy_done = nullptr;
@@ -176,13 +179,16 @@ int ensure_init(int device)
     c.consts_cap = 1;
     CK(cudaHostAlloc((void**)&c.h_consts, sizeof(S5ImageConsts), cudaHostAllocDefault));
     CK(cudaMalloc((void**)&c.d_consts, sizeof(S5ImageConsts)));
-    CK(cudaMalloc((void**)&c.d_counter, 8 * sizeof(unsigned long long)));   /* [0..2] tile counters, [4..5] queue counts */
-    CK(cudaMalloc((void**)&c.d_counter2, 16 * sizeof(unsigned long long)));
+    /* three blocks of {8 counters ([0..2] tile counters, [4..7] queue counts), DevStats}: the default one and the two alternating sets of
+     * SIM5_FLAG_DEFER_REDO trains.  Counters and stats of a call are adjacent, so ONE memset per call clears both */
+    static_assert(sizeof(DevStats) % sizeof(unsigned long long) == 0, "DevStats is made of 64-bit counters");
+    CK(cudaMalloc((void**)&c.d_counter, 3 * S5_BLK_WORDS * sizeof(unsigned long long)));
+    c.d_counter2 = c.d_counter + S5_BLK_WORDS;
     CK(cudaEventCreateWithFlags(&c.ev_redo_done[0], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.ev_redo_done[1], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.ev_fast_done, cudaEventDisableTiming));
     c.redo_pending[0] = c.redo_pending[1] = false; c.defer_buf = 0; c.last_counts = c.d_counter + 4;
-    CK(cudaMalloc((void**)&c.d_stats, sizeof(DevStats)));
+    c.d_stats = (DevStats*)(c.d_counter + 8);
     CK(cudaHostAlloc((void**)&c.h_stats, sizeof(DevStats), cudaHostAllocDefault));
     /* the stepper keeps ~100 doubles of live state per thread and calls non-inlined Carlson routines */
     cudaDeviceSetLimit(cudaLimitStackSize, 8192);
@@ -410,10 +416,10 @@ void shutdown_ctx(Context& c)
     if (c.azq2_f.p) cudaFree(c.azq2_f.p); c.azq2_f = Plane();
     if (c.azq2_key.p) cudaFree(c.azq2_key.p); c.azq2_key = Plane();
     if (c.azq2_redo.p) cudaFree(c.azq2_redo.p); c.azq2_redo = Plane();
-    cudaFree(c.d_counter2); c.d_counter2 = nullptr;
+    c.d_counter2 = nullptr;
     cudaEventDestroy(c.ev_redo_done[0]); cudaEventDestroy(c.ev_redo_done[1]); cudaEventDestroy(c.ev_fast_done);
     for (int i = 0; i < 8; i++) { if (c.batch[i]) cudaFree(c.batch[i]); c.batch[i] = nullptr; c.batch_bytes[i] = 0; }
-    cudaFreeHost(c.h_scr); cudaFreeHost(c.h_consts); cudaFree(c.d_consts); cudaFree(c.d_counter); cudaFree(c.d_stats); cudaFreeHost(c.h_stats);
+    cudaFreeHost(c.h_scr); cudaFreeHost(c.h_consts); cudaFree(c.d_consts); cudaFree(c.d_counter); c.d_counter = nullptr; c.d_stats = nullptr; cudaFreeHost(c.h_stats);
     cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev3);
     for (int k = 0; k < S5_RING; k++) for (int i = 0; i < 5; i++) cudaEventDestroy(c.ring[k][i]);
     for (int i = 0; i < S5_MAX_CHUNKS; i++) cudaEventDestroy(c.ev_chunk[i]);
@@ -710,7 +716,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         const int b = c.defer_buf;
         c.defer_buf ^= 1;
         rc = join_deferred(c, b); if (rc) return rc;
-        cnt = c.d_counter2 + 8 * b;
+        cnt = c.d_counter2 + S5_BLK_WORDS * b;
         if (b == 1) {
             size_t qpix = (size_t)q.cap;
             rc = reserve(c.azq2_f, qpix * S5_AZ_NFIELDS * sizeof(double)); if (rc) return rc;
@@ -727,10 +733,10 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     c.ev1 = c.ring[c.ring_pos][0]; c.evp[0] = c.ring[c.ring_pos][1]; c.evp[1] = c.ring[c.ring_pos][2]; c.evp[2] = c.ring[c.ring_pos][3];
     c.ev2 = c.ring[c.ring_pos][4];
     c.ring_phases[c.ring_pos] = 0;
-    CK(cudaEventRecord(c.ev0, c.stream));
-    CK(cudaMemsetAsync(c.d_stats, 0, sizeof(DevStats), c.stream));
+    DevStats* const d_stats = (DevStats*)(cnt + 8);          /* this call's stats sit behind its counters */
     int grid = 0, launches = 0;
-    CK(cudaEventRecord(c.ev1, c.stream));
+    if (npix == 0) CK(cudaMemsetAsync(cnt, 0, S5_BLK_WORDS * sizeof(unsigned long long), c.stream));
+    CK(cudaEventRecord(c.ev1, c.stream));                    /* start of the call (one memset of 400 bytes precedes the first kernel) */
     for (int ch = 0; ch < nchunks && npix > 0; ch++) {
         int lr0 = chunk_lr[ch];
         int lrows = chunk_lr[ch + 1] - lr0;
@@ -747,20 +753,20 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                 set_dev_plane(&dd, i, (char*)c.planes[i].p + pix0 * kPlaneInfo[i].elem);
             }
         }
-        CK(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), c.stream));
+        CK(cudaMemsetAsync(cnt, 0, (ch == 0 ? S5_BLK_WORDS : 8) * sizeof(unsigned long long), c.stream));      /* counters per chunk, stats once */
         if (p->mode == SIM5_MODE_STEPWISE) {
             grid = persistent_grid(s5::k_trace_lanes<s5::StepwiseProg>, s5::StepwiseProg::THREADS);
-            s5::k_trace_lanes<s5::StepwiseProg><<<grid, s5::StepwiseProg::THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
+            s5::k_trace_lanes<s5::StepwiseProg><<<grid, s5::StepwiseProg::THREADS, 0, c.stream>>>(cc, dd, cnt, d_stats);
         } else if (p->mode == SIM5_MODE_SURFACE) {
             grid = persistent_grid(s5::k_trace_lanes<s5::SurfaceProg>, s5::SurfaceProg::THREADS);
-            s5::k_trace_lanes<s5::SurfaceProg><<<grid, s5::SurfaceProg::THREADS, 0, c.stream>>>(cc, dd, c.d_counter, c.d_stats);
+            s5::k_trace_lanes<s5::SurfaceProg><<<grid, s5::SurfaceProg::THREADS, 0, c.stream>>>(cc, dd, cnt, d_stats);
         } else if (two_phase) {
             if (p->outputs & SIM5_OUT_DELAY) {
                 grid = persistent_grid(s5::k_trace_eqplane<true, true>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
-                s5::k_trace_eqplane<true, true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, cnt, c.d_stats);
+                s5::k_trace_eqplane<true, true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, cnt, d_stats);
             } else {
                 grid = persistent_grid(s5::k_trace_eqplane<true>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
-                s5::k_trace_eqplane<true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, cnt, c.d_stats);
+                s5::k_trace_eqplane<true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, cnt, d_stats);
             }
             if (ch == 0) CK(cudaEventRecord(c.evp[0], c.stream));
             int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_AZ_THREADS);
@@ -774,6 +780,23 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                 if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
                 s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, cnt + 2, 0);
             } else {
+                if (defer) {
+                    /* a train of images: ONE tolerance-mode launch covers both queues on the launch stream (the steps of a split image are
+                     * short, every stream operation counts); both redo passes go to the auxiliary stream, in a few CTAs (a 512-thread CTA of
+                     * the bit-faithful kernel fills the register file of its SM, and the next call's tracing kernel is about to want the SMs);
+                     * nothing joins the launch stream here */
+                    int g_f = persistent_grid(s5::k_azimuth_fast<0>, S5_AZF_THREADS);
+                    s5::k_azimuth_fast<0><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
+                    const int gs_rc = g_rc < S5_DEFER_REDO_CTAS ? g_rc : S5_DEFER_REDO_CTAS, gs_rr = g_rr < S5_DEFER_REDO_CTAS ? g_rr : S5_DEFER_REDO_CTAS;
+                    CK(cudaEventRecord(c.evp[1], c.stream));             /* end of the call on the launch stream; the redo passes wait for it */
+                    CK(cudaStreamWaitEvent(c.aux_stream, c.evp[1], 0));
+                    s5::k_azimuth<s5::GEOD_TYPE_RC><<<gs_rc, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, cnt + 2, 1);
+                    s5::k_azimuth<s5::GEOD_TYPE_RR><<<gs_rr, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, cnt + 1, 1);
+                    const int b = (cnt == c.d_counter2) ? 0 : 1;
+                    CK(cudaEventRecord(c.ev_redo_done[b], c.aux_stream));
+                    c.redo_pending[b] = true;
+                    launches -= 1;
+                } else {
                 /* RR chain on the launch stream, RC chain (3 % of the hits) on the auxiliary stream: the two bit-faithful redo
                  * passes are latency-bound single waves, so they run side by side instead of back to back */
                 CK(cudaEventRecord(c.ev_fork, c.stream));
@@ -782,19 +805,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                 s5::k_azimuth_fast<1><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
                 g_f = persistent_grid(s5::k_azimuth_fast<2>, S5_AZF_THREADS);
                 s5::k_azimuth_fast<2><<<g_f, S5_AZF_THREADS, 0, c.aux_stream>>>(cc, q, dd.phi);
-                if (defer) {
-                    /* both redo passes stay on the auxiliary stream, in a few CTAs (a 512-thread CTA of the bit-faithful kernel fills the register
-                     * file of its SM, and the next call's tracing kernel is about to want the SMs); nothing joins the launch stream here */
-                    const int gs_rc = g_rc < S5_DEFER_REDO_CTAS ? g_rc : S5_DEFER_REDO_CTAS, gs_rr = g_rr < S5_DEFER_REDO_CTAS ? g_rr : S5_DEFER_REDO_CTAS;
-                    CK(cudaEventRecord(c.ev_fast_done, c.stream));
-                    s5::k_azimuth<s5::GEOD_TYPE_RC><<<gs_rc, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, cnt + 2, 1);
-                    CK(cudaStreamWaitEvent(c.aux_stream, c.ev_fast_done, 0));
-                    s5::k_azimuth<s5::GEOD_TYPE_RR><<<gs_rr, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, cnt + 1, 1);
-                    const int b = (cnt == c.d_counter2) ? 0 : 1;
-                    CK(cudaEventRecord(c.ev_redo_done[b], c.aux_stream));
-                    c.redo_pending[b] = true;
-                    if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
-                } else {
+                {
                     s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, cnt + 2, 1);
                     CK(cudaEventRecord(c.ev_join, c.aux_stream));
                     if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
@@ -802,17 +813,18 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                     s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, redo_threads, 0, c.stream>>>(cc, q, dd.phi, cnt + 1, 1);
                     CK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
                 }
+                }
                 launches += 2;
             }
-            if (ch == 0) CK(cudaEventRecord(c.evp[2], c.stream));
+            if (ch == 0 && !defer) CK(cudaEventRecord(c.evp[2], c.stream));
             launches += 2;
         } else {
             if (p->outputs & SIM5_OUT_DELAY) {
                 grid = persistent_grid(s5::k_trace_eqplane<false, true>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
-                s5::k_trace_eqplane<false, true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+                s5::k_trace_eqplane<false, true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, cnt, d_stats);
             } else {
                 grid = persistent_grid(s5::k_trace_eqplane<false>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
-                s5::k_trace_eqplane<false><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, c.d_counter, c.d_stats);
+                s5::k_trace_eqplane<false><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, cnt, d_stats);
             }
         }
         launches += 1;
@@ -845,14 +857,16 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     }
     c.phases = (nchunks == 1) ? launches : 0;      /* per-kernel times are defined for single-chunk calls only */
     c.ring_phases[c.ring_pos] = c.phases;
-    if (devptr || npix == 0) CK(cudaEventRecord(c.ev2, c.stream));
+    c.ring_defer[c.ring_pos] = defer;
+    c.last_defer = defer;
+    if ((devptr || npix == 0) && !defer) CK(cudaEventRecord(c.ev2, c.stream));      /* (a deferred call ends at evp[1]) */
     if (async) return SIM5_OK;
     if (nchunks > 1) {
         CK(cudaEventRecord(c.ev2, c.stream));
         CK(cudaEventRecord(c.ev_copy_done, c.copy_stream));
         CK(cudaStreamWaitEvent(c.stream, c.ev_copy_done, 0));
     }
-    CK(cudaMemcpyAsync(c.h_stats, c.d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaMemcpyAsync(c.h_stats, d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c.stream));
     CK(cudaEventRecord(c.ev3, c.stream));
     CK(cudaStreamSynchronize(c.stream));
     if (stats) {
@@ -863,7 +877,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         stats->total_steps = (int64_t)c.h_stats->steps;
         float ms = 0;
         cudaEventElapsedTime(&ms, c.ev1, c.ev2); stats->kernel_ms = ms;
-        cudaEventElapsedTime(&ms, c.ev0, c.ev3); stats->total_ms = ms;
+        cudaEventElapsedTime(&ms, c.ev1, c.ev3); stats->total_ms = ms;
         stats->kernel_launches = launches;
         stats->sm_count = c.sm_count; stats->grid_ctas = grid; stats->cta_threads = (p->mode == SIM5_MODE_SURFACE) ? s5::SurfaceProg::THREADS : lanes ? S5_CTA_THREADS : S5_EQ_THREADS;
     }
@@ -1057,13 +1071,13 @@ extern "C" int sim5_last_phase_ms(double* ms, int n, int64_t* items)
     if (c.ready) CK(cudaSetDevice(c.device));
     if (!c.ready || !ms || n < 1) { set_error("sim5_last_phase_ms: no context / no output"); return SIM5_ERR_BAD_PARAM; }
     if (c.phases < 1) { set_error("sim5_last_phase_ms: no image call recorded"); return SIM5_ERR_BAD_PARAM; }
-    CK(cudaEventSynchronize(c.ev2));
+    CK(cudaEventSynchronize(c.last_defer ? c.evp[1] : c.ev2));
     float t = 0;
     for (int i = 0; i < n; i++) ms[i] = 0.0;
     if (items) items[0] = items[1] = 0;
     if (c.phases == 1) { CK(cudaEventElapsedTime(&t, c.ev1, c.ev2)); ms[0] = t; return 1; }
     cudaEvent_t seq[4] = {c.ev1, c.evp[0], c.evp[1], c.evp[2]};
-    for (int i = 0; i < 3 && i < n; i++) { CK(cudaEventElapsedTime(&t, seq[i], seq[i + 1])); ms[i] = t; }
+    for (int i = 0; i < (c.last_defer ? 2 : 3) && i < n; i++) { CK(cudaEventElapsedTime(&t, seq[i], seq[i + 1])); ms[i] = t; }
     if (items) {
         unsigned long long cnt[2] = {0, 0};
         CK(cudaMemcpy(cnt, c.last_counts, sizeof cnt, cudaMemcpyDeviceToHost));
@@ -1084,11 +1098,12 @@ extern "C" int sim5_phase_history(int back, double* ms, int n)
     int phases = c.ring_phases[pos];
     if (phases < 1) { set_error("sim5_phase_history: no image call recorded in that slot"); return SIM5_ERR_BAD_PARAM; }
     cudaEvent_t* e = c.ring[pos];
-    CK(cudaEventSynchronize(e[4]));
+    const bool dfr = c.ring_defer[pos];
+    CK(cudaEventSynchronize(dfr ? e[2] : e[4]));
     float t = 0;
     for (int i = 0; i < n; i++) ms[i] = 0.0;
     if (phases == 1) { CK(cudaEventElapsedTime(&t, e[0], e[4])); ms[0] = t; return 1; }
-    for (int i = 0; i < 3 && i < n; i++) { CK(cudaEventElapsedTime(&t, e[i], e[i + 1])); ms[i] = t; }
+    for (int i = 0; i < (dfr ? 2 : 3) && i < n; i++) { CK(cudaEventElapsedTime(&t, e[i], e[i + 1])); ms[i] = t; }
     return phases;
 }
 

@@ -456,6 +456,62 @@ S5_HD S5_NOINL double cr_atan(double x)
     }
     return copysign(a.h, x);
 }
+S5_HD S5_NOINL double cr_acos(double x);
+/* The stepper alternates m -> theta = acos(m) -> theta + dtheta -> m' = cos(theta + dtheta) every step (sim5raytrace.c:177), so the acos
+ * of a step is the inverse of the cos of the step before.  AngCarry keeps what that cos knew: its argument th and the low word of its
+ * double-double result, i.e. cos(th) = m + lo to ~2^-68.  Then acos(m) = th + lo / sqrt(1 - m^2) + O(lo^2): one FMA, one reciprocal
+ * square root and a handful of operations instead of a double-double sqrt, two double-double divisions and the arctangent kernel
+ * (cr_acos was 28 % of the stepwise kernel's stall samples, profiles/r04b_hotspots_stepwise.txt).  The shortcut is taken only when the
+ * rounding of th + correction is beyond doubt (both ends of the error interval round to the same double); otherwise -- near a rounding
+ * boundary, near the poles, after a restart -- cr_acos runs.  Either way the value is the correctly rounded one that cr_acos returns. */
+#if defined(S5_STEP_STATS) && !defined(__CUDA_ARCH__)
+extern "C" long long s5_stat[16];                    /* tools/step_stats.cpp: how often each path of the stepper runs */
+#define S5_STAT(i) __atomic_fetch_add(&crm::s5_stat[i], 1LL, __ATOMIC_RELAXED)
+#else
+#define S5_STAT(i) ((void)0)
+#endif
+struct AngCarry { double th, lo, m; };
+S5_HD S5_INL void carry_reset(AngCarry* c) { c->th = 0.0; c->lo = 0.0; c->m = 2.0; }      /* m = 2 matches no cosine */
+S5_HD S5_NOINL double cr_cos_carry(double x, AngCarry* c)          /* == cr_cos(x) */
+{
+    double ax = fabs(x);
+    c->m = 2.0;
+    if (!(ax < 1.0e6)) {
+        if (ax != ax || ax > 1.7976931348623157e308) return x - x;
+        return cos(x);
+    }
+    if (ax < 7.450580596923828e-09) return 1.0;
+    dd r;
+    int k = reduce_pio2(x, r);
+    dd v = (k & 1) ? sin_kernel(r) : cos_kernel(r);
+    const bool neg = (k == 1 || k == 2);
+    const double m = neg ? -v.h : v.h;
+    c->th = x; c->lo = neg ? -v.l : v.l; c->m = m;
+    return m;
+}
+S5_HD S5_INL double cr_acos_carry(double m, const AngCarry* c)   /* == cr_acos(m) */
+{
+#if !defined(S5_NO_ANGLE_CARRY)
+    if (c->m == m && c->th > 0.05 && c->th < 3.09) {
+        double s2 = fma_(-m, m, 1.0);
+        if (s2 > 0.00390625) {
+#if defined(__CUDA_ARCH__)
+            double rs = rsqrt(s2);
+#else
+            double rs = 1.0 / sqrt(s2);
+#endif
+            double cc = mul_(c->lo, rs);
+            double e = fma_(mul_(fabs(m), rs), 0x1p-66, mul_(fabs(cc), 0x1p-30));
+            double r1 = add_(c->th, add_(cc, e)), r2 = add_(c->th, add_(cc, -e));
+            if (r1 == r2) return r1;
+            S5_STAT(5);
+        }
+    }
+#endif
+    S5_STAT(4);
+    return cr_acos(m);
+}
+
 /* sqrt(1 - x^2) as a double-double, 0 <= x <= 1 */
 S5_HD S5_INL dd sqrt_1mx2(double ax)
 {

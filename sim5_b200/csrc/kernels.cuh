@@ -70,8 +70,9 @@ struct AzQueue {
 #define S5_EQ_TILES_PER_SYNC 1    /* tiles a warp traces between two CTA barriers of the lockstep tile loop */
 #endif
 #ifndef S5_MIN_CTAS_STEP
-#define S5_MIN_CTAS_STEP 3        /* stepwise lane kernel: 1 CTA/SM (186 regs, 8 warps/SM) 153.7 ms, 3 (168 regs, 12 warps) 139.5, 4 (128) 141.2, 5 (96) 156.6
-                                     (cfg 4 at 512^2, profiles/r02w_step_sweep.log) */
+#define S5_MIN_CTAS_STEP 4        /* stepwise lane kernel, cfg 4 at 1024^2 after the angle carry took cr_acos out of the step (profiles/r05g_step_sweep.log, ms):
+                                     2 CTAs/SM 397, 3 (160 regs, 12 warps/SM) 324, 4 (128 regs, 16 warps) 308, 5 (96) 320; 64-thread CTAs x 6: 325.
+                                     (before: 1 CTA/SM 153.7, 3 139.5, 4 141.2, 5 156.6 at 512^2, profiles/r02w_step_sweep.log) */
 #endif
 #ifndef S5_MIN_CTAS_AZ
 #define S5_MIN_CTAS_AZ 4
@@ -355,6 +356,7 @@ k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigne
     typename PROG::State s;
     long long mypix = -1;
     bool live = false;
+    bool pend = false;             /* PROG::DEFERS: this lane's step waits for its expensive part */
     bool drained = false;          /* queue exhausted (warp-uniform) */
     unsigned long long my_steps = 0;
 
@@ -446,8 +448,20 @@ k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigne
         /* advance the live lanes */
         #pragma unroll 1
         for (int it = 0; it < S5_STEPS_PER_ROUND; it++) {
-            if (live) {
-                int cls = PROG::step(c, &s);
+            bool stepped = live;
+            if (PROG::DEFERS) {
+                /* the cheap part of the step for every lane that is not waiting; the expensive part (PROG::slow_step) for all waiting lanes at
+                 * once, as soon as PROG::DEFER_MIN of them wait or nothing else is left to do in this warp */
+                stepped = false;
+                if (live && !pend) { pend = PROG::try_step(c, &s); stepped = !pend; }
+                const unsigned pm = __ballot_sync(0xffffffffu, live && pend);
+                const unsigned rm = __ballot_sync(0xffffffffu, live && !pend);
+                if (pm && (__popc(pm) >= PROG::DEFER_MIN || rm == 0)) {
+                    if (live && pend) { PROG::slow_step(c, &s); pend = false; stepped = true; }
+                }
+            }
+            if (stepped) {
+                int cls = PROG::DEFERS ? PROG::post(c, &s) : PROG::step(c, &s);
                 if (cls) {
                     PixelOut o;
                     PROG::finish(c, &s, cls, &o);

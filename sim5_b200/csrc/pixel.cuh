@@ -788,6 +788,8 @@ struct StepRay {           /* live state of one stepwise ray (the persistent ker
     double x[4], k[4];
     RayData rtd;
     double I, tau;
+    crm::AngCarry ac;      /* the polar angle behind x[2], left by the previous step's cosine */
+    double dl, th0;        /* a step whose RK4 fallback is pending (k_trace_lanes runs those for several lanes at once) */
     int steps;
     unsigned gt;
 };
@@ -817,14 +819,25 @@ S5_HD S5_INL bool stepwise_start(const S5ImageConsts& c, int ix, int iy, StepRay
     geodesic_momentum(&gd, P, r0, s->x[2], s->k);
     if (isnan(P) || isnan(s->x[2]) || isnan(s->k[1]) || isnan(s->k[2])) { o->status = SIM5_ST_NOSTART | s->gt; return false; }
     raytrace_prepare(c.a, s->x, s->k, c.pf, 0, &s->rtd);
+    crm::carry_reset(&s->ac);
     s->I = 0.0; s->tau = 0.0; s->steps = 0;
     return true;
 }
-/* one raytrace() call + torus emission; returns 0 while the ray is live, else the termination class */
-S5_HD S5_INL int stepwise_step(const S5ImageConsts& c, StepRay* s)
+/* a raytrace() call in two parts: stepwise_try runs the Verlet step and returns true if the RK4 fallback is needed (stepwise_rk4);
+ * stepwise_post = the torus emission along the finished step and the termination tests: 0 while the ray is live, else the class */
+S5_HD S5_INL bool stepwise_try(const S5ImageConsts& c, StepRay* s)
 {
-    double dl = c.step_max;
-    raytrace(s->x, s->k, &dl, &s->rtd);
+    s->dl = c.step_max;
+    return raytrace_verlet(s->x, s->k, &s->dl, &s->rtd, &s->ac, &s->th0);
+}
+S5_HD S5_INL void stepwise_rk4(const S5ImageConsts& c, StepRay* s)
+{
+    (void)c;
+    raytrace_rk4(s->x, s->k, s->dl, &s->rtd, s->th0, &s->ac);
+}
+S5_HD S5_INL int stepwise_post(const S5ImageConsts& c, StepRay* s)
+{
+    const double dl = s->dl;
     s->steps++;
     {
         double r = s->x[1], m = s->x[2];
@@ -832,6 +845,7 @@ S5_HD S5_INL int stepwise_step(const S5ImageConsts& c, StepRay* s)
         double z = r * m;
         double sv = sq((R - c.torus_rc) / c.torus_w) + sq(z / (c.torus_h * R));
         if (sv < 13.8) {
+            S5_STAT(7);
             Metric M;
             kerr_metric(c.a, r, m, &M);
             double Om = Omega_from_ell(c.torus_ell, &M);
@@ -853,6 +867,12 @@ S5_HD S5_INL int stepwise_step(const S5ImageConsts& c, StepRay* s)
     if (s->rtd.error > 1e-2) return SIM5_ST_ERRBREAK;
     if (s->steps >= c.max_steps) return SIM5_ST_MAXSTEPS;
     return 0;
+}
+/* one raytrace() call + torus emission; returns 0 while the ray is live, else the termination class */
+S5_HD S5_INL int stepwise_step(const S5ImageConsts& c, StepRay* s)
+{
+    if (stepwise_try(c, s)) stepwise_rk4(c, s);
+    return stepwise_post(c, s);
 }
 S5_HD S5_INL void stepwise_finish(const S5ImageConsts& c, StepRay* s, int cls, PixelOut* o)
 {
@@ -1031,17 +1051,36 @@ S5_HD S5_MID int surface_step(const S5ImageConsts& c, SurfRay* s)
 #define S5_STEP_BATCH 0           /* 0: free-running warps with lane refill (steps per ray vary by an order of magnitude) */
 #endif
 #ifndef S5_MIN_CTAS_STEP
-#define S5_MIN_CTAS_STEP 3
+#define S5_MIN_CTAS_STEP 4
+#endif
+#ifndef S5_STEP_REFILL_MIN
+#define S5_STEP_REFILL_MIN 8      /* idle lanes of a warp that trigger a refill: 2 -> 354 ms, 4 -> 324, 8 -> 311 (cfg 4 at 1024^2, profiles/r05g_step_sweep.log):
+                                     a refill runs the ray start (init_inf, P_int: ~30 steps' worth) with only the idle lanes active */
+#endif
+#ifndef S5_RK4_BATCH
+#define S5_RK4_BATCH 1            /* lanes of a warp that must wait for the RK4 fallback before it runs; 1: run it at once, as raytrace() does.
+                                     Holding the fallback back does NOT pay (cfg 4 at 512^2 / 1024^2, ms, profiles/r05f_step_sweep.log): 1 -> 98.3 / 324,
+                                     3 -> 121 / 371, 4 -> 133 / 389, 6 -> 140 / 419, 8 -> 151 / 434.  RK4 steps come in runs (a ray needs the fallback for
+                                     many consecutive steps around a turning point, and so do its neighbours in the warp at about the same time), so the
+                                     lanes of a warp already take it together, and a lane that waits holds up a long run */
 #endif
 struct StepwiseProg {
     typedef StepRay State;
-    static const int REFILL_MIN = 4;              /* idle lanes of a warp that trigger a refill (S5_REFILL_MIN) */
+    static const int REFILL_MIN = S5_STEP_REFILL_MIN;   /* idle lanes of a warp that trigger a refill */
     static const int MIN_CTAS = S5_MIN_CTAS_STEP; /* resident 128-thread CTAs per SM the kernel is compiled for */
     static const int THREADS = S5_STEP_THREADS;
     static const int BATCH = S5_STEP_BATCH;
     static S5_HD S5_INL bool start(const S5ImageConsts& c, int ix, int iy, State* s, PixelOut* o) { return stepwise_start(c, ix, iy, s, o); }
     static S5_HD S5_INL int step(const S5ImageConsts& c, State* s) { return stepwise_step(c, s); }
     static S5_HD S5_INL void finish(const S5ImageConsts& c, State* s, int cls, PixelOut* o) { stepwise_finish(c, s, cls, o); }
+    /* the step in two parts: `slow` (the RK4 fallback, 0.3 % of the steps, ~4 steps' worth of work) is held back until DEFER_MIN lanes of the
+     * warp want it (or no lane can do anything else).  Per-ray arithmetic and order are unchanged.  tools/step_stats.cpp: with 32 lanes a warp
+     * met an RK4 step in 8.9 % of its rounds and idled 31 lanes for it */
+    static const bool DEFERS = (S5_RK4_BATCH > 1);
+    static const int DEFER_MIN = S5_RK4_BATCH;
+    static S5_HD S5_INL bool try_step(const S5ImageConsts& c, State* s) { return stepwise_try(c, s); }
+    static S5_HD S5_INL void slow_step(const S5ImageConsts& c, State* s) { stepwise_rk4(c, s); }
+    static S5_HD S5_INL int post(const S5ImageConsts& c, State* s) { return stepwise_post(c, s); }
 };
 /* Launch shape of the SURFACE lane kernel (1024^2 preset, ms; profiles/r01x_sweep.log, r02z_surf_sweep.log).  Lane refill does not pay
  * here: a ray's start (init_inf, P_int) costs ~30 sub-steps, so refilling a few idle lanes while the rest of the warp waits loses more
@@ -1064,7 +1103,7 @@ struct StepwiseProg {
 #define S5_SURF_BATCH 1           /* > 0: CTA-batch variant of the lane kernel with a barrier every S5_SURF_BATCH sub-steps; 0: warps with lane refill */
 #endif
 #ifndef S5_MIN_CTAS_STEP
-#define S5_MIN_CTAS_STEP 3
+#define S5_MIN_CTAS_STEP 4
 #endif
 struct SurfaceProg {
     typedef SurfRay State;
@@ -1074,6 +1113,11 @@ struct SurfaceProg {
     static const int BATCH = S5_SURF_BATCH;
     static S5_HD S5_INL bool start(const S5ImageConsts& c, int ix, int iy, State* s, PixelOut* o) { return surface_start(c, ix, iy, s, o); }
     /* the kernel's protocol is "0 while live"; SIM5_ST_HIT0 is 0, so the class travels with bit 8 set */
+    static const bool DEFERS = false;
+    static const int DEFER_MIN = 1;
+    static S5_HD S5_INL bool try_step(const S5ImageConsts&, State*) { return false; }
+    static S5_HD S5_INL void slow_step(const S5ImageConsts&, State*) { }
+    static S5_HD S5_INL int post(const S5ImageConsts&, State*) { return 0; }
     static S5_HD S5_INL int step(const S5ImageConsts& c, State* s) { int r = surface_step(c, s); return r < 0 ? 0 : (r | 0x100); }
     static S5_HD S5_INL void finish(const S5ImageConsts& c, State* s, int cls, PixelOut* o) { surface_finish(c, s, cls & 0xff, o); }
 };

@@ -49,8 +49,8 @@ S5_HD S5_INL void raytrace_prepare(double bh_spin, const double x[4], const doub
     Gamma(&G, k, k, rtd->dk);
 }
 
-/* sim5raytrace.c:250-323 */
-S5_HD S5_INL void raytrace_rk4(double x[4], double k[4], double dl, RayData* rtd)
+/* sim5raytrace.c:250-323.  th0 = acos(x[2]) (the caller has it); *ac receives the angle behind the new x[2] */
+S5_HD S5_INL void raytrace_rk4(double x[4], double k[4], double dl, RayData* rtd, double th0, crm::AngCarry* ac)
 {
     Metric m;
     Conn G;
@@ -60,7 +60,7 @@ S5_HD S5_INL void raytrace_rk4(double x[4], double k[4], double dl, RayData* rtd
     double kt0 = rtd->kt;
     int i;
 
-    x[2] = cr_acos(x[2]);
+    x[2] = th0;
 
 #define S5_CONN_AT(xx) do { if (rtd->opt_gr) kerr_connection(rtd->bh_spin, (xx)[1], crm::cr_cos((xx)[2]), &G); \
                             else flat_connection((xx)[1], crm::cr_cos((xx)[2]), &G); } while (0)
@@ -89,7 +89,7 @@ S5_HD S5_INL void raytrace_rk4(double x[4], double k[4], double dl, RayData* rtd
         x[i] += dl / 6. * (k1[i] + 2. * k2[i] + 2. * k3[i] + k4[i]);
         k[i] += dl / 6. * (dk1[i] + 2. * dk2[i] + 2. * dk3[i] + dk4[i]);
     }
-    x[2] = crm::cr_cos(x[2]);
+    x[2] = crm::cr_cos_carry(x[2], ac);
 
     if (rtd->opt_gr) kerr_connection(rtd->bh_spin, x[1], x[2], &G); else flat_connection(x[1], x[2], &G);
     Gamma(&G, k, k, rtd->dk);
@@ -99,8 +99,13 @@ S5_HD S5_INL void raytrace_rk4(double x[4], double k[4], double dl, RayData* rtd
     rtd->error = (float)frac_err(kt1, kt0);
 }
 
-/* one step.  sim5raytrace.c:108-245 */
-S5_HD S5_INL void raytrace(double x[4], double k[4], double* step, RayData* rtd)
+/* one step, first part: the velocity-Verlet step with its fixed-point momentum solve (sim5raytrace.c:108-226).  Returns false when
+ * the step was accepted (x, k, rtd advanced).  Returns true when the reference would now fall back to RK4 (sim5raytrace.c:219-226):
+ * x, k are back at their values, *step holds the step length and *th0 = acos(x[2]) for raytrace_rk4.  The split lets the lane kernel
+ * run the (five times more expensive, 0.3 % of the steps) RK4 fallback for several lanes of a warp at once instead of idling 31 lanes
+ * every time one lane needs it; the operations of a ray and their order are those of raytrace().
+ * *ac: the angle behind x[2] if the previous step of this ray left one (crm::AngCarry) */
+S5_HD S5_INL bool raytrace_verlet(double x[4], double k[4], double* step, RayData* rtd, crm::AngCarry* ac, double* th0_out)
 {
     int i;
     Metric m;
@@ -124,7 +129,9 @@ S5_HD S5_INL void raytrace(double x[4], double k[4], double* step, RayData* rtd)
     double half_dl2 = 0.5 * dl * dl;
     xp[0] = x[0] + k[0] * dl + dk[0] * half_dl2;
     xp[1] = x[1] + k[1] * dl + dk[1] * half_dl2;
-    xp[2] = crm::cr_cos(cr_acos(x[2]) + (k[2] * dl + dk[2] * half_dl2));
+    const double th0 = crm::cr_acos_carry(x[2], ac);
+    crm::AngCarry acp;
+    xp[2] = crm::cr_cos_carry(th0 + (k[2] * dl + dk[2] * half_dl2), &acp);
     xp[3] = x[3] + k[3] * dl + dk[3] * half_dl2;
 
     for (i = 0; i < 4; i++) k[i] += dk[i] * half_dl;
@@ -149,24 +156,40 @@ S5_HD S5_INL void raytrace(double x[4], double k[4], double* step, RayData* rtd)
         kp[3] = k[3] + k_deriv3(&G, kp_prev) * half_dl;  k_frac_error += frac_err(kp[3], kp_prev[3]);
         k_iter++;
     } while (k_frac_error > 1e-2 * 1e-3 && k_iter < 3);
+    S5_STAT(0); S5_STAT(k_iter);
 
     kt = kp[0] * m.g00 + kp[3] * m.g03;
     kk = fabs(dotprod(kp, kp, &m));
     rtd->error = (float)fmax(frac_err(kt, rtd->kt), kk);
     if ((k_frac_error > 1e-2 * 1e-2) || (rtd->error > 1e-2 * 1e-2)) {
         for (i = 0; i < 4; i++) { x[i] = x_orig[i]; k[i] = k_orig[i]; }
-        raytrace_rk4(x, k, dl, rtd);
+        S5_STAT(6);
+        *th0_out = th0;
         *step = dl;
-        return;
+        return true;
     }
 
     for (i = 0; i < 4; i++) { x[i] = xp[i]; k[i] = kp[i]; }
+    *ac = acp;
     dk[0] = k_deriv0(&G, kp);
     dk[1] = k_deriv1(&G, kp);
     dk[2] = k_deriv2(&G, kp);
     dk[3] = k_deriv3(&G, kp);
     rtd->kt = kt;
     *step = dl;
+    return false;
+}
+/* one step.  sim5raytrace.c:108-245 */
+S5_HD S5_INL void raytrace(double x[4], double k[4], double* step, RayData* rtd, crm::AngCarry* ac)
+{
+    double th0;
+    if (raytrace_verlet(x, k, step, rtd, ac, &th0)) raytrace_rk4(x, k, *step, rtd, th0, ac);
+}
+S5_HD S5_INL void raytrace(double x[4], double k[4], double* step, RayData* rtd)
+{
+    crm::AngCarry ac;
+    crm::carry_reset(&ac);
+    raytrace(x, k, step, rtd, &ac);
 }
 
 /* relative drift of the Carter constant.  sim5raytrace.c:327-343 */

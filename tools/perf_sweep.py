@@ -34,7 +34,7 @@ if os.environ.get("SWEEP_EXACT"):
 p = abi.default_params(2); p.outputs = abi.OUT_R|abi.OUT_G|abi.OUT_FLUX|abi.OUT_STATUS; ms, st = t(p); res["cfg2_nophi_ms"] = round(ms,3); res["cfg2_nophi_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
 p = abi.default_params(2); p.flags = abi.FLAG_SINGLE_PASS; ms, st = t(p); res["cfg2_single_pass_ms"] = round(ms,3); res.pop("_phases", None)
 p = abi.default_params(3); ms, st = t(p); res["cfg3_ms"] = round(ms,3); res["cfg3_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
-p = abi.default_params(4, 512); ms, st = t(p, 1); res["cfg4_512_ms"] = round(ms,2); res["cfg4_steps_s"] = "%%.3e" %% (st.total_steps/ms*1e3)
+p = abi.default_params(4, 512); ms, st = t(p, 3); res["cfg4_512_ms"] = round(ms,2); res["cfg4_steps_s"] = "%%.3e" %% (st.total_steps/ms*1e3)
 if os.environ.get("SWEEP_NOREFILL"):
     p.flags = abi.FLAG_NO_REFILL; ms, st = t(p, 1); res["cfg4_512_norefill_ms"] = round(ms,2)
 p = abi.default_params(5, 512); p.n_spin, p.n_incl = 8, 4; ms, st = t(p, 2); res["cfg5_8x4x512_ms"] = round(ms,2); res["cfg5_rays_s"] = "%%.3e" %% (st.rays/ms*1e3)
