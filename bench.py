@@ -262,7 +262,11 @@ def bind_to_gpu_numa_node(local):
 
 
 def run_ours(args):
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
+    # stdout carries exactly ONE line, the JSON: everything native libraries print on the way (NCCL's version banner, ...) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -570,7 +574,8 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         fence()
         if shm is not None:
@@ -618,6 +623,12 @@ class SharedHostImage:
         dist.broadcast_object_list(names, src=0)
         if rank != 0:
             self.segs = [shared_memory.SharedMemory(name=nm) for nm in names[0]]
+            try:      # the creator unlinks; an attaching process must not let its resource tracker "clean up" the segment at exit (Python < 3.13)
+                from multiprocessing import resource_tracker
+                for sgm in self.segs:
+                    resource_tracker.unregister(sgm._name, "shared_memory")
+            except Exception:
+                pass
         npdt = {C.c_double: np.float64, C.c_int32: np.int32, C.c_uint8: np.uint8}
         self.planes = HostImageView(abi.ImageOut(), (p.ny, p.nx))
         for (name, ct), seg in zip(specs, self.segs):

@@ -781,21 +781,24 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                 s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, cnt + 2, 0);
             } else {
                 if (defer) {
-                    /* a train of images: ONE tolerance-mode launch covers both queues on the launch stream (the steps of a split image are
-                     * short, every stream operation counts); both redo passes go to the auxiliary stream, in a few CTAs (a 512-thread CTA of
-                     * the bit-faithful kernel fills the register file of its SM, and the next call's tracing kernel is about to want the SMs);
-                     * nothing joins the launch stream here */
-                    int g_f = persistent_grid(s5::k_azimuth_fast<0>, S5_AZF_THREADS);
-                    s5::k_azimuth_fast<0><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
+                    /* a train of images: RR hits on the launch stream, the RC chain (3 % of the hits; 0.2 ms alone on a full image) beside it on
+                     * the auxiliary stream, where both redo passes stay too, in a few CTAs (a 512-thread CTA of the bit-faithful kernel fills the
+                     * register file of its SM, and the next call's tracing kernel is about to want the SMs); nothing joins the launch stream here.
+                     * (One launch for both queues, k_azimuth_fast<0>, saves a stream operation but serialises the RC part: 2 GPUs 1.35 -> 1.53 ms,
+                     * profiles/r05h_bench_cfg2_n2.json.) */
+                    CK(cudaStreamWaitEvent(c.aux_stream, c.evp[0], 0));              /* evp[0]: phase A done */
+                    int g_f = persistent_grid(s5::k_azimuth_fast<1>, S5_AZF_THREADS);
+                    s5::k_azimuth_fast<1><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
+                    g_f = persistent_grid(s5::k_azimuth_fast<2>, S5_AZF_THREADS);
+                    s5::k_azimuth_fast<2><<<g_f, S5_AZF_THREADS, 0, c.aux_stream>>>(cc, q, dd.phi);
                     const int gs_rc = g_rc < S5_DEFER_REDO_CTAS ? g_rc : S5_DEFER_REDO_CTAS, gs_rr = g_rr < S5_DEFER_REDO_CTAS ? g_rr : S5_DEFER_REDO_CTAS;
-                    CK(cudaEventRecord(c.evp[1], c.stream));             /* end of the call on the launch stream; the redo passes wait for it */
-                    CK(cudaStreamWaitEvent(c.aux_stream, c.evp[1], 0));
+                    CK(cudaEventRecord(c.evp[1], c.stream));             /* end of the call on the launch stream; the RR redo pass waits for it */
                     s5::k_azimuth<s5::GEOD_TYPE_RC><<<gs_rc, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, cnt + 2, 1);
+                    CK(cudaStreamWaitEvent(c.aux_stream, c.evp[1], 0));
                     s5::k_azimuth<s5::GEOD_TYPE_RR><<<gs_rr, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, cnt + 1, 1);
                     const int b = (cnt == c.d_counter2) ? 0 : 1;
                     CK(cudaEventRecord(c.ev_redo_done[b], c.aux_stream));
                     c.redo_pending[b] = true;
-                    launches -= 1;
                 } else {
                 /* RR chain on the launch stream, RC chain (3 % of the hits) on the auxiliary stream: the two bit-faithful redo
                  * passes are latency-bound single waves, so they run side by side instead of back to back */

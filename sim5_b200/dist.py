@@ -4,7 +4,8 @@ The photon path shards by rows: every ray is independent, per-image constants ar
 traces the row blocks b (of `block_rows` rows) with b % W == r  -- an INTERLEAVED static split, so the
 expensive rows around the black-hole shadow are dealt round-robin to all ranks (per-rank cost equal to
 within ~1 %), which is what the reference's "static + work stealing" intent needs without any
-cross-process counter.  The only collective is the gather of the finished planes at the end.
+cross-process counter.  The only collective is the gather of the finished planes at the end (images) or the reduce(sum)
+of the per-rank transfer-function histograms (HISTOGRAM mode, lattice_images).
 """
 
 DEFAULT_BLOCK_ROWS = 32
@@ -45,6 +46,13 @@ def assemble(parts, world, block_rows=DEFAULT_BLOCK_ROWS):
     import numpy as np
     st = np.stack(list(parts), 0).reshape(world, nb, block_rows, nx)
     return st.transpose(1, 0, 2, 3).reshape(world * rows_local, nx)
+
+
+def lattice_images(n_images, rank, world):
+    """The (spin, inclination) lattice images of HISTOGRAM mode that `rank` traces: an INTERLEAVED deal, image i -> rank i mod W
+    (what split_count / split_index mean in that mode).  Every rank zeroes the bins of the other ranks' images, so the per-rank
+    histograms add up to the lattice: one reduce(sum) at the end."""
+    return list(range(rank, n_images, world))
 
 
 def lattice_range(n_images, rank, world):

@@ -69,3 +69,61 @@ def test_two_rank_gloo_gather_reassembles_the_image():
     full, _, _ = run(p, 1)
     for k in out:
         assert np.array_equal(out[k], full.image(k)), k
+
+
+def _hist_images(p, images):
+    """the lattice histogram with only `images` filled (CPU checker standing in for the rank's GPU)"""
+    import ctypes as C
+    nb = p.n_bins
+    acc = np.zeros(p.n_spin * p.n_incl * nb)
+    for img in images:
+        q = abi.ImageParams.from_buffer_copy(p)
+        q.lattice_begin, q.lattice_end = img, img + 1
+        h = np.zeros_like(acc)
+        hp = h.ctypes.data_as(C.POINTER(C.c_double))
+        if H.have_ref():
+            assert H.load_ref().ref_trace_histogram(C.byref(q), hp, 1, 1) >= 0
+        else:
+            assert H.load_oracle().orc_trace_histogram(C.byref(q), hp, 1) >= 0
+        acc[img * nb:(img + 1) * nb] = h[img * nb:(img + 1) * nb]
+    return acc
+
+
+def _hist_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p = abi.default_params(5, 24)
+        p.n_spin, p.n_incl, p.n_bins = 3, 2, 16
+        mine = sdist.lattice_images(p.n_spin * p.n_incl, rank, world)
+        t = torch.from_numpy(_hist_images(p, mine))
+        tdist.reduce(t, dst=0, op=tdist.ReduceOp.SUM)          # the one collective of cfg 5
+        if rank == 0:
+            q.put((t.numpy().copy(), mine))
+    finally:
+        tdist.destroy_process_group()
+
+
+@pytest.mark.skipif(not (H.have_ref() or H.have_oracle()), reason="no CPU checker built")
+def test_two_rank_gloo_reduce_of_the_interleaved_lattice():
+    """cfg 5 at N > 1: image i of the lattice goes to rank i mod W, the per-rank histograms (zero outside the rank's images) are
+    reduced with one sum -- the host-side logic of `bench.py --config 5 --gpus N` and of sim5_trace_image_multi."""
+    assert sdist.lattice_images(7, 1, 3) == [1, 4] and sorted(sum((sdist.lattice_images(2048, r, 8) for r in range(8)), [])) == list(range(2048))
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_hist_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    red, mine0 = q.get(timeout=180)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert mine0 == [0, 2, 4]
+    p = abi.default_params(5, 24)
+    p.n_spin, p.n_incl, p.n_bins = 3, 2, 16
+    full = _hist_images(p, range(6))
+    assert np.array_equal(red, full)        # disjoint images: the sum adds zeros, bit for bit
+    assert np.all(red.reshape(6, 16).sum(axis=1) > 0)
