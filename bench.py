@@ -411,7 +411,12 @@ def run_ours(args):
     # brackets (they run beside the next call), so there the per-step kernel time is the whole timed region / K
     kms = torch.tensor([(ev0.elapsed_time(ev1) / args.steps) if defer else (sum(a.elapsed_time(b) for a, b in kev) / len(kev))], dtype=torch.float64, device=dev)
     cnt = torch.tensor([launches, total_steps_local, hits_local], dtype=torch.float64, device=dev)
+    # per-rank table: this rank's device time of the timed region and of its kernels per step, its units of work
+    mine_t = torch.tensor([ev0.elapsed_time(ev1) / args.steps, phase_ms[0] / args.steps, phase_ms[1] / args.steps, phase_ms[2] / args.steps,
+                           float(rays_local), float(total_steps_local), float(hits_local)], dtype=torch.float64, device=dev)
+    per_rank = [torch.zeros_like(mine_t) for _ in range(world)] if world > 1 else [mine_t]
     if world > 1:
+        dist.all_gather(per_rank, mine_t)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(kms, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
@@ -563,6 +568,8 @@ def run_ours(args):
                               "flop_per_ray": flop_step / max(rays_local, 1), "kernels_ms_total": kernel_ms,
                               "note": "the flops of the algorithm actually run, all kernels of the step, per rank"},
                      "hbm_written_bytes_per_launch": (rays_local * bpr) if not hist_mode else p.n_spin * p.n_incl * p.n_bins * 8})
+        roof["per_rank"] = [dict(zip(("ms_per_step", "phase_a_ms", "azimuth_ms", "redo_ms", "rays", "raytrace_steps", "disk_hits"), [round(float(v), 4) for v in t.tolist()]))
+                            for t in per_rank]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -346,7 +346,7 @@ S5_HD S5_NOINL double log_core(double x, double xl)
     e -= 1023;
     int i = (int)((b >> 45) & 127);
     double m = from_bits((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-    double scale = x / m;                                /* exact power of two */
+    double scale = from_bits(b & 0x7ff0000000000000LL);  /* x / m: the power of two of x's binade, taken from its exponent field (x is normal here) */
     if (i >= CRM_LOG_SPLIT) { m *= 0.5; e += 1; scale += scale; }
     double c = CRM_LOGTAB(i, 0), lch = CRM_LOGTAB(i, 1), lcl = CRM_LOGTAB(i, 2);
     double r = fma_(m, c, -1.0);                       /* exact, |r| < 2^-7 */

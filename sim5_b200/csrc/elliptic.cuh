@@ -640,7 +640,10 @@ S5_HD S5_MID double jacobi_icn_ex(double z, double m, double* rfv, double* z_use
 
     double f = rf(z * z, 1.0 - m * (1. - z * z), 1.0);
     *rfv = f; *z_used = z; *m_used = m; *have = true;
-    double v = sqrt(1. - z * z) * f;
+    ff::Quick o;
+    double sz = o.sqrt(1. - z * z);
+    if (!o.ok) sz = sqrt(1. - z * z);
+    double v = sz * f;
     return (z > 0.0) ? v : 2. / sqrt(1. - m) * elliptic_f_sin(-z, m / (m - 1.)) + v;
 }
 S5_HD S5_INL double jacobi_icn(double z, double m)
@@ -656,7 +659,8 @@ S5_HD S5_INL double jacobi_itn(double z, double m)
 }
 
 /* sn, cn, dn by descending Landen (AGM) + back substitution.  sim5elliptic.c:535-596 */
-S5_HD S5_NOINL void jacobi_sncndn(double u, double m, double* sn_, double* cn_, double* dn_)
+template <class OPS>
+S5_HD S5_INL void jacobi_sncndn_t(OPS& o, double u, double m, double* sn_, double* cn_, double* dn_)
 {
     if (m == 1.0) m = 0.999999999;
     const double CA = 1.0e-8;
@@ -667,8 +671,8 @@ S5_HD S5_NOINL void jacobi_sncndn(double u, double m, double* sn_, double* cn_, 
         bool neg = (emc < 0.0);
         if (neg) {
             d = 1.0 - emc;
-            emc /= -1.0 / d;
-            u *= (d = sqrt(d));
+            emc = o.div(emc, o.div(-1.0, d));
+            u *= (d = o.sqrt(d));
         }
         double a = 1.0, c = 0.0;
         double am[13], gm[13];
@@ -677,7 +681,7 @@ S5_HD S5_NOINL void jacobi_sncndn(double u, double m, double* sn_, double* cn_, 
         for (int i = 0; i < 13; i++) {
             last = i;
             am[i] = a;
-            gm[i] = (emc = sqrt(emc));
+            gm[i] = (emc = o.sqrt(emc));
             c = 0.5 * (a + emc);
             if (fabs(a - emc) <= CA * a) break;
             emc *= a;
@@ -686,16 +690,16 @@ S5_HD S5_NOINL void jacobi_sncndn(double u, double m, double* sn_, double* cn_, 
         u *= c;
         cr_sincos(u, &sn, &cn);
         if (sn != 0.0) {
-            a = cn / sn;
+            a = o.div(cn, sn);
             c *= a;
             for (int i = last; i >= 0; i--) {
                 double b = am[i];
                 a *= c;
                 c *= dn;
-                dn = (gm[i] + a) / (b + a);
-                a = c / b;
+                dn = o.div(gm[i] + a, b + a);
+                a = o.div(c, b);
             }
-            a = 1.0 / sqrt(c * c + 1.0);
+            a = o.div(1.0, o.sqrt(c * c + 1.0));
             sn = (sn >= 0.0 ? a : -a);
             cn = c * sn;
         }
@@ -703,7 +707,7 @@ S5_HD S5_NOINL void jacobi_sncndn(double u, double m, double* sn_, double* cn_, 
             a = dn;
             dn = cn;
             cn = a;
-            sn /= d;
+            sn = o.div(sn, d);
         }
     } else {
         cn = 1.0 / cosh(u);
@@ -711,6 +715,12 @@ S5_HD S5_NOINL void jacobi_sncndn(double u, double m, double* sn_, double* cn_, 
         sn = tanh(u);
     }
     *sn_ = sn; *cn_ = cn; *dn_ = dn;
+}
+S5_HD S5_NOINL void jacobi_sncndn(double u, double m, double* sn_, double* cn_, double* dn_)
+{
+    ff::Quick f;
+    jacobi_sncndn_t(f, u, m, sn_, cn_, dn_);
+    if (!f.ok) { ff::Plain p; jacobi_sncndn_t(p, u, m, sn_, cn_, dn_); }
 }
 S5_HD S5_INL double jacobi_sn(double u, double m) { double s, c, d; jacobi_sncndn(u, m, &s, &c, &d); return s; }
 S5_HD S5_INL double jacobi_cn(double u, double m) { double s, c, d; jacobi_sncndn(u, m, &s, &c, &d); return c; }

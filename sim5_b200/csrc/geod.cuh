@@ -44,11 +44,12 @@ struct Geodesic {          /* == struct geodesic, sim5kerr-geod.h:42-68 (240 byt
 static_assert(sizeof(Geodesic) == 240, "geodesic ABI");
 
 /* csqrt of a real number (imaginary part +0), glibc semantics */
-S5_HD S5_INL Cplx csqrt_real(double x)
+template <class OPS>
+S5_HD S5_INL Cplx csqrt_real(OPS& o, double x)
 {
     if (x != x) return Cplx{x, x};
-    if (x < 0.0) return Cplx{0.0, sqrt(-x)};
-    return Cplx{fabs(sqrt(x)), 0.0};
+    if (x < 0.0) return Cplx{0.0, o.sqrt(-x)};
+    return Cplx{fabs(o.sqrt(x)), 0.0};
 }
 
 /* sim5math.c:49-58 */
@@ -62,7 +63,8 @@ S5_HD S5_INL int ensure_range(double* v, double lo, double hi, double acc)
 }
 
 /* roots of R(r), geodesic class, pericentre and R-integral to the pericentre.  sim5kerr-geod.c:985-1104 */
-S5_HD S5_MID int geodesic_R_roots(Geodesic* g, double r0, int* error, double* isn_inf = nullptr)
+template <class OPS>
+S5_HD S5_INL int geodesic_R_roots_t(OPS& o, Geodesic* g, double r0, int* error, double* isn_inf)
 {
     double a = g->a, l = g->l, q = g->q;
     double a2 = sq(a), l2 = sq(l);
@@ -74,17 +76,19 @@ S5_HD S5_MID int geodesic_R_roots(Geodesic* g, double r0, int* error, double* is
     F = -27. / 4. * (D * D * D) - 108. * a2 * q * D + 108. * sq(C);
     X = sq(F) - 4. * (E * E * E);
     if (X >= 0) {
-        double sX = sqrt(X);
+        double sX = o.sqrt(X);
         A = (F > sX ? +1 : -1) * 1. / 3. * crm::cr_pow_third(fabs(F - sX) / 2.) +
             (F > -sX ? +1 : -1) * 1. / 3. * crm::cr_pow_third(fabs(F + sX) / 2.);
     } else {
-        Z = sqrt(sq(F / 54.) + sq(sqrt(-X) / 54.));
-        z = cr_atan2(sqrt(-X) / 54., F / 54.);
-        A = crm::cr_pow_third(Z) * 2. * crm::cr_cos(z / 3.);
+        const double sX54 = o.div(o.sqrt(-X), 54.), F54 = o.div(F, 54.);
+        Z = o.sqrt(sq(F54) + sq(sX54));
+        z = cr_atan2(sX54, F54);
+        A = crm::cr_pow_third(Z) * 2. * crm::cr_cos(o.div(z, 3.));
     }
-    B = sqrt(A + D);
-    Cplx s12 = csqrt_real(-A + 2. * D - 4. * C / B);
-    Cplx s34 = csqrt_real(-A + 2. * D + 4. * C / B);
+    B = o.sqrt(A + D);
+    const double C4B = o.div(4. * C, B);
+    Cplx s12 = csqrt_real(o, -A + 2. * D - C4B);
+    Cplx s34 = csqrt_real(o, -A + 2. * D + C4B);
     Cplx p1 = Cplx{+B / 2. + .5 * s12.re,  .5 * s12.im};
     Cplx p2 = Cplx{+B / 2. - .5 * s12.re, -(.5 * s12.im)};
     Cplx p3 = Cplx{-B / 2. + .5 * s34.re,  .5 * s34.im};
@@ -137,12 +141,12 @@ S5_HD S5_MID int geodesic_R_roots(Geodesic* g, double r0, int* error, double* is
     switch (g->type) {
         case GEOD_TYPE_RR:
             r1 = g->r1.re; r2 = g->r2.re; r3 = g->r3.re; r4 = g->r4.re;
-            mm = ((r2 - r3) * (r1 - r4)) / ((r2 - r4) * (r1 - r3));
+            mm = o.div((r2 - r3) * (r1 - r4), (r2 - r4) * (r1 - r3));
             g->rp = r1;
             {
-                double u = jacobi_isn(sqrt((r2 - r4) / (r1 - r4)), mm);
+                double u = jacobi_isn(o.sqrt(o.div(r2 - r4, r1 - r4)), mm);
                 if (isn_inf) *isn_inf = u;          /* == the u1 of integral_R_rp_re_inf, sim5elliptic.c:1039-1040 */
-                g->Rpc = 2. / sqrt((r1 - r3) * (r2 - r4)) * u;
+                g->Rpc = o.div(2., o.sqrt((r1 - r3) * (r2 - r4))) * u;
             }
             break;
         case GEOD_TYPE_RR_BH:
@@ -153,11 +157,11 @@ S5_HD S5_MID int geodesic_R_roots(Geodesic* g, double r0, int* error, double* is
             break;
         case GEOD_TYPE_RC:
             r1 = g->r1.re; r2 = g->r2.re; u = g->r3.re; v = g->r3.im;
-            A = sqrt(sq(r1 - u) + sq(v));
-            B = sqrt(sq(r2 - u) + sq(v));
-            mm = (sq(A + B) - sq(r1 - r2)) / (4. * A * B);
+            A = o.sqrt(sq(r1 - u) + sq(v));
+            B = o.sqrt(sq(r2 - u) + sq(v));
+            mm = o.div(sq(A + B) - sq(r1 - r2), 4. * A * B);
             g->rp = r1;
-            g->Rpc = 1. / sqrt(A * B) * jacobi_icn((A - B) / (A + B), mm);
+            g->Rpc = o.div(1., o.sqrt(A * B)) * jacobi_icn(o.div(A - B, A + B), mm);
             break;
         default: {  /* CC */
             r1 = g->r1.re; r2 = g->r3.re; r3 = g->r1.im; r4 = g->r3.im;
@@ -172,9 +176,17 @@ S5_HD S5_MID int geodesic_R_roots(Geodesic* g, double r0, int* error, double* is
     }
     return 1;
 }
+S5_HD S5_MID int geodesic_R_roots(Geodesic* g, double r0, int* error, double* isn_inf = nullptr)
+{
+    ff::Quick f;
+    int rc = geodesic_R_roots_t(f, g, r0, error, isn_inf);
+    if (!f.ok) { ff::Plain p; rc = geodesic_R_roots_t(p, g, r0, error, isn_inf); }
+    return rc;
+}
 
 /* roots of Theta(mu).  sim5kerr-geod.c:1109-1184 (CPU branch: extended-precision m2m, m2p) */
-S5_HD S5_MID int geodesic_T_roots(Geodesic* g, double m, int* error)
+template <class OPS>
+S5_HD S5_INL int geodesic_T_roots_t(OPS& o, Geodesic* g, double m, int* error)
 {
     double a = g->a, l = g->l, q = g->q;
     double a2 = sq(a), l2 = sq(l);
@@ -185,10 +197,10 @@ S5_HD S5_MID int geodesic_T_roots(Geodesic* g, double m, int* error)
         return 0;
     }
     if (q > 0.0) {
-        g->mm = g->m2p / (g->m2p + g->m2m);
+        g->mm = o.div(g->m2p, g->m2p + g->m2m);
         if ((g->mm < 0.0) || (g->mm >= 1.0)) { if (error) *error = GD_ERROR_MM_RANGE; return 0; }
-        if (fabs(m) > sqrt(g->m2p)) { if (error) *error = GD_ERROR_MU0_RANGE; return 0; }
-        g->mK = 1. / sqrt(a2 * (g->m2p + g->m2m));
+        if (fabs(m) > o.sqrt(g->m2p)) { if (error) *error = GD_ERROR_MU0_RANGE; return 0; }
+        g->mK = o.div(1., o.sqrt(a2 * (g->m2p + g->m2m)));
     } else if (q < 0.0) {
         g->mm = (g->m2p + g->m2m) / g->m2p;
         if ((g->mm < 0.0) || (g->mm >= 1.0)) { if (error) *error = GD_ERROR_MM_RANGE; return 0; }
@@ -199,6 +211,13 @@ S5_HD S5_MID int geodesic_T_roots(Geodesic* g, double m, int* error)
         return 0;
     }
     return 1;
+}
+S5_HD S5_MID int geodesic_T_roots(Geodesic* g, double m, int* error)
+{
+    ff::Quick f;
+    int rc = geodesic_T_roots_t(f, g, m, error);
+    if (!f.ok) { ff::Plain p; rc = geodesic_T_roots_t(p, g, m, error); }
+    return rc;
 }
 
 S5_HD S5_INL double theta_int(const Geodesic* g, double x) { return g->mK * jacobi_icn(x / sqrt(g->m2p), g->mm); }
@@ -276,16 +295,17 @@ S5_HD S5_MID double geodesic_P_int(const Geodesic* g, double r, int ppc)
 }
 
 /* P -> r.  sim5kerr-geod.c:290-357 */
-S5_HD S5_MID double geodesic_position_rad(const Geodesic* g, double P)
+template <class OPS>
+S5_HD S5_INL double geodesic_position_rad_t(OPS& o, const Geodesic* g, double P)
 {
     if ((P <= 0.0) || (P >= 2. * g->Rpc)) return NAN;
     if (P == g->Rpc) return g->rp;
     if (g->type == GEOD_TYPE_RR) {
         double r1 = g->r1.re, r2 = g->r2.re, r3 = g->r3.re, r4 = g->r4.re;
-        double m4 = ((r2 - r3) * (r1 - r4)) / ((r2 - r4) * (r1 - r3));
-        double x4 = 0.5 * fabs(P - g->Rpc) * sqrt((r2 - r4) * (r1 - r3));
+        double m4 = o.div((r2 - r3) * (r1 - r4), (r2 - r4) * (r1 - r3));
+        double x4 = 0.5 * fabs(P - g->Rpc) * o.sqrt((r2 - r4) * (r1 - r3));
         double sn2 = sq(jacobi_sn(x4, m4));
-        return (r1 * (r2 - r4) - r2 * (r1 - r4) * sn2) / (r2 - r4 - (r1 - r4) * sn2);
+        return o.div(r1 * (r2 - r4) - r2 * (r1 - r4) * sn2, r2 - r4 - (r1 - r4) * sn2);
     }
     if (g->type == GEOD_TYPE_RC) {
         if (P > g->Rpc) return NAN;
@@ -297,6 +317,13 @@ S5_HD S5_MID double geodesic_position_rad(const Geodesic* g, double P)
         return (r2 * A - r1 * B - (r2 * A + r1 * B) * cn) / ((A - B) - (A + B) * cn);
     }
     return NAN;
+}
+S5_HD S5_MID double geodesic_position_rad(const Geodesic* g, double P)
+{
+    ff::Quick f;
+    double r = geodesic_position_rad_t(f, g, P);
+    if (!f.ok) { ff::Plain p; r = geodesic_position_rad_t(p, g, P); }
+    return r;
 }
 
 /* helper shared by the three polar routines: sign of d(mu)/dP at P and the start of the current theta-oscillation.

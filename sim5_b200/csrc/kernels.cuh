@@ -164,6 +164,10 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
         AzIn z;
         bool deferred = false;
         size_t i = 0;
+#if S5_EQ_DYN_SMEM_ON
+        extern __shared__ double s_dyn[];
+        Geodesic* const gslot = reinterpret_cast<Geodesic*>(reinterpret_cast<char*>(s_dyn) + (size_t)threadIdx.x * S5_GD_SLOT_BYTES);
+#endif
 #if !defined(S5_EQ_FREERUN) && !defined(S5_EQ_NO_STAGE_SYNC)
         {   /* every thread runs the routine (it has CTA barriers); threads past the end of the image trace its last pixel and drop the result */
             const bool valid = (long long)t < ntiles && p < npix;
@@ -173,8 +177,6 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
             int iy = s5_local_to_image_row(&c, lr);
             PixelOut o;
 #if defined(S5_EQ_SMEM_GD)
-            extern __shared__ double s_dyn[];
-            Geodesic* gslot = reinterpret_cast<Geodesic*>(reinterpret_cast<char*>(s_dyn) + (size_t)threadIdx.x * S5_GD_SLOT_BYTES);
             deferred = trace_eqplane_pixel_t<DEFER, DELAY, true, true>(c, ix, iy, &o, &z, gslot) && valid;
 #else
             deferred = trace_eqplane_pixel_t<DEFER, DELAY, true>(c, ix, iy, &o, &z) && valid;
@@ -223,9 +225,17 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
             if (slot >= 0) {
                 double* f = q.f + slot;
                 const long long cap = q.cap;
+#if S5_EQ_DYN_SMEM_ON && !defined(S5_EQ_FREERUN) && !defined(S5_EQ_NO_STAGE_SYNC)
+                /* the geodesic's share of the item goes from its shared-memory slot straight to the queue (az_make_tail filled the rest of z) */
+                const Geodesic* g = gslot;
+                S5_ST(&f[0 * cap], g->r1.re);  S5_ST(&f[1 * cap], g->r2.re);  S5_ST(&f[2 * cap], g->r3.re);   S5_ST(&f[3 * cap], is_rr ? g->r4.re : g->r3.im);
+                S5_ST(&f[4 * cap], g->l);   S5_ST(&f[5 * cap], g->m2m); S5_ST(&f[6 * cap], g->m2p);  S5_ST(&f[7 * cap], g->mm);
+                S5_ST(&f[8 * cap], g->Tpp); S5_ST(&f[9 * cap], g->Tip); S5_ST(&f[10 * cap], g->Rpc); S5_ST(&f[11 * cap], g->beta);
+#else
                 S5_ST(&f[0 * cap], z.e0);  S5_ST(&f[1 * cap], z.e1);  S5_ST(&f[2 * cap], z.e2);   S5_ST(&f[3 * cap], z.e3);
                 S5_ST(&f[4 * cap], z.l);   S5_ST(&f[5 * cap], z.m2m); S5_ST(&f[6 * cap], z.m2p);  S5_ST(&f[7 * cap], z.mm);
                 S5_ST(&f[8 * cap], z.Tpp); S5_ST(&f[9 * cap], z.Tip); S5_ST(&f[10 * cap], z.Rpc); S5_ST(&f[11 * cap], z.beta);
+#endif
                 S5_ST(&f[12 * cap], z.K_mm); S5_ST(&f[13 * cap], z.rf_u); S5_ST(&f[14 * cap], z.isn_inf); S5_ST(&f[15 * cap], z.r); S5_ST(&f[16 * cap], z.P);
                 S5_ST(&q.key[slot], (unsigned long long)i | ((unsigned long long)(z.nrr & 15) << 48) | ((unsigned long long)(z.rf_ok ? 1 : 0) << 56));
             }

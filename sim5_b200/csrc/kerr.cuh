@@ -261,10 +261,18 @@ S5_HD S5_INL double Omega_from_ell(double ell, const Metric* g) { return -(g->g0
 /* sim5kerr.c:1114-1124 */
 S5_HD S5_INL double ell_from_Omega(double Omega, const Metric* g) { return -(g->g03 + g->g33 * Omega) / (g->g00 + g->g03 * Omega); }
 /* sim5kerr.c:1127-1141 */
+template <class OPS>
+S5_HD S5_INL double gfactorK_t(OPS& o, double r, double a, double l)
+{
+    double Om = o.div(1., a + crm::cr_pow_1p5(r));
+    return o.div(o.sqrt(1. - o.div(2., r) * sq(1. - a * Om) - (r * r + a * a) * sq(Om)), 1. - Om * l);
+}
 S5_HD S5_MID double gfactorK(double r, double a, double l)
 {
-    double Om = 1. / (a + crm::cr_pow_1p5(r));
-    return sqrt(1. - 2. / r * sq(1. - a * Om) - (r * r + a * a) * sq(Om)) / (1. - Om * l);
+    ff::Quick f;
+    double g = gfactorK_t(f, r, a, l);
+    if (!f.ok) { ff::Plain p; g = gfactorK_t(p, r, a, l); }
+    return g;
 }
 /* sim5kerr.c:1295-1309 */
 S5_HD S5_INL void fourvelocity_azimuthal(double Omega, const Metric* g, double U[4])

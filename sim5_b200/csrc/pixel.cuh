@@ -47,16 +47,24 @@ S5_HD S5_INL void pixel_impact(const S5ImageConsts& c, int ix, int iy, double* a
 }
 
 /* Page-Thorne flux with the per-image pieces hoisted.  sim5disk-nt.c:109-146 */
-S5_HD S5_MID double disk_nt_flux(const S5ImageConsts& c, double r)
+template <class OPS>
+S5_HD S5_INL double disk_nt_flux_t(OPS& o, const S5ImageConsts& c, double r)
 {
     if (r <= c.nt_rms) return 0.0;
-    double x = sqrt(r);
-    double f0 = x - c.nt_x0 - c.nt_k0 * cr_log(x / c.nt_x0);
-    double f1 = c.nt_k1 * cr_log((x - c.nt_x1) / c.nt_d1);
-    double f2 = c.nt_k2 * cr_log((x - c.nt_x2) / c.nt_d2);
-    double f3 = c.nt_k3 * cr_log((x - c.nt_x3) / c.nt_d3);
-    double F = 1. / (c.nt_4pi * r) * 1.5 / (x * x * (x * x * x - 3. * x + c.nt_2a)) * (f0 - f1 - f2 - f3);
-    return 9.1721376255e+28 * F * c.nt_mdot / c.nt_mass;
+    double x = o.sqrt(r);
+    double f0 = x - c.nt_x0 - c.nt_k0 * cr_log(o.div(x, c.nt_x0));
+    double f1 = c.nt_k1 * cr_log(o.div(x - c.nt_x1, c.nt_d1));
+    double f2 = c.nt_k2 * cr_log(o.div(x - c.nt_x2, c.nt_d2));
+    double f3 = c.nt_k3 * cr_log(o.div(x - c.nt_x3, c.nt_d3));
+    double F = o.div(o.div(1., c.nt_4pi * r) * 1.5, x * x * (x * x * x - 3. * x + c.nt_2a)) * (f0 - f1 - f2 - f3);
+    return o.div(9.1721376255e+28 * F * c.nt_mdot, c.nt_mass);
+}
+S5_HD S5_MID double disk_nt_flux(const S5ImageConsts& c, double r)
+{
+    ff::Quick f;
+    double F = disk_nt_flux_t(f, c, r);
+    if (!f.ok) { ff::Plain p; F = disk_nt_flux_t(p, c, r); }
+    return F;
 }
 
 /* harness: Chandrasekhar limb polarization degree, linear interpolation (sim5_b200.h table) */
@@ -77,8 +85,16 @@ struct RayCache {
     double rf_u;        /* the R_F inside icn_u; equals the R_F of elliptic_pi_cos(cos_i/sqrt(m2p), ., mm) */
     double rf_u_z, rf_u_m;
     double isn_inf;     /* sn^-1 at r = infinity (RR rays): Rpc and both integral_R_rp_re_inf calls */
+    double u_pol;       /* cos_i / sqrt(m2p): the argument of icn_u, of every crossing order and of the rf_u test (the reference forms it 3-4 times) */
     bool have_rf_u;
 };
+S5_HD S5_INL double polar_amplitude(const Geodesic* g)
+{
+    ff::Quick o;
+    double u = o.div(g->cos_i, o.sqrt(g->m2p));
+    if (!o.ok) u = g->cos_i / sqrt(g->m2p);
+    return u;
+}
 
 /* geodesic_init_inf with the T-integrals' Carlson values kept for the crossings and the azimuth.
  * Same results as geodesic_init_inf_sc (geod.cuh). */
@@ -101,7 +117,8 @@ S5_HD S5_INL int init_inf_cached(const S5ImageConsts& c, double alpha, double be
     if (!geodesic_T_roots(g, g->cos_i, error)) return 0;
     /* theta_int(0) == mK*K(mm): jacobi_icn(0/sqrt(m2p), mm) takes its z == 0 exit (0 <= mm < 1 here) */
     k->K_mm = elliptic_k(g->mm);
-    k->icn_u = jacobi_icn_ex(g->cos_i / sqrt(g->m2p), g->mm, &k->rf_u, &k->rf_u_z, &k->rf_u_m, &k->have_rf_u);
+    k->u_pol = polar_amplitude(g);
+    k->icn_u = jacobi_icn_ex(k->u_pol, g->mm, &k->rf_u, &k->rf_u_z, &k->rf_u_m, &k->have_rf_u);
     g->Tpp = 2. * (g->mK * k->K_mm);
     g->Tip = g->mK * k->icn_u;
     *error = GD_OK;
@@ -111,7 +128,7 @@ S5_HD S5_INL int init_inf_cached(const S5ImageConsts& c, double alpha, double be
 S5_HD S5_INL double crossing_cached(const Geodesic* g, int order, const RayCache& k)
 {
     if (g->q <= 0.0) return NAN;
-    double u = g->cos_i / sqrt(g->m2p);
+    double u = k.u_pol;
     double u0 = u;
     if (!ensure_range(&u, -1.0, +1.0, 1e-4)) return NAN;
     double icn = (u == u0) ? k.icn_u : jacobi_icn(u, g->mm);
@@ -138,6 +155,17 @@ struct AzIn {
 };
 #define S5_AZ_NFIELDS 17
 
+/* the part of the item that is NOT in the geodesic struct (the lockstep kernels keep the geodesic in a shared-memory slot and copy its
+ * fields into the queue from there: the item never exists as a 160-byte local copy) */
+S5_HD S5_INL void az_make_tail(const Geodesic* g, const RayCache& k, double r, double P, AzIn* z)
+{
+    z->K_mm = k.K_mm; z->rf_u = k.rf_u; z->isn_inf = k.isn_inf;
+    z->r = r; z->P = P;
+    z->type = g->type; z->nrr = g->nrr;
+    /* m2p / (m2m + m2p) is g->mm for q > 0 (geodesic_T_roots: the same quotient of the same operands); q < 0 rays never hit the disk */
+    double tm = (g->q > 0.0) ? g->mm : g->m2p / (g->m2m + g->m2p);
+    z->rf_ok = k.have_rf_u && (k.rf_u_z == k.u_pol) && (k.rf_u_m == tm);
+}
 S5_HD S5_INL void az_make(const Geodesic* g, const RayCache& k, double r, double P, AzIn* z)
 {
     if (g->type == GEOD_TYPE_RR) { z->e0 = g->r1.re; z->e1 = g->r2.re; z->e2 = g->r3.re; z->e3 = g->r4.re; }
@@ -675,7 +703,8 @@ S5_HD S5_INL bool trace_eqplane_pixel_t(const S5ImageConsts& c, int ix, int iy, 
         else {
             /* theta_int(0) == mK*K(mm): jacobi_icn(0/sqrt(m2p), mm) takes its z == 0 exit (0 <= mm < 1 here) */
             k.K_mm = elliptic_k(gd.mm);
-            k.icn_u = jacobi_icn_ex(gd.cos_i / sqrt(gd.m2p), gd.mm, &k.rf_u, &k.rf_u_z, &k.rf_u_m, &k.have_rf_u);
+            k.u_pol = polar_amplitude(&gd);
+            k.icn_u = jacobi_icn_ex(k.u_pol, gd.mm, &k.rf_u, &k.rf_u_z, &k.rf_u_m, &k.have_rf_u);
             gd.Tpp = 2. * (gd.mK * k.K_mm);
             gd.Tip = gd.mK * k.icn_u;
         }
@@ -714,7 +743,10 @@ S5_HD S5_INL bool trace_eqplane_pixel_t(const S5ImageConsts& c, int ix, int iy, 
         o->r = r;
         if (c.outputs & SIM5_OUT_PHI) {
             if (DEFER) {
-                if (gd.type == GEOD_TYPE_RR || gd.type == GEOD_TYPE_RC) { az_make(&gd, k, r, P, defer); deferred = true; }
+                if (gd.type == GEOD_TYPE_RR || gd.type == GEOD_TYPE_RC) {
+                    if (SGD) az_make_tail(&gd, k, r, P, defer); else az_make(&gd, k, r, P, defer);
+                    deferred = true;
+                }
                 else o->phi = NAN;               /* geodesic_position_azm returns NaN for the other types */
             } else {
                 o->phi = (c.flags & SIM5_FLAG_EXACT_AZIMUTH) ? azimuth_equatorial(&gd, k, r, P) : azimuth_equatorial_default(&gd, k, r, P);
