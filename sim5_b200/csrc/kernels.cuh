@@ -39,11 +39,25 @@ struct DevStats {                 /* device-side counters, flushed once per CTA 
  * front, RC items from the back of the same arrays, so each phase-B launch sees one geodesic type only */
 struct AzQueue {
     double* f;                    /* [S5_AZ_NFIELDS][cap] */
-    unsigned long long* key;      /* [cap]: bits 0..47 output index, bits 48..51 nrr, bit 56 rf_ok */
+    unsigned long long* key;      /* [cap]: bits 0..47 output index, 48..51 nrr, 52 ppc, 53 beta >= 0, 54 turn (AzIn), 56 rf_ok */
     unsigned long long* count;    /* [0] RR items, [1] RC items, [2] RR / [3] RC items the tolerance-mode kernel handed back (redo lists) */
     unsigned* redo;               /* [cap] slots of those items: RR from the front, RC from the back */
     long long cap;                /* 0: no queue -> the azimuth is computed inline by phase A */
 };
+
+S5_HD S5_INL unsigned long long az_key(size_t i, const AzIn& z)
+{
+    return (unsigned long long)i | ((unsigned long long)(z.nrr & 15) << 48) | ((unsigned long long)(z.ppc ? 1 : 0) << 52) |
+           ((unsigned long long)(z.beta_nonneg ? 1 : 0) << 53) | ((unsigned long long)(z.turn ? 1 : 0) << 54) | ((unsigned long long)(z.rf_ok ? 1 : 0) << 56);
+}
+S5_HD S5_INL void az_unkey(unsigned long long key, AzIn* z)
+{
+    z->nrr = (int)((key >> 48) & 15);
+    z->ppc = ((key >> 52) & 1) != 0;
+    z->beta_nonneg = ((key >> 53) & 1) != 0;
+    z->turn = ((key >> 54) & 1) != 0;
+    z->rf_ok = ((key >> 56) & 1) != 0;
+}
 
 #define S5_CTA_THREADS 128
 #ifndef S5_EQ_THREADS
@@ -229,15 +243,13 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
                 /* the geodesic's share of the item goes from its shared-memory slot straight to the queue (az_make_tail filled the rest of z) */
                 const Geodesic* g = gslot;
                 S5_ST(&f[0 * cap], g->r1.re);  S5_ST(&f[1 * cap], g->r2.re);  S5_ST(&f[2 * cap], g->r3.re);   S5_ST(&f[3 * cap], is_rr ? g->r4.re : g->r3.im);
-                S5_ST(&f[4 * cap], g->l);   S5_ST(&f[5 * cap], g->m2m); S5_ST(&f[6 * cap], g->m2p);  S5_ST(&f[7 * cap], g->mm);
-                S5_ST(&f[8 * cap], g->Tpp); S5_ST(&f[9 * cap], g->Tip); S5_ST(&f[10 * cap], g->Rpc); S5_ST(&f[11 * cap], g->beta);
+                S5_ST(&f[4 * cap], g->l);   S5_ST(&f[5 * cap], g->m2m); S5_ST(&f[6 * cap], g->m2p);
 #else
                 S5_ST(&f[0 * cap], z.e0);  S5_ST(&f[1 * cap], z.e1);  S5_ST(&f[2 * cap], z.e2);   S5_ST(&f[3 * cap], z.e3);
-                S5_ST(&f[4 * cap], z.l);   S5_ST(&f[5 * cap], z.m2m); S5_ST(&f[6 * cap], z.m2p);  S5_ST(&f[7 * cap], z.mm);
-                S5_ST(&f[8 * cap], z.Tpp); S5_ST(&f[9 * cap], z.Tip); S5_ST(&f[10 * cap], z.Rpc); S5_ST(&f[11 * cap], z.beta);
+                S5_ST(&f[4 * cap], z.l);   S5_ST(&f[5 * cap], z.m2m); S5_ST(&f[6 * cap], z.m2p);
 #endif
-                S5_ST(&f[12 * cap], z.K_mm); S5_ST(&f[13 * cap], z.rf_u); S5_ST(&f[14 * cap], z.isn_inf); S5_ST(&f[15 * cap], z.r); S5_ST(&f[16 * cap], z.P);
-                S5_ST(&q.key[slot], (unsigned long long)i | ((unsigned long long)(z.nrr & 15) << 48) | ((unsigned long long)(z.rf_ok ? 1 : 0) << 56));
+                S5_ST(&f[7 * cap], z.r); S5_ST(&f[8 * cap], z.K_mm); S5_ST(&f[9 * cap], z.rf_u); S5_ST(&f[10 * cap], z.isn_inf);
+                S5_ST(&q.key[slot], az_key(i, z));
             }
         }
       }
@@ -277,14 +289,13 @@ k_azimuth(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double* __re
             const double* f = q.f + slot;
             AzIn z;
             z.e0 = f[0 * cap];  z.e1 = f[1 * cap];  z.e2 = f[2 * cap];   z.e3 = f[3 * cap];
-            z.l = f[4 * cap];   z.m2m = f[5 * cap]; z.m2p = f[6 * cap];  z.mm = f[7 * cap];
-            z.Tpp = f[8 * cap]; z.Tip = f[9 * cap]; z.Rpc = f[10 * cap]; z.beta = f[11 * cap];
-            z.K_mm = f[12 * cap]; z.rf_u = f[13 * cap]; z.isn_inf = f[14 * cap]; z.r = f[15 * cap]; z.P = f[16 * cap];
+            z.l = f[4 * cap];   z.m2m = f[5 * cap]; z.m2p = f[6 * cap];  z.r = f[7 * cap];
+            z.K_mm = f[8 * cap]; z.rf_u = f[9 * cap]; z.isn_inf = f[10 * cap];
+            z.mm = z.m2p / (z.m2p + z.m2m);          /* == g->mm (geodesic_T_roots, q > 0) */
             unsigned long long key = q.key[slot];
             z.a = a_eff; z.cos_i = cos_i;
             z.type = TYPE;
-            z.nrr = (int)((key >> 48) & 15);
-            z.rf_ok = ((key >> 56) & 1) != 0;
+            az_unkey(key, &z);
             double v = azimuth_from_t<true>(z);
             if (valid) phi[key & 0xffffffffffffULL] = v;
         }
@@ -320,13 +331,17 @@ k_azimuth_fast(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double*
         const double* f = q.f + slot;
         AzIn z;
         z.e0 = f[0 * cap];  z.e1 = f[1 * cap];  z.e2 = f[2 * cap];   z.e3 = f[3 * cap];
-        z.l = f[4 * cap];   z.m2m = f[5 * cap]; z.m2p = f[6 * cap];  z.mm = f[7 * cap];
-        z.Tpp = f[8 * cap]; z.Tip = f[9 * cap]; z.Rpc = f[10 * cap]; z.beta = f[11 * cap];
-        z.K_mm = f[12 * cap]; z.rf_u = 0.0; z.isn_inf = 0.0; z.r = f[15 * cap]; z.P = f[16 * cap];
+        z.l = f[4 * cap];   z.m2m = f[5 * cap]; z.m2p = f[6 * cap];  z.r = f[7 * cap];
+#if defined(S5_POLAR_DUPLICATION)
+        z.K_mm = f[8 * cap]; z.mm = z.m2p / (z.m2p + z.m2m);
+#else
+        z.K_mm = 0.0; z.mm = 0.0;                    /* not used by the tolerance-mode routines (the complete Pi is an AGM of its own) */
+#endif
+        z.rf_u = 0.0; z.isn_inf = 0.0;
         unsigned long long key = q.key[slot];
         z.a = a_eff; z.cos_i = cos_i;
         z.type = is_rr ? GEOD_TYPE_RR : GEOD_TYPE_RC;
-        z.nrr = (int)((key >> 48) & 15);
+        az_unkey(key, &z);
         z.rf_ok = false;
         bool ok;
         double v = is_rr ? azimuth_fast_rr(z, &ok) : azimuth_fast_rc(z, &ok);

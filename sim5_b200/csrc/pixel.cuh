@@ -146,21 +146,38 @@ S5_HD S5_INL double crossing_cached(const Geodesic* g, int order, const RayCache
  * occupancy than one fused kernel, and phase B is free of RR/RC divergence. */
 struct AzIn {
     double e0, e1, e2, e3;      /* RR: r1..r4 (real) ; RC: r1, r2, Re r3, Im r3 */
-    double l, m2m, m2p, mm, Tpp, Tip, Rpc, beta;
+    double l, m2m, m2p, mm;
     double K_mm, rf_u, isn_inf;
-    double r, P;
+    double r;
     double a, cos_i;            /* per-image: the clamped spin g->a and cos(i) */
     int type, nrr;
     bool rf_ok;                 /* rf_u is the R_F of elliptic_pi_cos(cos_i/sqrt(m2p), ., m2p/(m2m+m2p)) */
+    /* the three decisions geodesic_position_azm takes from P, Rpc, Tpp, Tip and beta (sim5kerr-geod.c:476, 528-546), taken where those
+     * numbers are (phase A) and queued as three bits of the key instead of five doubles */
+    bool ppc;                   /* (nrr > 0) && (P > Rpc): the hit lies behind the radial turning point */
+    bool beta_nonneg;           /* beta >= 0 */
+    bool turn;                  /* P >= T + Tpp with T = -(Tpp - Tip) (beta >= 0) or -Tip: the hit lies behind the first polar turning point */
 };
-#define S5_AZ_NFIELDS 17
+/* queue item: e0 e1 e2 e3 l m2m m2p r | K_mm rf_u isn_inf -- the tolerance-mode kernel reads the first 8, the bit-faithful one all 11;
+ * mm = m2p / (m2m + m2p) is re-formed by the reader (the same quotient of the same operands as geodesic_T_roots forms for q > 0, and only
+ * q > 0 rays cross the equatorial plane) */
+#define S5_AZ_NFIELDS 11
+#define S5_AZ_NFAST 8
+S5_HD S5_INL void az_decide(const Geodesic* g, double P, AzIn* z)
+{
+    z->ppc = (g->nrr > 0) && (P > g->Rpc);
+    z->beta_nonneg = (g->beta >= 0.0);
+    double T = z->beta_nonneg ? -(g->Tpp - g->Tip) : -g->Tip;
+    z->turn = (P >= T + g->Tpp);
+}
 
 /* the part of the item that is NOT in the geodesic struct (the lockstep kernels keep the geodesic in a shared-memory slot and copy its
  * fields into the queue from there: the item never exists as a 160-byte local copy) */
 S5_HD S5_INL void az_make_tail(const Geodesic* g, const RayCache& k, double r, double P, AzIn* z)
 {
     z->K_mm = k.K_mm; z->rf_u = k.rf_u; z->isn_inf = k.isn_inf;
-    z->r = r; z->P = P;
+    z->r = r;
+    az_decide(g, P, z);
     z->type = g->type; z->nrr = g->nrr;
     /* m2p / (m2m + m2p) is g->mm for q > 0 (geodesic_T_roots: the same quotient of the same operands); q < 0 rays never hit the disk */
     double tm = (g->q > 0.0) ? g->mm : g->m2p / (g->m2m + g->m2p);
@@ -170,9 +187,10 @@ S5_HD S5_INL void az_make(const Geodesic* g, const RayCache& k, double r, double
 {
     if (g->type == GEOD_TYPE_RR) { z->e0 = g->r1.re; z->e1 = g->r2.re; z->e2 = g->r3.re; z->e3 = g->r4.re; }
     else                          { z->e0 = g->r1.re; z->e1 = g->r2.re; z->e2 = g->r3.re; z->e3 = g->r3.im; }
-    z->l = g->l; z->m2m = g->m2m; z->m2p = g->m2p; z->mm = g->mm; z->Tpp = g->Tpp; z->Tip = g->Tip; z->Rpc = g->Rpc; z->beta = g->beta;
+    z->l = g->l; z->m2m = g->m2m; z->m2p = g->m2p; z->mm = g->mm;
+    az_decide(g, P, z);
     z->K_mm = k.K_mm; z->rf_u = k.rf_u; z->isn_inf = k.isn_inf;
-    z->r = r; z->P = P; z->a = g->a; z->cos_i = g->cos_i;
+    z->r = r; z->a = g->a; z->cos_i = g->cos_i;
     z->type = g->type; z->nrr = g->nrr;
     double tm = g->m2p / (g->m2m + g->m2p);
     z->rf_ok = k.have_rf_u && (k.rf_u_z == g->cos_i / sqrt(g->m2p)) && (k.rf_u_m == tm);
@@ -195,7 +213,7 @@ template <bool SYNC>
 S5_HD S5_MID double azimuth_from_t(const AzIn& z)
 {
     double phi = 0.0;
-    int ppc = (z.nrr > 0) && (z.P > z.Rpc);
+    int ppc = z.ppc;
     double a2 = sq(z.a);
     double rp = 1. + sqrt(1. - a2);
     double rm = 1. - sqrt(1. - a2);
@@ -274,17 +292,13 @@ S5_HD S5_MID double azimuth_from_t(const AzIn& z)
         phi_ip = z.l / z.a * integral_T_mp(z.m2m, z.m2p, 1.0, z.cos_i);
     }
 
-    double T;
-    double sign_dm = (z.beta >= 0.0) ? +1.0 : -1.0;
+    double sign_dm = z.beta_nonneg ? +1.0 : -1.0;
     if (sign_dm > 0.0) {
-        T = -(z.Tpp - z.Tip);
         phi -= phi_pp - phi_ip;
     } else {
-        T = -z.Tip;
         phi -= phi_ip;
     }
-    if (z.P >= T + z.Tpp) {
-        T += z.Tpp;
+    if (z.turn) {
         phi += phi_pp;
         sign_dm = -sign_dm;
     }
@@ -387,29 +401,26 @@ S5_HD S5_MID double azimuth_fast_polar(const AzIn& z, bool* ok, float* mag)
     if (!gp) { qc = pc = cu2 = qu = pu = 1.0; good = false; }
 #if defined(S5_POLAR_DUPLICATION)
     double rfK = (tm == z.mm) ? z.K_mm : rf_hi(0.0, qc, 1.0);
-    double comp = rfK + tn * rj_hi(0.0, qc, 1.0, pc) * (1.0 / 3.0);
+    double comp = rfK + tn * rj_hi(0.0, qc, 1.0, pc) * HK(THIRD);
 #else
     double comp = cel_pi_hi(qc, pc);                 /* complete Pi(tn | tm): AGM instead of a duplication sequence */
 #endif
     double Fu, Ju;
     rfj_hi<1, true>(cu2, qu, 1.0, &pu, &Fu, &Ju);
-    double vu = ff::sqrt_ap0(1.0 - cu2) * (Fu - ns2 * Ju * (1.0 / 3.0));
+    double vu = ff::sqrt_ap0(1.0 - cu2) * (Fu - ns2 * Ju * HK(THIRD));
     double la = ff::div_ap(z.l, z.a);
     double T0 = tpre * comp;
     double phi_pp = 2.0 * la * T0;
     double phi_mp = la * T0;
     double phi_ip = la * (tpre * vu);
 
-    double T;
-    double sign_dm = (z.beta >= 0.0) ? +1.0 : -1.0;
+    double sign_dm = z.beta_nonneg ? +1.0 : -1.0;
     if (sign_dm > 0.0) {
-        T = -(z.Tpp - z.Tip);
         phi -= phi_pp - phi_ip;
     } else {
-        T = -z.Tip;
         phi -= phi_ip;
     }
-    if (z.P >= T + z.Tpp) {
+    if (z.turn) {
         phi += phi_pp;
         sign_dm = -sign_dm;
     }
@@ -452,8 +463,8 @@ S5_HD S5_INL bool rr_limit(double s2, double c2, double m2, double aa2, double c
     rfj_hi<2, true>(c2, q, 1.0, pp, &F, J);
     double sn = ff::sqrt_ap0(s2);
     double u = sn * F;
-    double Pp = sn * (F + c2p * s2 * pv_finish(J[0], F, t0) * (1.0 / 3.0));
-    double Pm = sn * (F + c2m * s2 * pv_finish(J[1], F, t1) * (1.0 / 3.0));
+    double Pp = sn * (F + c2p * s2 * pv_finish(J[0], F, t0) * HK(THIRD));
+    double Pm = sn * (F + c2m * s2 * pv_finish(J[1], F, t1) * HK(THIRD));
     br[0] += sgn * ((c2p - aa2) * Pp + aa2 * u);
     br[1] += sgn * ((c2m - aa2) * Pm + aa2 * u);
     float csd = ff::sqrtf_ap(gf(c2) * gf(s2) * gf(q));
@@ -466,7 +477,7 @@ S5_HD S5_INL bool rr_limit(double s2, double c2, double m2, double aa2, double c
 S5_HD S5_MID double azimuth_fast_rr(const AzIn& z, bool* ok)
 {
     const double r = z.r;
-    int ppc = (z.nrr > 0) && (z.P > z.Rpc);
+    int ppc = z.ppc;
     double a2 = sq(z.a);
     double sq1 = ff::sqrt_ap(1. - a2);
     double rp = 1. + sq1, rm = 1. - sq1;
@@ -553,8 +564,8 @@ S5_HD S5_MID double azimuth_fast_rc(const AzIn& z, bool* ok)
         nP[j][0] = amp_noise(csd, (float)pp[0]);
         nP[j][1] = amp_noise(csd, (float)pp[1]);
         Fh[j] = s * F;
-        Ph[j][0] = s * (F + nn[0] * s2 * pv_finish(J[0], F, t0) * (1.0 / 3.0));
-        Ph[j][1] = s * (F + nn[1] * s2 * pv_finish(J[1], F, t1) * (1.0 / 3.0));
+        Ph[j][0] = s * (F + nn[0] * s2 * pv_finish(J[0], F, t0) * HK(THIRD));
+        Ph[j][1] = s * (F + nn[1] * s2 * pv_finish(J[1], F, t1) * HK(THIRD));
         #pragma unroll
         for (int k = 0; k < 2; k++) {
             double am = fabs(mma[k]);
@@ -580,8 +591,8 @@ S5_HD S5_MID double azimuth_fast_rc(const AzIn& z, bool* ok)
         if (!(hi_domain_p(pt[0]) && hi_domain_p(pt[1]))) { pt[0] = pt[1] = 1.0; good = false; }
         double J[2];
         rfj_hi<2, true>(0.0, qc, 1.0, pt, &Kc, J);
-        Pc[0] = Kc + nn[0] * pv_finish(J[0], Kc, t0) * (1.0 / 3.0);
-        Pc[1] = Kc + nn[1] * pv_finish(J[1], Kc, t1) * (1.0 / 3.0);
+        Pc[0] = Kc + nn[0] * pv_finish(J[0], Kc, t0) * HK(THIRD);
+        Pc[1] = Kc + nn[1] * pv_finish(J[1], Kc, t1) * HK(THIRD);
     }
     /* u(c) = F_cos(c): F(|c|) or 2K - F(|c|); Pi_cos alike.  index 0 = at r (u1), 1 = at infinity (u2) */
     double uu[2], AB[2];
