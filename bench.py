@@ -83,7 +83,7 @@ def config_dict(abi, cfg, p, n_gpus, gather="peer", extra=None):
         l2 = "no input reads (rays are generated from the pixel index); no per-pixel output, the 4 MB histogram is accumulated with atomics in L2"
     else:
         par = ("one GPU, whole image" if n_gpus == 1 else
-               "rows interleaved over %d GPUs in 32-row blocks; %s" % (n_gpus, "every rank stores its rows into rank 0's image planes over NVLink peer memory (CUDA IPC), barrier at the end"
+               "rows interleaved over %d GPUs in 32-row blocks; %s" % (n_gpus, "every rank's rows land in rank 0's image planes over NVLink peer memory (CUDA IPC; copy-engine transfers of the finished row blocks under the next step's kernels), barrier at the end"
                                                                        if gather == "peer" else "NCCL gather of compact planes to rank 0 + re-assembly"))
         mb = n * n * bpr // 1000000
         l2 = "no input reads (rays are generated from the pixel index); %d MB of output planes per step %s 126 MB L2, written with streaming stores" % (mb, ">" if mb > 126 else "<")
@@ -320,6 +320,10 @@ def run_ours(args):
         # the image lives in rank 0's HBM; every rank maps those planes (CUDA IPC, peer access over NVLink/NVSwitch) and its kernels store
         # their interleaved row blocks straight into the final image: the transfer rides under the FP64 work, no gather, no re-assembly
         p.flags |= abi.FLAG_FULL_INDEX
+        if rank != 0 and args.peer_copy == "dma":
+            # ... by DMA: the rank traces into local compact planes and the copy engine moves the finished row blocks into rank 0's image
+            # under the next step's kernels (8-byte stores from 7 kernels at once saturate rank 0's NVLink ingress and stretch phase A by 50 %)
+            p.flags |= abi.FLAG_STAGE_COPY
         if rank == 0:
             image = api.DevicePlanes(p, names=names)
             blob = [image.handles()]
@@ -677,6 +681,9 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N>1: 'peer' = every rank stores its rows into rank 0's image over NVLink peer memory (default); "
                          "'nccl' = compact planes + torch.distributed gather + re-assembly on rank 0 (A/B)")
+    ap.add_argument("--peer-copy", default="dma", choices=["dma", "stores"],
+                    help="N>1 with --gather peer: 'dma' = ranks 1..N-1 trace into local planes and the copy engine moves their row blocks into rank 0's image "
+                         "under the next step's kernels (default); 'stores' = their kernels store straight into rank 0's planes over NVLink (A/B)")
     ap.add_argument("--defer-redo", default="auto", choices=["auto", "on", "off"], help="SIM5_FLAG_DEFER_REDO for the timed train (auto: only with more than one GPU)")
     ap.add_argument("--exact-azimuth", action="store_true", help="A/B: bit-faithful azimuth kernels (SIM5_FLAG_EXACT_AZIMUTH) instead of the tolerance-mode default")
     args = ap.parse_args()

@@ -81,6 +81,12 @@ extern "C" {
                                         latency-bound wave over ~0.3 % of the rays) are left running on the library's auxiliary stream while the NEXT
                                         call's tracing kernel starts (two alternating work queues).  phi of a call is complete once sim5_join() has been
                                         enqueued on / sim5_synchronize() has returned for the launch stream */
+#define SIM5_FLAG_STAGE_COPY   0x100 /* with DEVICE_PTRS | ASYNC | FULL_INDEX and split_count > 1 (the planes are another GPU's, mapped with sim5_ipc_import): trace into
+                                        library-owned compact planes in LOCAL memory and move the finished row blocks into the caller's full-image planes with the
+                                        copy engine (one strided 2-D copy per plane on the library's copy stream, two alternating scratch sets), so the transfer of
+                                        image k rides under the kernels of image k+1 instead of every plane store crossing NVLink.  With 8 GPUs the ~70 MB per GPU
+                                        and image otherwise arrive at the assembling GPU as 8-byte stores from 7 kernels at once and stretch their tracing kernels
+                                        by 50 % (profiles/r05m_bench_cfg2_n8.json).  The planes are complete after sim5_join() / sim5_synchronize() */
 #define SIM5_FLAG_ASYNC         0x4  /* with DEVICE_PTRS: enqueue on the library stream (sim5_set_stream) and return without
                                         synchronising; stats are not filled.  Pair with sim5_synchronize(). */
 

@@ -88,6 +88,11 @@ struct Context {
     cudaEvent_t ev_redo_done[2] = {nullptr, nullptr}, ev_fast_done = nullptr;
     bool redo_pending[2] = {false, false};
     int defer_buf = 0;
+    /* SIM5_FLAG_STAGE_COPY: two alternating sets of local compact planes; the copy of set s to the caller's (peer) planes ends at ev_stage_done[s] */
+    Plane stage[2][SIM5_NPLANES];
+    cudaEvent_t ev_stage_done[2] = {nullptr, nullptr}, ev_stage_go = nullptr;
+    bool stage_pending[2] = {false, false};
+    int stage_buf = 0;
     unsigned long long* last_counts = nullptr;           /* queue counts of the most recent image call (sim5_last_phase_ms) */
     void* batch[8] = {nullptr};
     size_t batch_bytes[8] = {0};
@@ -187,6 +192,10 @@ int ensure_init(int device)
     CK(cudaEventCreateWithFlags(&c.ev_redo_done[0], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.ev_redo_done[1], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.ev_fast_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c.ev_stage_done[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c.ev_stage_done[1], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c.ev_stage_go, cudaEventDisableTiming));
+    c.stage_pending[0] = c.stage_pending[1] = false; c.stage_buf = 0;
     c.redo_pending[0] = c.redo_pending[1] = false; c.defer_buf = 0; c.last_counts = c.d_counter + 4;
     c.d_stats = (DevStats*)(c.d_counter + 8);
     CK(cudaHostAlloc((void**)&c.h_stats, sizeof(DevStats), cudaHostAllocDefault));
@@ -417,6 +426,10 @@ void shutdown_ctx(Context& c)
     if (c.azq2_key.p) cudaFree(c.azq2_key.p); c.azq2_key = Plane();
     if (c.azq2_redo.p) cudaFree(c.azq2_redo.p); c.azq2_redo = Plane();
     c.d_counter2 = nullptr;
+    cudaStreamSynchronize(c.copy_stream);
+    for (int b = 0; b < 2; b++) for (auto& pl : c.stage[b]) { if (pl.p) cudaFree(pl.p); pl = Plane(); }
+    cudaEventDestroy(c.ev_stage_done[0]); cudaEventDestroy(c.ev_stage_done[1]); cudaEventDestroy(c.ev_stage_go);
+    c.stage_pending[0] = c.stage_pending[1] = false;
     cudaEventDestroy(c.ev_redo_done[0]); cudaEventDestroy(c.ev_redo_done[1]); cudaEventDestroy(c.ev_fast_done);
     for (int i = 0; i < 8; i++) { if (c.batch[i]) cudaFree(c.batch[i]); c.batch[i] = nullptr; c.batch_bytes[i] = 0; }
     cudaFreeHost(c.h_scr); cudaFreeHost(c.h_consts); cudaFree(c.d_consts); cudaFree(c.d_counter); c.d_counter = nullptr; c.d_stats = nullptr; cudaFreeHost(c.h_stats);
@@ -467,6 +480,13 @@ int join_deferred(Context& c, int only_buf /* -1: all */)
         if (!c.redo_pending[b] || (only_buf >= 0 && b != only_buf)) continue;
         CK(cudaStreamWaitEvent(c.stream, c.ev_redo_done[b], 0));
         c.redo_pending[b] = false;
+    }
+    if (only_buf < 0) {
+        for (int b = 0; b < 2; b++) {                  /* ... and for the staged plane copies of SIM5_FLAG_STAGE_COPY calls */
+            if (!c.stage_pending[b]) continue;
+            CK(cudaStreamWaitEvent(c.stream, c.ev_stage_done[b], 0));
+            c.stage_pending[b] = false;
+        }
     }
     return SIM5_OK;
 }
@@ -652,8 +672,22 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     DevOut d;
     memset(&d, 0, sizeof d);
     d.compact = (!devptr || (split > 1 && !(p->flags & SIM5_FLAG_FULL_INDEX))) ? 1 : 0;
+    const bool stage_copy = devptr && async && split > 1 && npix > 0 && (p->flags & SIM5_FLAG_FULL_INDEX) && (p->flags & SIM5_FLAG_STAGE_COPY);
+    int sb = 0;
+    if (stage_copy) {
+        sb = c.stage_buf;
+        c.stage_buf ^= 1;
+        if (c.stage_pending[sb]) { CK(cudaStreamWaitEvent(c.stream, c.ev_stage_done[sb], 0)); c.stage_pending[sb] = false; }      /* the set is free again */
+        d.compact = 1;
+    }
     for (int i = 0; i < SIM5_NPLANES; i++) {
         if (!(p->outputs & kPlaneInfo[i].bit)) continue;
+        if (stage_copy) {
+            rc = reserve(c.stage[sb][i], npix * kPlaneInfo[i].elem);
+            if (rc) return rc;
+            set_dev_plane(&d, i, c.stage[sb][i].p);
+            continue;
+        }
         if (devptr) { set_dev_plane(&d, i, host_plane(out, i)); continue; }
         rc = reserve(c.planes[i], (npix ? npix : 1) * kPlaneInfo[i].elem);
         if (rc) return rc;
@@ -857,6 +891,21 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                 }
             }
         }
+    }
+    if (stage_copy) {
+        /* the finished row blocks go to the caller's full-image planes by DMA: block j of this call is srows rows, `split` blocks apart in the image */
+        CK(cudaEventRecord(c.ev_stage_go, c.stream));
+        CK(cudaStreamWaitEvent(c.copy_stream, c.ev_stage_go, 0));
+        if (defer) CK(cudaStreamWaitEvent(c.copy_stream, c.ev_redo_done[(cnt == c.d_counter2) ? 0 : 1], 0));      /* phi is complete after the redo passes */
+        for (int i = 0; i < SIM5_NPLANES; i++) {
+            if (!(p->outputs & kPlaneInfo[i].bit)) continue;
+            const size_t es = kPlaneInfo[i].elem;
+            const size_t blk = (size_t)srows * p->nx * es;
+            char* dst = (char*)host_plane(out, i) + ((size_t)rb + (size_t)p->split_index * srows) * p->nx * es;
+            CK(cudaMemcpy2DAsync(dst, blk * split, c.stage[sb][i].p, blk, blk, (size_t)(nrows_local / srows), cudaMemcpyDeviceToDevice, c.copy_stream));
+        }
+        CK(cudaEventRecord(c.ev_stage_done[sb], c.copy_stream));
+        c.stage_pending[sb] = true;
     }
     c.phases = (nchunks == 1) ? launches : 0;      /* per-kernel times are defined for single-chunk calls only */
     c.ring_phases[c.ring_pos] = c.phases;

@@ -455,6 +455,14 @@ k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigne
                 if (p < npix) {
                     int lr = (int)(p / nx);
                     int ix = (int)(p - (long long)lr * nx);
+                    if (PROG::CENTER_OUT) {
+                        /* longest rays first: the k-th row handed out is the k-th closest to the middle of this call's rows (mid, mid-1, mid+1, ...).
+                         * The rays that take the most steps pass closest to the hole, i.e. sit in the middle rows; started last they ARE the tail of the
+                         * kernel (a ray cannot be split: 8000 steps x ~7 us), started first the cheap outer rows fill in behind them */
+                        const int nr = c.nrows_local, mid = nr >> 1;
+                        lr = (lr & 1) ? mid - ((lr + 1) >> 1) : mid + (lr >> 1);
+                        p = (long long)lr * nx + ix;
+                    }
                     int iy = s5_local_to_image_row(&c, lr);
                     PixelOut o;
                     mypix = p;

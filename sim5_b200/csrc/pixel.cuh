@@ -1119,6 +1119,11 @@ struct StepwiseProg {
     /* the step in two parts: `slow` (the RK4 fallback, 0.3 % of the steps, ~4 steps' worth of work) is held back until DEFER_MIN lanes of the
      * warp want it (or no lane can do anything else).  Per-ray arithmetic and order are unchanged.  tools/step_stats.cpp: with 32 lanes a warp
      * met an RK4 step in 8.9 % of its rounds and idled 31 lanes for it */
+#if defined(S5_STEP_ROW_MAJOR)
+    static const bool CENTER_OUT = false;
+#else
+    static const bool CENTER_OUT = true;          /* hand the rows out from the middle of the image outwards (k_trace_lanes) */
+#endif
     static const bool DEFERS = (S5_RK4_BATCH > 1);
     static const int DEFER_MIN = S5_RK4_BATCH;
     static S5_HD S5_INL bool try_step(const S5ImageConsts& c, State* s) { return stepwise_try(c, s); }
@@ -1156,6 +1161,7 @@ struct SurfaceProg {
     static const int BATCH = S5_SURF_BATCH;
     static S5_HD S5_INL bool start(const S5ImageConsts& c, int ix, int iy, State* s, PixelOut* o) { return surface_start(c, ix, iy, s, o); }
     /* the kernel's protocol is "0 while live"; SIM5_ST_HIT0 is 0, so the class travels with bit 8 set */
+    static const bool CENTER_OUT = false;
     static const bool DEFERS = false;
     static const int DEFER_MIN = 1;
     static S5_HD S5_INL bool try_step(const S5ImageConsts&, State*) { return false; }

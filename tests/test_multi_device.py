@@ -117,3 +117,30 @@ def test_chunks_ignore_split_rows_without_a_split(gpu_api):
             assert np.array_equal(ref[k], got[k], equal_nan=True), k
     finally:
         L.sim5_set_chunk_rays(0)
+
+
+def test_stage_copy_assembles_the_image_by_dma(gpu_api):
+    """SIM5_FLAG_STAGE_COPY: the calls of an interleaved split trace into library-owned compact planes and the finished row blocks are
+    moved into ONE full-image set of planes by strided 2-D copies on the copy stream (what the ranks of a multi-GPU job do with the
+    assembling rank's peer-mapped planes); a train of such calls, with and without deferred redo passes, gives the image of one call."""
+    L = gpu_api.lib()
+    for cfg, nx, ny in ((2, 160, 192), (3, 96, 128), (4, 40, 64)):
+        p = abi.default_params(cfg, nx, ny)
+        full, _ = _single(gpu_api, p)
+        names = tuple(k for k in full.arrays)
+        img = gpu_api.DevicePlanes(p, names=names)
+        try:
+            st = abi.TraceStats()
+            for defer in (0, abi.FLAG_DEFER_REDO):
+                for rep in range(3):                      # a train: the two scratch sets alternate
+                    for r in range(4):
+                        q = abi.ImageParams.from_buffer_copy(p)
+                        q.flags = abi.FLAG_DEVICE_PTRS | abi.FLAG_ASYNC | abi.FLAG_FULL_INDEX | abi.FLAG_STAGE_COPY | defer
+                        q.split_count, q.split_index, q.split_rows = 4, r, 8
+                        gpu_api.check(L.sim5_trace_image(C.byref(q), C.byref(img.out), C.byref(st)), "sim5_trace_image")
+                gpu_api.check(L.sim5_synchronize(), "sim5_synchronize")
+                for k in names:
+                    assert np.array_equal(img.to_host(k), full[k], equal_nan=True), (cfg, k, defer)
+        finally:
+            gpu_api.check(L.sim5_synchronize(), "sim5_synchronize")
+            img.close()
