@@ -304,7 +304,7 @@ def run_ours(args):
         else:
             rows = sdist.apply_split(p, rank, world)
     rays_local = (len(range(rank, p.n_spin * p.n_incl, world)) * n * n) if hist_mode else rows * n
-    p.flags = abi.FLAG_DEVICE_PTRS | (0 if hist_mode else abi.FLAG_ASYNC) | (abi.FLAG_EXACT_AZIMUTH if args.exact_azimuth else 0)
+    p.flags = abi.FLAG_DEVICE_PTRS | (0 if hist_mode else abi.FLAG_ASYNC) | (abi.FLAG_EXACT_AZIMUTH if args.exact_azimuth else 0) | (abi.FLAG_ROW_MAJOR if args.row_major else 0)
     # a train of images: the redo wave of step k can run beside the kernels of step k+1 (SIM5_FLAG_DEFER_REDO); it pays when the wave is a
     # large part of the step (multi-GPU split), on one GPU it is neutral to slightly negative -> by default for N > 1 only
     defer = two_phase and ((world > 1) if args.defer_redo == "auto" else (args.defer_redo == "on"))
@@ -684,6 +684,7 @@ def main():
     ap.add_argument("--peer-copy", default="dma", choices=["dma", "stores"],
                     help="N>1 with --gather peer: 'dma' = ranks 1..N-1 trace into local planes and the copy engine moves their row blocks into rank 0's image "
                          "under the next step's kernels (default); 'stores' = their kernels store straight into rank 0's planes over NVLink (A/B)")
+    ap.add_argument("--row-major", action="store_true", help="A/B, config 4: rows top to bottom instead of from the middle outwards (SIM5_FLAG_ROW_MAJOR)")
     ap.add_argument("--defer-redo", default="auto", choices=["auto", "on", "off"], help="SIM5_FLAG_DEFER_REDO for the timed train (auto: only with more than one GPU)")
     ap.add_argument("--exact-azimuth", action="store_true", help="A/B: bit-faithful azimuth kernels (SIM5_FLAG_EXACT_AZIMUTH) instead of the tolerance-mode default")
     args = ap.parse_args()

@@ -87,6 +87,7 @@ extern "C" {
                                         image k rides under the kernels of image k+1 instead of every plane store crossing NVLink.  With 8 GPUs the ~70 MB per GPU
                                         and image otherwise arrive at the assembling GPU as 8-byte stores from 7 kernels at once and stretch their tracing kernels
                                         by 50 % (profiles/r05m_bench_cfg2_n8.json).  The planes are complete after sim5_join() / sim5_synchronize() */
+#define SIM5_FLAG_ROW_MAJOR    0x200 /* A/B testing, STEPWISE: hand the rows to the lanes top to bottom instead of from the middle of the image outwards */
 #define SIM5_FLAG_ASYNC         0x4  /* with DEVICE_PTRS: enqueue on the library stream (sim5_set_stream) and return without
                                         synchronising; stats are not filled.  Pair with sim5_synchronize(). */
 

@@ -455,7 +455,7 @@ k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigne
                 if (p < npix) {
                     int lr = (int)(p / nx);
                     int ix = (int)(p - (long long)lr * nx);
-                    if (PROG::CENTER_OUT) {
+                    if (PROG::CENTER_OUT && !(c.flags & SIM5_FLAG_ROW_MAJOR)) {
                         /* longest rays first: the k-th row handed out is the k-th closest to the middle of this call's rows (mid, mid-1, mid+1, ...).
                          * The rays that take the most steps pass closest to the hole, i.e. sit in the middle rows; started last they ARE the tail of the
                          * kernel (a ray cannot be split: 8000 steps x ~7 us), started first the cheap outer rows fill in behind them */
