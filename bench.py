@@ -320,7 +320,7 @@ def run_ours(args):
         # the image lives in rank 0's HBM; every rank maps those planes (CUDA IPC, peer access over NVLink/NVSwitch) and its kernels store
         # their interleaved row blocks straight into the final image: the transfer rides under the FP64 work, no gather, no re-assembly
         p.flags |= abi.FLAG_FULL_INDEX
-        if rank != 0 and args.peer_copy == "dma":
+        if rank != 0 and (args.peer_copy == "dma" or (args.peer_copy == "auto" and world >= 8)):
             # ... by DMA: the rank traces into local compact planes and the copy engine moves the finished row blocks into rank 0's image
             # under the next step's kernels (8-byte stores from 7 kernels at once saturate rank 0's NVLink ingress and stretch phase A by 50 %)
             p.flags |= abi.FLAG_STAGE_COPY
@@ -681,9 +681,11 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N>1: 'peer' = every rank stores its rows into rank 0's image over NVLink peer memory (default); "
                          "'nccl' = compact planes + torch.distributed gather + re-assembly on rank 0 (A/B)")
-    ap.add_argument("--peer-copy", default="dma", choices=["dma", "stores"],
+    ap.add_argument("--peer-copy", default="auto", choices=["auto", "dma", "stores"],
                     help="N>1 with --gather peer: 'dma' = ranks 1..N-1 trace into local planes and the copy engine moves their row blocks into rank 0's image "
-                         "under the next step's kernels (default); 'stores' = their kernels store straight into rank 0's planes over NVLink (A/B)")
+                         "under the next step's kernels; 'stores' = their kernels store straight into rank 0's planes over NVLink; 'auto' (default) = dma from "
+                         "8 GPUs on, where the stores of 7 kernels saturate rank 0's NVLink ingress (8 GPUs: 0.915 vs 1.095 ms per step; 4 GPUs: 1.644 vs 1.633, "
+                         "2 GPUs: 3.189 vs 3.176 -- profiles/r05o_*, r05n_*)")
     ap.add_argument("--row-major", action="store_true", help="A/B, config 4: rows top to bottom instead of from the middle outwards (SIM5_FLAG_ROW_MAJOR)")
     ap.add_argument("--defer-redo", default="auto", choices=["auto", "on", "off"], help="SIM5_FLAG_DEFER_REDO for the timed train (auto: only with more than one GPU)")
     ap.add_argument("--exact-azimuth", action="store_true", help="A/B: bit-faithful azimuth kernels (SIM5_FLAG_EXACT_AZIMUTH) instead of the tolerance-mode default")
