@@ -88,6 +88,11 @@ struct Context {
     cudaEvent_t ev_redo_done[2] = {nullptr, nullptr}, ev_fast_done = nullptr;
     bool redo_pending[2] = {false, false};
     int defer_buf = 0;
+    /* trains of SIM5_FLAG_DEFER_REDO calls: the kernels of consecutive calls alternate between two internal launch streams; the caller's stream only
+     * carries the entry / exit events */
+    cudaStream_t train_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_entry[2] = {nullptr, nullptr}, ev_a_done[2] = {nullptr, nullptr}, ev_train_done[2] = {nullptr, nullptr};
+    bool train_pending[2] = {false, false};
     /* SIM5_FLAG_STAGE_COPY: two alternating sets of local compact planes; the copy of set s to the caller's (peer) planes ends at ev_stage_done[s] */
     Plane stage[2][SIM5_NPLANES];
     cudaEvent_t ev_stage_done[2] = {nullptr, nullptr}, ev_stage_go = nullptr;
@@ -192,6 +197,13 @@ int ensure_init(int device)
     CK(cudaEventCreateWithFlags(&c.ev_redo_done[0], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.ev_redo_done[1], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.ev_fast_done, cudaEventDisableTiming));
+    for (int b = 0; b < 2; b++) {
+        CK(cudaStreamCreateWithFlags(&c.train_stream[b], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c.ev_entry[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.ev_a_done[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.ev_train_done[b], cudaEventDisableTiming));
+        c.train_pending[b] = false;
+    }
     CK(cudaEventCreateWithFlags(&c.ev_stage_done[0], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.ev_stage_done[1], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.ev_stage_go, cudaEventDisableTiming));
@@ -426,6 +438,11 @@ void shutdown_ctx(Context& c)
     if (c.azq2_key.p) cudaFree(c.azq2_key.p); c.azq2_key = Plane();
     if (c.azq2_redo.p) cudaFree(c.azq2_redo.p); c.azq2_redo = Plane();
     c.d_counter2 = nullptr;
+    for (int b = 0; b < 2; b++) {
+        cudaStreamSynchronize(c.train_stream[b]); cudaStreamDestroy(c.train_stream[b]); c.train_stream[b] = nullptr;
+        cudaEventDestroy(c.ev_entry[b]); cudaEventDestroy(c.ev_a_done[b]); cudaEventDestroy(c.ev_train_done[b]);
+        c.train_pending[b] = false;
+    }
     cudaStreamSynchronize(c.copy_stream);
     for (int b = 0; b < 2; b++) for (auto& pl : c.stage[b]) { if (pl.p) cudaFree(pl.p); pl = Plane(); }
     cudaEventDestroy(c.ev_stage_done[0]); cudaEventDestroy(c.ev_stage_done[1]); cudaEventDestroy(c.ev_stage_go);
@@ -474,17 +491,23 @@ extern "C" int sim5_set_chunk_rays(int64_t rays)
 
 namespace {
 /* the launch stream waits for the redo passes that SIM5_FLAG_DEFER_REDO calls left running on the auxiliary stream */
-int join_deferred(Context& c, int only_buf /* -1: all */)
+int join_deferred(Context& c, int only_buf /* -1: all */, cudaStream_t on = nullptr)
 {
+    if (!on) on = c.stream;
     for (int b = 0; b < 2; b++) {
         if (!c.redo_pending[b] || (only_buf >= 0 && b != only_buf)) continue;
-        CK(cudaStreamWaitEvent(c.stream, c.ev_redo_done[b], 0));
+        CK(cudaStreamWaitEvent(on, c.ev_redo_done[b], 0));
         c.redo_pending[b] = false;
     }
     if (only_buf < 0) {
+        for (int b = 0; b < 2; b++) {                  /* ... for the internal launch streams of a train */
+            if (!c.train_pending[b]) continue;
+            CK(cudaStreamWaitEvent(on, c.ev_train_done[b], 0));
+            c.train_pending[b] = false;
+        }
         for (int b = 0; b < 2; b++) {                  /* ... and for the staged plane copies of SIM5_FLAG_STAGE_COPY calls */
             if (!c.stage_pending[b]) continue;
-            CK(cudaStreamWaitEvent(c.stream, c.ev_stage_done[b], 0));
+            CK(cudaStreamWaitEvent(on, c.ev_stage_done[b], 0));
             c.stage_pending[b] = false;
         }
     }
@@ -677,7 +700,6 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     if (stage_copy) {
         sb = c.stage_buf;
         c.stage_buf ^= 1;
-        if (c.stage_pending[sb]) { CK(cudaStreamWaitEvent(c.stream, c.ev_stage_done[sb], 0)); c.stage_pending[sb] = false; }      /* the set is free again */
         d.compact = 1;
     }
     for (int i = 0; i < SIM5_NPLANES; i++) {
@@ -746,10 +768,19 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
      * before the previous one), every other kind of call first waits for all of them */
     const bool defer = two_phase && async && nchunks == 1 && (p->flags & SIM5_FLAG_DEFER_REDO) && !(p->flags & SIM5_FLAG_EXACT_AZIMUTH);
     unsigned long long* cnt = c.d_counter;
+    cudaStream_t ls = c.stream;                  /* the stream this call's kernels are launched on */
+    const bool alt = defer && !(p->flags & SIM5_FLAG_ONE_STREAM);
     if (defer) {
         const int b = c.defer_buf;
         c.defer_buf ^= 1;
-        rc = join_deferred(c, b); if (rc) return rc;
+        if (alt) {
+            /* behind everything the caller has enqueued so far, and behind the tracing kernel of the previous call of the train */
+            ls = c.train_stream[b];
+            CK(cudaEventRecord(c.ev_entry[b], c.stream));
+            CK(cudaStreamWaitEvent(ls, c.ev_entry[b], 0));
+            CK(cudaStreamWaitEvent(ls, c.ev_a_done[b ^ 1], 0));
+        }
+        rc = join_deferred(c, b, ls); if (rc) return rc;
         cnt = c.d_counter2 + S5_BLK_WORDS * b;
         if (b == 1) {
             size_t qpix = (size_t)q.cap;
@@ -769,8 +800,9 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     c.ring_phases[c.ring_pos] = 0;
     DevStats* const d_stats = (DevStats*)(cnt + 8);          /* this call's stats sit behind its counters */
     int grid = 0, launches = 0;
-    if (npix == 0) CK(cudaMemsetAsync(cnt, 0, S5_BLK_WORDS * sizeof(unsigned long long), c.stream));
-    CK(cudaEventRecord(c.ev1, c.stream));                    /* start of the call (one memset of 400 bytes precedes the first kernel) */
+    if (stage_copy && c.stage_pending[sb]) { CK(cudaStreamWaitEvent(ls, c.ev_stage_done[sb], 0)); c.stage_pending[sb] = false; }      /* the scratch set is free again */
+    if (npix == 0) CK(cudaMemsetAsync(cnt, 0, S5_BLK_WORDS * sizeof(unsigned long long), ls));
+    CK(cudaEventRecord(c.ev1, ls));                          /* start of the call (one memset of 400 bytes precedes the first kernel) */
     for (int ch = 0; ch < nchunks && npix > 0; ch++) {
         int lr0 = chunk_lr[ch];
         int lrows = chunk_lr[ch + 1] - lr0;
@@ -787,22 +819,23 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                 set_dev_plane(&dd, i, (char*)c.planes[i].p + pix0 * kPlaneInfo[i].elem);
             }
         }
-        CK(cudaMemsetAsync(cnt, 0, (ch == 0 ? S5_BLK_WORDS : 8) * sizeof(unsigned long long), c.stream));      /* counters per chunk, stats once */
+        CK(cudaMemsetAsync(cnt, 0, (ch == 0 ? S5_BLK_WORDS : 8) * sizeof(unsigned long long), ls));      /* counters per chunk, stats once */
         if (p->mode == SIM5_MODE_STEPWISE) {
             grid = persistent_grid(s5::k_trace_lanes<s5::StepwiseProg>, s5::StepwiseProg::THREADS);
-            s5::k_trace_lanes<s5::StepwiseProg><<<grid, s5::StepwiseProg::THREADS, 0, c.stream>>>(cc, dd, cnt, d_stats);
+            s5::k_trace_lanes<s5::StepwiseProg><<<grid, s5::StepwiseProg::THREADS, 0, ls>>>(cc, dd, cnt, d_stats);
         } else if (p->mode == SIM5_MODE_SURFACE) {
             grid = persistent_grid(s5::k_trace_lanes<s5::SurfaceProg>, s5::SurfaceProg::THREADS);
-            s5::k_trace_lanes<s5::SurfaceProg><<<grid, s5::SurfaceProg::THREADS, 0, c.stream>>>(cc, dd, cnt, d_stats);
+            s5::k_trace_lanes<s5::SurfaceProg><<<grid, s5::SurfaceProg::THREADS, 0, ls>>>(cc, dd, cnt, d_stats);
         } else if (two_phase) {
             if (p->outputs & SIM5_OUT_DELAY) {
                 grid = persistent_grid(s5::k_trace_eqplane<true, true>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
-                s5::k_trace_eqplane<true, true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, cnt, d_stats);
+                s5::k_trace_eqplane<true, true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, ls>>>(cc, dd, q, cnt, d_stats);
             } else {
                 grid = persistent_grid(s5::k_trace_eqplane<true>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
-                s5::k_trace_eqplane<true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, cnt, d_stats);
+                s5::k_trace_eqplane<true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, ls>>>(cc, dd, q, cnt, d_stats);
             }
-            if (ch == 0) CK(cudaEventRecord(c.evp[0], c.stream));
+            if (ch == 0) CK(cudaEventRecord(c.evp[0], ls));
+            if (alt) CK(cudaEventRecord(c.ev_a_done[(cnt == c.d_counter2) ? 0 : 1], ls));      /* the next call of the train may start its tracing kernel */
             int g_rr = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RR>, S5_AZ_THREADS);
             int g_rc = persistent_grid(s5::k_azimuth<s5::GEOD_TYPE_RC>, S5_AZ_THREADS);
             /* the redo passes are one latency-bound wave (~0.1 ms whatever the number of items).  Tried and dropped (profiles/r02y_redo_sweep.log):
@@ -810,9 +843,9 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
              * items over all CTAs without barriers (0.14 / 0.22 ms against 0.10 / 0.24): the wave is bound by walking ~120 KB of code, not by the pipe */
             const int redo_threads = S5_AZ_THREADS;
             if (p->flags & SIM5_FLAG_EXACT_AZIMUTH) {
-                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, cnt + 1, 0);
-                if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
-                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, c.stream>>>(cc, q, dd.phi, cnt + 2, 0);
+                s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, S5_AZ_THREADS, 0, ls>>>(cc, q, dd.phi, cnt + 1, 0);
+                if (ch == 0) CK(cudaEventRecord(c.evp[1], ls));
+                s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, S5_AZ_THREADS, 0, ls>>>(cc, q, dd.phi, cnt + 2, 0);
             } else {
                 if (defer) {
                     /* a train of images: RR hits on the launch stream, the RC chain (3 % of the hits; 0.2 ms alone on a full image) beside it on
@@ -822,11 +855,11 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                      * profiles/r05h_bench_cfg2_n2.json.) */
                     CK(cudaStreamWaitEvent(c.aux_stream, c.evp[0], 0));              /* evp[0]: phase A done */
                     int g_f = persistent_grid(s5::k_azimuth_fast<1>, S5_AZF_THREADS);
-                    s5::k_azimuth_fast<1><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
+                    s5::k_azimuth_fast<1><<<g_f, S5_AZF_THREADS, 0, ls>>>(cc, q, dd.phi);
                     g_f = persistent_grid(s5::k_azimuth_fast<2>, S5_AZF_THREADS);
                     s5::k_azimuth_fast<2><<<g_f, S5_AZF_THREADS, 0, c.aux_stream>>>(cc, q, dd.phi);
                     const int gs_rc = g_rc < S5_DEFER_REDO_CTAS ? g_rc : S5_DEFER_REDO_CTAS, gs_rr = g_rr < S5_DEFER_REDO_CTAS ? g_rr : S5_DEFER_REDO_CTAS;
-                    CK(cudaEventRecord(c.evp[1], c.stream));             /* end of the call on the launch stream; the RR redo pass waits for it */
+                    CK(cudaEventRecord(c.evp[1], ls));             /* end of the call on the launch stream; the RR redo pass waits for it */
                     s5::k_azimuth<s5::GEOD_TYPE_RC><<<gs_rc, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, cnt + 2, 1);
                     CK(cudaStreamWaitEvent(c.aux_stream, c.evp[1], 0));
                     s5::k_azimuth<s5::GEOD_TYPE_RR><<<gs_rr, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, cnt + 1, 1);
@@ -836,45 +869,45 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                 } else {
                 /* RR chain on the launch stream, RC chain (3 % of the hits) on the auxiliary stream: the two bit-faithful redo
                  * passes are latency-bound single waves, so they run side by side instead of back to back */
-                CK(cudaEventRecord(c.ev_fork, c.stream));
+                CK(cudaEventRecord(c.ev_fork, ls));
                 CK(cudaStreamWaitEvent(c.aux_stream, c.ev_fork, 0));
                 int g_f = persistent_grid(s5::k_azimuth_fast<1>, S5_AZF_THREADS);
-                s5::k_azimuth_fast<1><<<g_f, S5_AZF_THREADS, 0, c.stream>>>(cc, q, dd.phi);
+                s5::k_azimuth_fast<1><<<g_f, S5_AZF_THREADS, 0, ls>>>(cc, q, dd.phi);
                 g_f = persistent_grid(s5::k_azimuth_fast<2>, S5_AZF_THREADS);
                 s5::k_azimuth_fast<2><<<g_f, S5_AZF_THREADS, 0, c.aux_stream>>>(cc, q, dd.phi);
                 {
                     s5::k_azimuth<s5::GEOD_TYPE_RC><<<g_rc, redo_threads, 0, c.aux_stream>>>(cc, q, dd.phi, cnt + 2, 1);
                     CK(cudaEventRecord(c.ev_join, c.aux_stream));
-                    if (ch == 0) CK(cudaEventRecord(c.evp[1], c.stream));
+                    if (ch == 0) CK(cudaEventRecord(c.evp[1], ls));
                     /* the redo list: items outside the fast routines' domain or flagged by the conditioning guard (~0.3 %) */
-                    s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, redo_threads, 0, c.stream>>>(cc, q, dd.phi, cnt + 1, 1);
-                    CK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
+                    s5::k_azimuth<s5::GEOD_TYPE_RR><<<g_rr, redo_threads, 0, ls>>>(cc, q, dd.phi, cnt + 1, 1);
+                    CK(cudaStreamWaitEvent(ls, c.ev_join, 0));
                 }
                 }
                 launches += 2;
             }
-            if (ch == 0 && !defer) CK(cudaEventRecord(c.evp[2], c.stream));
+            if (ch == 0 && !defer) CK(cudaEventRecord(c.evp[2], ls));
             launches += 2;
         } else {
             if (p->outputs & SIM5_OUT_DELAY) {
                 grid = persistent_grid(s5::k_trace_eqplane<false, true>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
-                s5::k_trace_eqplane<false, true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, cnt, d_stats);
+                s5::k_trace_eqplane<false, true><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, ls>>>(cc, dd, q, cnt, d_stats);
             } else {
                 grid = persistent_grid(s5::k_trace_eqplane<false>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
-                s5::k_trace_eqplane<false><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, c.stream>>>(cc, dd, q, cnt, d_stats);
+                s5::k_trace_eqplane<false><<<grid, S5_EQ_THREADS, S5_EQ_DYN_SMEM, ls>>>(cc, dd, q, cnt, d_stats);
             }
         }
         launches += 1;
         CK(cudaGetLastError());
         if (devptr) continue;
         /* this chunk's rows go home on the copy stream while the next chunk computes */
-        cudaStream_t cs = c.stream;
+        cudaStream_t cs = ls;
         if (nchunks > 1) {
-            CK(cudaEventRecord(c.ev_chunk[ch], c.stream));
+            CK(cudaEventRecord(c.ev_chunk[ch], ls));
             CK(cudaStreamWaitEvent(c.copy_stream, c.ev_chunk[ch], 0));
             cs = c.copy_stream;
         } else {
-            CK(cudaEventRecord(c.ev2, c.stream));
+            CK(cudaEventRecord(c.ev2, ls));
         }
         for (int i = 0; i < SIM5_NPLANES; i++) {
             if (!(p->outputs & kPlaneInfo[i].bit)) continue;
@@ -894,7 +927,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     }
     if (stage_copy) {
         /* the finished row blocks go to the caller's full-image planes by DMA: block j of this call is srows rows, `split` blocks apart in the image */
-        CK(cudaEventRecord(c.ev_stage_go, c.stream));
+        CK(cudaEventRecord(c.ev_stage_go, ls));
         CK(cudaStreamWaitEvent(c.copy_stream, c.ev_stage_go, 0));
         if (defer) CK(cudaStreamWaitEvent(c.copy_stream, c.ev_redo_done[(cnt == c.d_counter2) ? 0 : 1], 0));      /* phi is complete after the redo passes */
         for (int i = 0; i < SIM5_NPLANES; i++) {
@@ -911,7 +944,12 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     c.ring_phases[c.ring_pos] = c.phases;
     c.ring_defer[c.ring_pos] = defer;
     c.last_defer = defer;
-    if ((devptr || npix == 0) && !defer) CK(cudaEventRecord(c.ev2, c.stream));      /* (a deferred call ends at evp[1]) */
+    if ((devptr || npix == 0) && !defer) CK(cudaEventRecord(c.ev2, ls));      /* (a deferred call ends at evp[1]) */
+    if (alt) {
+        const int b = (cnt == c.d_counter2) ? 0 : 1;
+        CK(cudaEventRecord(c.ev_train_done[b], ls));
+        c.train_pending[b] = true;
+    }
     if (async) return SIM5_OK;
     if (nchunks > 1) {
         CK(cudaEventRecord(c.ev2, c.stream));
