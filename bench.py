@@ -309,7 +309,7 @@ def run_ours(args):
     # large part of the step (multi-GPU split), on one GPU it is neutral to slightly negative -> by default for N > 1 only
     defer = two_phase and ((world > 1) if args.defer_redo == "auto" else (args.defer_redo == "on"))
     if defer:
-        p.flags |= abi.FLAG_DEFER_REDO | (abi.FLAG_ONE_STREAM if args.one_stream else 0)
+        p.flags |= abi.FLAG_DEFER_REDO | (abi.FLAG_ALT_STREAMS if args.alt_streams else 0)
     peer = world > 1 and args.gather == "peer" and not hist_mode
     gath, image, loc, hist = None, None, None, None
     out = abi.ImageOut()
@@ -686,7 +686,7 @@ def main():
                          "under the next step's kernels; 'stores' = their kernels store straight into rank 0's planes over NVLink; 'auto' (default) = dma from "
                          "8 GPUs on, where the stores of 7 kernels saturate rank 0's NVLink ingress (8 GPUs: 0.915 vs 1.095 ms per step; 4 GPUs: 1.644 vs 1.633, "
                          "2 GPUs: 3.189 vs 3.176 -- profiles/r05o_*, r05n_*)")
-    ap.add_argument("--one-stream", action="store_true", help="A/B: keep the deferred train on one launch stream (SIM5_FLAG_ONE_STREAM)")
+    ap.add_argument("--alt-streams", action="store_true", help="A/B: let the calls of the deferred train alternate between two launch streams (SIM5_FLAG_ALT_STREAMS; measured slower)")
     ap.add_argument("--row-major", action="store_true", help="A/B, config 4: rows top to bottom instead of from the middle outwards (SIM5_FLAG_ROW_MAJOR)")
     ap.add_argument("--defer-redo", default="auto", choices=["auto", "on", "off"], help="SIM5_FLAG_DEFER_REDO for the timed train (auto: only with more than one GPU)")
     ap.add_argument("--exact-azimuth", action="store_true", help="A/B: bit-faithful azimuth kernels (SIM5_FLAG_EXACT_AZIMUTH) instead of the tolerance-mode default")

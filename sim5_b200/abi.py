@@ -18,7 +18,7 @@ FLAG_DEVICE_PTRS, FLAG_NO_REFILL, FLAG_ASYNC, FLAG_SINGLE_PASS, FLAG_NO_OVERLAP,
 FLAG_DEFER_REDO = 0x80
 FLAG_STAGE_COPY = 0x100
 FLAG_ROW_MAJOR = 0x200
-FLAG_ONE_STREAM = 0x400
+FLAG_ALT_STREAMS = 0x400
 # status classes
 ST_HIT0, ST_HIT1, ST_MISS, ST_NOCROSS0, ST_NOCROSS1, ST_HIT2, ST_NOCROSS2 = 0, 1, 2, 3, 4, 5, 6
 ST_HORIZON, ST_ESCAPE, ST_ERRBREAK, ST_MAXSTEPS, ST_NOSTART = 8, 9, 10, 11, 12

@@ -769,7 +769,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     const bool defer = two_phase && async && nchunks == 1 && (p->flags & SIM5_FLAG_DEFER_REDO) && !(p->flags & SIM5_FLAG_EXACT_AZIMUTH);
     unsigned long long* cnt = c.d_counter;
     cudaStream_t ls = c.stream;                  /* the stream this call's kernels are launched on */
-    const bool alt = defer && !(p->flags & SIM5_FLAG_ONE_STREAM);
+    const bool alt = defer && (p->flags & SIM5_FLAG_ALT_STREAMS);      /* A/B only: co-running the two kernels slows both (sim5_b200.h) */
     if (defer) {
         const int b = c.defer_buf;
         c.defer_buf ^= 1;

@@ -131,7 +131,7 @@ def test_stage_copy_assembles_the_image_by_dma(gpu_api):
         img = gpu_api.DevicePlanes(p, names=names)
         try:
             st = abi.TraceStats()
-            for defer in (0, abi.FLAG_DEFER_REDO):
+            for defer in (0, abi.FLAG_DEFER_REDO, abi.FLAG_DEFER_REDO | abi.FLAG_ALT_STREAMS):
                 for rep in range(3):                      # a train: the two scratch sets alternate
                     for r in range(4):
                         q = abi.ImageParams.from_buffer_copy(p)
