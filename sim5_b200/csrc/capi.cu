@@ -90,7 +90,7 @@ struct Context {
     int defer_buf = 0;
     /* trains of SIM5_FLAG_DEFER_REDO calls: the kernels of consecutive calls alternate between two internal launch streams; the caller's stream only
      * carries the entry / exit events */
-    cudaStream_t train_stream[2] = {nullptr, nullptr};
+    cudaStream_t train_stream[2] = {nullptr, nullptr}, hi_stream = nullptr;      /* low priority: tracing kernels of a train; high priority: its azimuth kernels */
     cudaEvent_t ev_entry[2] = {nullptr, nullptr}, ev_a_done[2] = {nullptr, nullptr}, ev_train_done[2] = {nullptr, nullptr};
     bool train_pending[2] = {false, false};
     /* SIM5_FLAG_STAGE_COPY: two alternating sets of local compact planes; the copy of set s to the caller's (peer) planes ends at ev_stage_done[s] */
@@ -197,8 +197,11 @@ int ensure_init(int device)
     CK(cudaEventCreateWithFlags(&c.ev_redo_done[0], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.ev_redo_done[1], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.ev_fast_done, cudaEventDisableTiming));
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);       /* numerically lower = higher priority */
+    CK(cudaStreamCreateWithPriority(&c.hi_stream, cudaStreamNonBlocking, prio_hi));
     for (int b = 0; b < 2; b++) {
-        CK(cudaStreamCreateWithFlags(&c.train_stream[b], cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithPriority(&c.train_stream[b], cudaStreamNonBlocking, prio_lo));
         CK(cudaEventCreateWithFlags(&c.ev_entry[b], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c.ev_a_done[b], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c.ev_train_done[b], cudaEventDisableTiming));
@@ -438,6 +441,7 @@ void shutdown_ctx(Context& c)
     if (c.azq2_key.p) cudaFree(c.azq2_key.p); c.azq2_key = Plane();
     if (c.azq2_redo.p) cudaFree(c.azq2_redo.p); c.azq2_redo = Plane();
     c.d_counter2 = nullptr;
+    cudaStreamSynchronize(c.hi_stream); cudaStreamDestroy(c.hi_stream); c.hi_stream = nullptr;
     for (int b = 0; b < 2; b++) {
         cudaStreamSynchronize(c.train_stream[b]); cudaStreamDestroy(c.train_stream[b]); c.train_stream[b] = nullptr;
         cudaEventDestroy(c.ev_entry[b]); cudaEventDestroy(c.ev_a_done[b]); cudaEventDestroy(c.ev_train_done[b]);
@@ -854,6 +858,7 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
                      * (One launch for both queues, k_azimuth_fast<0>, saves a stream operation but serialises the RC part: 2 GPUs 1.35 -> 1.53 ms,
                      * profiles/r05h_bench_cfg2_n2.json.) */
                     CK(cudaStreamWaitEvent(c.aux_stream, c.evp[0], 0));              /* evp[0]: phase A done */
+                    if (alt) { CK(cudaStreamWaitEvent(c.hi_stream, c.evp[0], 0)); ls = c.hi_stream; }      /* A/B: the azimuth on the high-priority stream */
                     int g_f = persistent_grid(s5::k_azimuth_fast<1>, S5_AZF_THREADS);
                     s5::k_azimuth_fast<1><<<g_f, S5_AZF_THREADS, 0, ls>>>(cc, q, dd.phi);
                     g_f = persistent_grid(s5::k_azimuth_fast<2>, S5_AZF_THREADS);

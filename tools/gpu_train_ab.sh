@@ -4,7 +4,7 @@ TAG=${1:-r05}
 mkdir -p gpurun_out
 python -m pytest tests/test_gpu_parity.py tests/test_multi_device.py -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log; tail -2 gpurun_out/${TAG}_pytest.log
 for size in 4096 1448; do
-  for mode in "" "--one-stream"; do
+  for mode in "" "--alt-streams"; do
     for rep in 1 2; do
       python bench.py --size $size --defer-redo on $mode --steps 40 --warmup 5 --no-cpu > gpurun_out/${TAG}_ab.json 2> gpurun_out/${TAG}_ab.err
       python - <<P
