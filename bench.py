@@ -461,9 +461,14 @@ def run_ours(args):
             sdist.apply_split(ph, rank, world)
             # ONE host image for the whole job: a POSIX shared-memory segment per plane, mapped and page-locked (cudaHostRegister)
             # by every rank; each rank's chunks go over its own PCIe link straight into the rows it owns, rank 0 reads the image
-            shm = SharedHostImage(api, abi, ph, rank, world, dist)
-            hp = shm.planes
-            e2e_note = "every rank copies its rows (chunks under its kernels, own PCIe link) into ONE shared page-locked host image (POSIX shm + cudaHostRegister) that rank 0 reads; ranks bound to their GPU's NUMA node (%s)" % numa
+            try:
+                shm = SharedHostImage(api, abi, ph, rank, world, dist)
+                hp = shm.planes
+                e2e_note = "every rank copies its rows (chunks under its kernels, own PCIe link) into ONE shared %s host image (POSIX shm + cudaHostRegister) that rank 0 reads; ranks bound to their GPU's NUMA node (%s)" % ("pageable (registration failed)" if shm.unregistered else "page-locked", numa)
+            except RuntimeError:
+                shm = None
+                hp = api.HostPlanes(ph, pinned=True)
+                e2e_note = "no shared-memory segment available: every rank copies its own rows to pinned host planes of its own (no process holds the whole host image)"
         else:
             hp = api.HostPlanes(ph, pinned=True)
             e2e_note = "sim5_trace_image with pinned HOST planes: chunks of ~2^21 rays, the copy of chunk k under the kernels of chunk k+1"
@@ -504,7 +509,7 @@ def run_ours(args):
         key = "g" if "g" in names else "intensity"
         if rank == 0:
             checksum = float(np.nansum(hp[key]))                 # the WHOLE host image, as rank 0 holds it
-        if peer and rank == 0:
+        if peer and rank == 0 and (world == 1 or shm is not None):
             # the image the ranks assembled in rank 0's HBM through peer stores, against the host image all ranks filled
             dsum = float(np.nansum(image.to_host(key)))
             image_check = {"plane": key, "sum_device_image": dsum, "sum_host_image": checksum, "rel_diff": abs(dsum - checksum) / max(abs(checksum), 1e-300)}
@@ -620,18 +625,29 @@ class SharedHostImage:
         import numpy as np
         from multiprocessing import shared_memory
         self.api, self.rank = api, rank
-        self.segs, self.ptrs = [], []
+        self.segs, self.ptrs, self.unregistered = [], [], False
         n = p.nx * p.ny
         names = [None]
         specs = [(name, ct) for name, bit, ct in abi.PLANES if p.outputs & bit]
         if rank == 0:
             made = []
-            for name, ct in specs:
-                seg = shared_memory.SharedMemory(create=True, size=n * C.sizeof(ct))
-                made.append(seg)
-            names = [[s.name for s in made]]
+            try:
+                need = sum(n * C.sizeof(ct) for _, ct in specs)
+                vfs = os.statvfs("/dev/shm")              # tmpfs hands out pages lazily: a segment that does not fit fails at first touch (SIGBUS), so ask first
+                if vfs.f_bavail * vfs.f_frsize < need + (64 << 20):
+                    raise OSError("/dev/shm has %d MB free, %d MB needed" % (vfs.f_bavail * vfs.f_frsize >> 20, need >> 20))
+                for name, ct in specs:
+                    made.append(shared_memory.SharedMemory(create=True, size=n * C.sizeof(ct)))
+                names = [[s.name for s in made]]
+            except Exception as e:      # e.g. /dev/shm too small: every rank falls back to planes of its own
+                for sgm in made:
+                    sgm.close(); sgm.unlink()
+                made, names = [], [None]
+                sys.stderr.write("bench.py: no shared host image (%s); every rank keeps its rows in pinned planes of its own\n" % e)
             self.segs = made
         dist.broadcast_object_list(names, src=0)
+        if names[0] is None:
+            raise RuntimeError("shared host image unavailable")
         if rank != 0:
             self.segs = [shared_memory.SharedMemory(name=nm) for nm in names[0]]
             try:      # the creator unlinks; an attaching process must not let its resource tracker "clean up" the segment at exit (Python < 3.13)
@@ -645,8 +661,10 @@ class SharedHostImage:
         for (name, ct), seg in zip(specs, self.segs):
             a = np.ndarray((n,), dtype=npdt[ct], buffer=seg.buf)
             addr = a.ctypes.data
-            api.check(api.lib().sim5_host_register(C.c_void_p(addr), C.c_size_t(a.nbytes)), "sim5_host_register")
-            self.ptrs.append(addr)
+            if api.lib().sim5_host_register(C.c_void_p(addr), C.c_size_t(a.nbytes)) == abi.OK:      # (unregistered memory still works: pageable copies)
+                self.ptrs.append(addr)
+            else:
+                self.unregistered = True
             self.planes.arrays[name] = a
             setattr(self.planes.out, name, addr)
         dist.barrier()
