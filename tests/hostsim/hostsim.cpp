@@ -36,6 +36,34 @@ void hs_batch_libm(int op, long n, const double* a, const double* b, double* o)
     }
 }
 
+/* the angle carry of the stepper (crmath.cuh): m = cos(th) through cr_cos_carry, then acos(m) through the carry and through cr_acos;
+ * took[i] = 1 where the shortcut (not the full routine) produced the value */
+void hs_acos_carry(long n, const double* th, double* m, double* via_carry, double* via_acos, int* took)
+{
+    for (long i = 0; i < n; i++) {
+        crm::AngCarry c;
+        crm::carry_reset(&c);
+        m[i] = crm::cr_cos_carry(th[i], &c);
+        via_acos[i] = crm::cr_acos(m[i]);
+        via_carry[i] = crm::cr_acos_carry(m[i], &c);
+        /* the shortcut is taken iff the carry is valid, away from the poles, and the rounding is beyond doubt: redo its decision */
+        took[i] = 0;
+        if (c.m == m[i] && c.th > 0.05 && c.th < 3.09) {
+            double s2 = fma(-m[i], m[i], 1.0);
+            if (s2 > 0.00390625) {
+                double rs = 1.0 / sqrt(s2), cc = c.lo * rs;
+                double e = fma(fabs(m[i]) * rs, 0x1p-66, fabs(cc) * 0x1p-30);
+                took[i] = (c.th + (cc + e) == c.th + (cc - e)) ? 1 : 0;
+            }
+        }
+    }
+}
+/* the conservative high-word form of the Carlson convergence test (fastfp.cuh) */
+void hs_surely_above_tol(long n, const double* e, const double* mu, int* out)
+{
+    for (long i = 0; i < n; i++) out[i] = ff::surely_above_tol(ff::hi_abs(e[i]), mu[i]) ? 1 : 0;
+}
+
 void hs_mu_roots(long n, const double* q, const double* l2, const double* a2, double* m2m, double* m2p)
 {
     for (long i = 0; i < n; i++) crm::x87_mu_roots(q[i], l2[i], a2[i], &m2m[i], &m2p[i]);

@@ -86,3 +86,44 @@ def test_x87_mu_roots_match_reference_structs(hs):
     m2m, m2p = H.batch_call(hs, "hs_mu_roots", [q, l * l, a * a], nout=2)
     assert np.array_equal(m2m, gd["m2m"][ok])
     assert np.array_equal(m2p, gd["m2p"][ok])
+
+
+def test_angle_carry_equals_cr_acos(hs):
+    """crmath.cuh AngCarry: acos(m) recovered from the cosine that produced m (th + lo / sqrt(1 - m^2)) is the SAME double cr_acos(m)
+    returns -- on 2e6 angles incl. the neighbourhood of the poles and of pi/2 -- and the shortcut, not the full routine, serves
+    nearly all of them (the stepper takes it on 99 % of its steps)."""
+    rng = np.random.default_rng(11)
+    n = 2_000_000
+    th = np.concatenate([rng.uniform(0.0, np.pi, n - 300000), rng.uniform(0.0, 0.06, 100000), np.pi - rng.uniform(0.0, 0.06, 100000),
+                         np.pi / 2 + rng.uniform(-1e-6, 1e-6, 100000)])
+    m = np.empty(n); a = np.empty(n); b = np.empty(n); took = np.zeros(n, dtype=np.int32)
+    f = hs.hs_acos_carry
+    f.restype = None
+    dp = C.POINTER(C.c_double)
+    f(C.c_long(n), th.ctypes.data_as(dp), m.ctypes.data_as(dp), a.ctypes.data_as(dp), b.ctypes.data_as(dp), took.ctypes.data_as(C.POINTER(C.c_int)))
+    assert np.array_equal(a, b), "carry and cr_acos disagree on %d of %d angles" % (int(np.sum(a != b)), n)
+    inner = (th > 0.05) & (th < 3.09) & (np.abs(m) < 0.998)
+    assert took[inner].mean() > 0.995, took[inner].mean()
+    assert np.all(took[~((th > 0.05) & (th < 3.09))] == 0)
+
+
+def test_convergence_pretest_is_conservative(hs):
+    """fastfp.cuh surely_above_tol: whenever the high-word test says "surely above", |e| / mu exceeds the Carlson tolerance 3e-4 (so the
+    exact test would say "not converged" too); it is undecided only in a narrow band above the tolerance."""
+    rng = np.random.default_rng(3)
+    n = 4_000_000
+    mu = np.ldexp(rng.uniform(1, 2, n), rng.integers(-100, 100, n))
+    ratio = 0.0003 * np.exp(rng.uniform(-0.6, 0.6, n))
+    e = mu * ratio * np.where(rng.random(n) < 0.5, -1.0, 1.0)
+    e[::1000] = 0.0
+    e[1::1000] = 5e-324
+    out = np.zeros(n, dtype=np.int32)
+    f = hs.hs_surely_above_tol
+    f.restype = None
+    dp = C.POINTER(C.c_double)
+    f(C.c_long(n), e.ctypes.data_as(dp), mu.ctypes.data_as(dp), out.ctypes.data_as(C.POINTER(C.c_int)))
+    d = np.abs(e / mu)
+    sure = out == 1
+    assert not np.any(sure & ~(d > 0.0003)), "pre-test claimed 'above' for a converged deviation"
+    assert (d[sure] / 0.0003).min() > 1.005
+    assert (d[~sure] / 0.0003).max() < 1.15          # undecided band: the exact test runs in the last one or two iterations only
