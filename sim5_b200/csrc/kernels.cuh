@@ -154,6 +154,15 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
 
 #if !defined(S5_EQ_FREERUN)
     __shared__ unsigned long long s_tile;
+#if defined(S5_EQ_PREFETCH_TILE)
+    /* A/B (-DS5_EQ_PREFETCH_TILE): the index of the NEXT batch is fetched while the current one is traced (the global atomic's latency and one
+     * of the two barriers per batch leave the critical path); a CTA claims one batch past the end, which nobody traces.  Measured: no
+     * difference (phase A 3.602 vs 3.607 ms at 4096^2, 0.4987 vs 0.4995 ms on a 2 M-ray slice, profiles/r05z_proxy.log): the second CTA of
+     * the SM already hides that latency.  Off by default. */
+    unsigned long long nxt = 0;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, (unsigned long long)(S5_EQ_THREADS / 32 * S5_EQ_TILES_PER_SYNC));
+    __syncthreads();
+#endif
 #endif
     for (;;) {
         unsigned long long t = 0;
@@ -161,13 +170,21 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
         /* the CTA takes S5_EQ_TILES_PER_SYNC tiles per warp at a time and passes a barrier per batch, so its 16 warps walk the (183 KB)
          * routine together and share instruction-cache lines: r01q sweep 5.33 vs 5.40 ms free-running (cfg 3: 2.67 vs 2.81 ms);
          * -DS5_EQ_FREERUN restores per-warp pulls */
+#if defined(S5_EQ_PREFETCH_TILE)
+        const unsigned long long cur = s_tile;
+        if ((long long)cur >= ntiles) break;
+        if (threadIdx.x == 0) nxt = atomicAdd(tile_counter, (unsigned long long)(S5_EQ_THREADS / 32 * S5_EQ_TILES_PER_SYNC));
+#define S5_CUR_TILE cur
+#else
         __syncthreads();
         if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, (unsigned long long)(S5_EQ_THREADS / 32 * S5_EQ_TILES_PER_SYNC));
         __syncthreads();
         if ((long long)s_tile >= ntiles) break;
+#define S5_CUR_TILE s_tile
+#endif
       #pragma unroll 1
       for (int sub = 0; sub < S5_EQ_TILES_PER_SYNC; sub++) {
-        t = s_tile + (unsigned long long)(sub * (S5_EQ_THREADS / 32)) + (threadIdx.x >> 5);
+        t = S5_CUR_TILE + (unsigned long long)(sub * (S5_EQ_THREADS / 32)) + (threadIdx.x >> 5);
 #else
         if (lane == 0) t = atomicAdd(tile_counter, 1ULL);
         t = __shfl_sync(0xffffffffu, t, 0);
@@ -253,6 +270,10 @@ k_trace_eqplane(const __grid_constant__ S5ImageConsts gconsts, DevOut out, AzQue
             }
         }
       }
+#if !defined(S5_EQ_FREERUN) && defined(S5_EQ_PREFETCH_TILE)
+        if (threadIdx.x == 0) s_tile = nxt;
+        __syncthreads();
+#endif
     }
     flush_stats(s_cnt, 0, gstats);
 }
