@@ -330,7 +330,10 @@ k_azimuth(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double* __re
  * a static grid-stride split is balanced.  Items whose arguments leave the fast routines' domain go to the redo lists and
  * are integrated by the bit-faithful k_azimuth<TYPE> afterwards. */
 #ifndef S5_AZF_THREADS
-#define S5_AZF_THREADS 256        /* r01f sweep (profiles/r01f_sweep.log): 256 x 2 CTAs/SM 3.14 ms, 128 x 4 3.32, 128 x 6 (80 regs, spills) 3.31, 128 x 3 3.46 */
+#define S5_AZF_THREADS 512        /* 512 x 2 CTAs/SM at 64 registers (32 warps/SM, 300 B of spills): round-2 sweeps on the final routine (profiles/r06a_proxy.log,
+                                     r06b_proxy.log; ms at 4096^2 / on a 2 M-ray slice, same box): 256 x 2 (128 regs, no spills) 2.69 / 0.348, 256 x 3 (80) 2.64 / 0.350,
+                                     384 x 2 (80) 2.63 / 0.340, 416 x 2 (72) 2.74 / 0.364, 448 x 2 (72) 2.57 / 0.355, 512 x 2 (64) 2.50 / 0.340; 192 x 3 and 224 x 2
+                                     are slower than 256 x 2.  (round 1, on the 4-sequence routine: 256 x 2 3.14 ms, 128 x 4 3.32, 128 x 6 3.31, 128 x 3 3.46) */
 #endif
 #ifndef S5_MIN_CTAS_AZF
 #define S5_MIN_CTAS_AZF 2
