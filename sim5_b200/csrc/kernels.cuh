@@ -61,7 +61,8 @@ S5_HD S5_INL void az_unkey(unsigned long long key, AzIn* z)
 
 #define S5_CTA_THREADS 128
 #ifndef S5_EQ_THREADS
-#define S5_EQ_THREADS 512          /* CTA size of the eq-plane trace kernels */
+#define S5_EQ_THREADS 512          /* CTA size of the eq-plane trace kernels.  Re-swept on the round-2 routine (profiles/r06e_proxy.log, phase A of the 4096^2
+                                      image, 2 CTAs/SM): 384 (80 regs) 3.73 ms, 416 (72) 4.12, 448 (72) 3.75, 480 (64) 3.75, 512 (64) 3.59 */
 #endif
 #ifndef S5_MIN_CTAS_EQ
 #define S5_MIN_CTAS_EQ 2          /* resident CTAs per SM the eq-plane kernel is compiled for.  With the CTA-lockstep tile loop the kernel is bound by
