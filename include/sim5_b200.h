@@ -88,11 +88,12 @@ extern "C" {
                                         and image otherwise arrive at the assembling GPU as 8-byte stores from 7 kernels at once and stretch their tracing kernels
                                         by 50 % (profiles/r05m_bench_cfg2_n8.json).  The planes are complete after sim5_join() / sim5_synchronize() */
 #define SIM5_FLAG_ROW_MAJOR    0x200 /* A/B testing, STEPWISE: hand the rows to the lanes top to bottom instead of from the middle of the image outwards */
-#define SIM5_FLAG_ALT_STREAMS  0x400 /* A/B testing, with DEFER_REDO: let the calls of a train alternate between two internal launch streams, ordered only by what
-                                        they share (the tracing kernel of image k+1 starts when the tracing kernel of image k is done, not when its azimuth
-                                        is), so the next image's tracing kernel runs beside the azimuth kernel.  Measured: it does NOT pay -- the two kernels
-                                        slow each other down (phase A 0.499 -> 0.514 ms, azimuth 0.356 -> 0.451 ms on a 2 M-ray slice; step 0.870 -> 0.890 ms;
-                                        4096^2: 6.28 -> 6.29 ms; profiles/r05q_train_ab.log) -- so a train stays on the caller's stream by default */
+#define SIM5_FLAG_ALT_STREAMS  0x400 /* A/B testing, with DEFER_REDO: overlap consecutive calls of a train -- the tracing kernels alternate between two internal
+                                        low-priority launch streams (image k+1 starts tracing when image k has finished tracing, not when its azimuth has), the
+                                        azimuth kernels run on a high-priority stream.  Measured: it does NOT pay.  Without priorities the two kernels share the SMs
+                                        and slow each other down (2 M-ray slice: phase A 0.499 -> 0.514 ms, azimuth 0.356 -> 0.451 ms, step 0.870 -> 0.890 ms;
+                                        profiles/r05q_train_ab.log); with them the step is 0.866 -> 0.885 ms (profiles/r05r_train_ab_priority.log).  A train
+                                        therefore stays on the caller's stream by default */
 #define SIM5_FLAG_ASYNC         0x4  /* with DEVICE_PTRS: enqueue on the library stream (sim5_set_stream) and return without
                                         synchronising; stats are not filled.  Pair with sim5_synchronize(). */
 
