@@ -94,6 +94,13 @@ extern "C" {
                                         and slow each other down (2 M-ray slice: phase A 0.499 -> 0.514 ms, azimuth 0.356 -> 0.451 ms, step 0.870 -> 0.890 ms;
                                         profiles/r05q_train_ab.log); with them the step is 0.866 -> 0.885 ms (profiles/r05r_train_ab_priority.log).  A train
                                         therefore stays on the caller's stream by default */
+#define SIM5_FLAG_SHARED_QUEUE 0x800 /* STEPWISE / SURFACE with DEVICE_PTRS, no row split: the rays of the image are handed out from the caller's counter
+                                        out->shared_counter -- a zeroed 64-bit word in memory every participating GPU can reach (the assembling GPU's, mapped
+                                        with sim5_ipc_import in the other processes) -- with system-scope atomics.  All GPUs of a job then pull rays of ONE
+                                        image from ONE queue, a warp refill at a time, and store into the full-image planes: the static row split plus work
+                                        stealing of north_star taken to its limit (everything is "tail").  For the step-wise modes, whose rays cost 1 600 ...
+                                        8 200 steps each: a static split leaves the GPUs up to 12 % apart (profiles/r05o_bench_cfg4_n4_centerout.json).
+                                        One counter word per call: a train of calls uses consecutive words */
 #define SIM5_FLAG_ASYNC         0x4  /* with DEVICE_PTRS: enqueue on the library stream (sim5_set_stream) and return without
                                         synchronising; stats are not filled.  Pair with sim5_synchronize(). */
 
@@ -227,6 +234,7 @@ typedef struct sim5_image_out {
     double  *spectrum;           /* SPECTRUM: [n_energy], always a HOST array (it is 2 KB) */
     double  *height;
     double  *delay;
+    uint64_t *shared_counter;    /* SIM5_FLAG_SHARED_QUEUE: the ray queue of this call (device-reachable, zero before the first participant starts) */
 } sim5_image_out;
 
 typedef struct sim5_trace_stats {
@@ -264,6 +272,8 @@ int   sim5_host_unregister(void* p);
 /* device memory helpers for SIM5_FLAG_DEVICE_PTRS users (e.g. a torch tensor's data_ptr works too) */
 void* sim5_device_alloc(size_t bytes);
 void  sim5_device_free(void* p);
+int   sim5_device_memset(void* p, int value, size_t bytes);            /* stream-ordered on the context's launch stream, then synchronised */
+int   sim5_host_to_device(void* dst, const void* src, size_t bytes);   /* same ordering; for small control words (a pre-set ray queue) */
 int   sim5_device_to_host(void* dst, const void* src, size_t bytes);   /* waits for the context's launch stream and deferred redo passes first */
 /* CUDA IPC for one-process-per-GPU jobs on one node: export a sim5_device_alloc'd plane as a 64-byte handle, import it in
  * another process (peer access over NVLink is enabled on first use), release the mapping before the owner frees the plane */
@@ -285,7 +295,10 @@ int  sim5_trace_image(const sim5_image_params* p, const sim5_image_out* out, sim
  * (pinned planes from sim5_host_alloc let the copies overlap the kernels).  SIM5_FLAG_DEVICE_PTRS: the planes live on devices[0] and
  * the other GPUs store their rows into them over NVLink (peer access).  HISTOGRAM: devices[0] adds the partial lattices up with loads
  * from its peers' memory, in a fixed order, before out->hist is written.  stats: counters summed over the devices, kernel_ms /
- * total_ms of the slowest device.  SIM5_FLAG_ASYNC and SIM5_FLAG_DEFER_REDO do not apply. */
+ * total_ms of the slowest device.  SIM5_FLAG_ASYNC and SIM5_FLAG_DEFER_REDO do not apply.
+ * SIM5_FLAG_SHARED_QUEUE (STEPWISE / SURFACE with DEVICE_PTRS): no row split at all -- every device runs the whole row range and pulls
+ * its rays from ONE counter on devices[0] (the library's own word when out->shared_counter is NULL), so the devices finish within one
+ * ray of each other whatever the image looks like; stats->rays of each device = the rays it pulled. */
 int  sim5_trace_image_multi(const sim5_image_params* p, const sim5_image_out* out, sim5_trace_stats* stats, const int* devices, int ndev);
 
 /* device time in ms of each kernel of the most recent sim5_trace_image call (CUDA events on the launch stream; waits for

@@ -19,6 +19,7 @@ FLAG_DEFER_REDO = 0x80
 FLAG_STAGE_COPY = 0x100
 FLAG_ROW_MAJOR = 0x200
 FLAG_ALT_STREAMS = 0x400
+FLAG_SHARED_QUEUE = 0x800
 # status classes
 ST_HIT0, ST_HIT1, ST_MISS, ST_NOCROSS0, ST_NOCROSS1, ST_HIT2, ST_NOCROSS2 = 0, 1, 2, 3, 4, 5, 6
 ST_HORIZON, ST_ESCAPE, ST_ERRBREAK, ST_MAXSTEPS, ST_NOSTART = 8, 9, 10, 11, 12
@@ -66,6 +67,7 @@ class ImageOut(C.Structure):
         ("chi", C.c_void_p), ("delta", C.c_void_p), ("mue", C.c_void_p), ("intensity", C.c_void_p),
         ("tau", C.c_void_p), ("qerr", C.c_void_p), ("steps", C.c_void_p), ("status", C.c_void_p),
         ("hist", C.c_void_p), ("spectrum", C.c_void_p), ("height", C.c_void_p), ("delay", C.c_void_p),
+        ("shared_counter", C.c_void_p),
     ]
 
 

@@ -51,6 +51,10 @@ def lib():
         L.sim5_device_alloc.argtypes = [C.c_size_t]
         L.sim5_device_alloc.restype = C.c_void_p
         L.sim5_device_free.argtypes = [C.c_void_p]
+        L.sim5_device_memset.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
+        L.sim5_device_memset.restype = C.c_int
+        L.sim5_host_to_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.sim5_host_to_device.restype = C.c_int
         L.sim5_device_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.sim5_device_to_host.restype = C.c_int
         L.sim5_ipc_export.argtypes = [C.c_void_p, C.c_void_p]

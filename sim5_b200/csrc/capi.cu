@@ -84,6 +84,7 @@ struct Context {
     Plane azq_f, azq_key;                 /* azimuth work-item queue (phase A -> phase B) */
     /* SIM5_FLAG_DEFER_REDO: a second queue and two counter blocks of its own, so the redo passes of call k can run beside call k+1 */
     Plane azq2_f, azq2_key, azq2_redo;
+    Plane shared_q;                       /* sim5_trace_image_multi + SIM5_FLAG_SHARED_QUEUE: the ray queue all devices pull from (on devices[0]) */
     unsigned long long* d_counter2 = nullptr;             /* [2][8] */
     cudaEvent_t ev_redo_done[2] = {nullptr, nullptr}, ev_fast_done = nullptr;
     bool redo_pending[2] = {false, false};
@@ -440,6 +441,7 @@ void shutdown_ctx(Context& c)
     if (c.azq2_f.p) cudaFree(c.azq2_f.p); c.azq2_f = Plane();
     if (c.azq2_key.p) cudaFree(c.azq2_key.p); c.azq2_key = Plane();
     if (c.azq2_redo.p) cudaFree(c.azq2_redo.p); c.azq2_redo = Plane();
+    if (c.shared_q.p) cudaFree(c.shared_q.p); c.shared_q = Plane();
     c.d_counter2 = nullptr;
     cudaStreamSynchronize(c.hi_stream); cudaStreamDestroy(c.hi_stream); c.hi_stream = nullptr;
     for (int b = 0; b < 2; b++) {
@@ -610,6 +612,24 @@ extern "C" int sim5_ipc_release(void* imported_ptr)
 
 /* Ordered behind everything the library has enqueued for this context: the launch stream (which is cudaStreamNonBlocking, so a plain
  * cudaMemcpy on the legacy stream would NOT wait for it) and the deferred redo passes of SIM5_FLAG_DEFER_REDO calls. */
+extern "C" int sim5_device_memset(void* p, int value, size_t bytes)
+{
+    if (!p) { set_error("sim5_device_memset: null pointer"); return SIM5_ERR_BAD_PARAM; }
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (ensure_init(-1) != SIM5_OK) return SIM5_ERR_NO_DEVICE;
+    CK(cudaMemsetAsync(p, value, bytes, g_ctx.stream));
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    return SIM5_OK;
+}
+extern "C" int sim5_host_to_device(void* dst, const void* src, size_t bytes)
+{
+    if (!dst || !src) { set_error("sim5_host_to_device: null pointer"); return SIM5_ERR_BAD_PARAM; }
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (ensure_init(-1) != SIM5_OK) return SIM5_ERR_NO_DEVICE;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    return SIM5_OK;
+}
 extern "C" int sim5_device_to_host(void* dst, const void* src, size_t bytes)
 {
     std::lock_guard<std::mutex> lk(g_ctx.mu);
@@ -724,6 +744,11 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
     s5_fill_image_consts(p, &consts);
     /* two-phase azimuth: phase A queues the disk hits, phase B integrates phi per geodesic type */
     bool lanes = (p->mode == SIM5_MODE_STEPWISE || p->mode == SIM5_MODE_SURFACE);
+    const bool shared_queue = (p->flags & SIM5_FLAG_SHARED_QUEUE) != 0;
+    if (shared_queue && !(lanes && devptr && split == 1 && out->shared_counter)) {
+        set_error("SIM5_FLAG_SHARED_QUEUE needs a lane mode (STEPWISE / SURFACE), DEVICE_PTRS, no row split and out->shared_counter");
+        return SIM5_ERR_BAD_PARAM;
+    }
     bool two_phase = !lanes && (p->outputs & SIM5_OUT_PHI) && !(p->flags & SIM5_FLAG_SINGLE_PASS) && npix > 0;
 
     /* Host planes: the rows are traced in CHUNKS so the device->host copy of chunk k (copy stream, copy engine) runs
@@ -824,12 +849,14 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
             }
         }
         CK(cudaMemsetAsync(cnt, 0, (ch == 0 ? S5_BLK_WORDS : 8) * sizeof(unsigned long long), ls));      /* counters per chunk, stats once */
+        /* the ray queue: this call's own counter, or the caller's shared word (several GPUs pull rays of one image from it) */
+        unsigned long long* rayq = shared_queue ? (unsigned long long*)out->shared_counter : cnt;
         if (p->mode == SIM5_MODE_STEPWISE) {
             grid = persistent_grid(s5::k_trace_lanes<s5::StepwiseProg>, s5::StepwiseProg::THREADS);
-            s5::k_trace_lanes<s5::StepwiseProg><<<grid, s5::StepwiseProg::THREADS, 0, ls>>>(cc, dd, cnt, d_stats);
+            s5::k_trace_lanes<s5::StepwiseProg><<<grid, s5::StepwiseProg::THREADS, 0, ls>>>(cc, dd, rayq, d_stats);
         } else if (p->mode == SIM5_MODE_SURFACE) {
             grid = persistent_grid(s5::k_trace_lanes<s5::SurfaceProg>, s5::SurfaceProg::THREADS);
-            s5::k_trace_lanes<s5::SurfaceProg><<<grid, s5::SurfaceProg::THREADS, 0, ls>>>(cc, dd, cnt, d_stats);
+            s5::k_trace_lanes<s5::SurfaceProg><<<grid, s5::SurfaceProg::THREADS, 0, ls>>>(cc, dd, rayq, d_stats);
         } else if (two_phase) {
             if (p->outputs & SIM5_OUT_DELAY) {
                 grid = persistent_grid(s5::k_trace_eqplane<true, true>, S5_EQ_THREADS, S5_EQ_DYN_SMEM);
@@ -970,6 +997,10 @@ extern "C" int sim5_trace_image(const sim5_image_params* p, const sim5_image_out
         for (int i = 0; i < 32; i++) stats->class_count[i] = (int64_t)c.h_stats->cls[i];
         for (int i = 0; i < 8; i++) stats->gtype_count[i] = (int64_t)c.h_stats->gtype[i];
         stats->total_steps = (int64_t)c.h_stats->steps;
+        if (shared_queue) {          /* the rays THIS device pulled from the shared queue */
+            stats->rays = 0;
+            for (int i = 0; i < 32; i++) stats->rays += stats->class_count[i];
+        }
         float ms = 0;
         cudaEventElapsedTime(&ms, c.ev1, c.ev2); stats->kernel_ms = ms;
         cudaEventElapsedTime(&ms, c.ev1, c.ev3); stats->total_ms = ms;
@@ -1006,6 +1037,7 @@ struct MultiJob {
     std::string err;
     sim5_trace_stats st;
     double* d_hist = nullptr;            /* HISTOGRAM: this device's partial lattice */
+    uint64_t* shared_q = nullptr;        /* SIM5_FLAG_SHARED_QUEUE: the one ray queue of the call, on devices[0] */
     double spec[S5_SPEC_MAX_E];          /* SPECTRUM: this device's partial sum */
 };
 
@@ -1063,6 +1095,17 @@ void multi_worker(MultiJob* job)
     const int seg_end[3]   = {rb + n_a, rb + n_a + n_b, re};
     const int seg_srows[3] = {srows_a, 1, 0};
     sim5_image_out o = *job->out;
+    if (job->shared_q) {
+        /* one queue for all devices: every GPU runs the whole row range and pulls rays from the counter on devices[0], a warp refill at a
+         * time, until it is empty -- no split to balance, the GPUs finish within one ray of each other */
+        q.row_begin = rb; q.row_end = re;
+        q.split_count = 0; q.split_index = 0; q.split_rows = 0;
+        o.shared_counter = job->shared_q;
+        int rc = sim5_trace_image(&q, &o, &job->st);
+        if (rc) fail(rc);
+        return;
+    }
+    q.flags &= ~(uint32_t)SIM5_FLAG_SHARED_QUEUE;
     if (p->mode == SIM5_MODE_SPECTRUM) { for (int k = 0; k < S5_SPEC_MAX_E; k++) job->spec[k] = 0.0; }
     for (int sgm = 0; sgm < 3; sgm++) {
         if (seg_end[sgm] <= seg_begin[sgm]) continue;
@@ -1102,10 +1145,27 @@ extern "C" int sim5_trace_image_multi(const sim5_image_params* p, const sim5_ima
     if (p->mode == SIM5_MODE_SPECTRUM && (p->n_energy < 1 || p->n_energy > S5_SPEC_MAX_E)) { set_error("bad spectrum grid"); return SIM5_ERR_BAD_PARAM; }
     if (p->mode == SIM5_MODE_HISTOGRAM && !out->hist) { set_error("HISTOGRAM mode needs out->hist"); return SIM5_ERR_NO_OUTPUT; }
     Context* caller = &g_ctx;
+    uint64_t* shared_q = nullptr;
+    if (p->flags & SIM5_FLAG_SHARED_QUEUE) {
+        const bool lanes = (p->mode == SIM5_MODE_STEPWISE || p->mode == SIM5_MODE_SURFACE);
+        if (!lanes || !(p->flags & SIM5_FLAG_DEVICE_PTRS)) { set_error("SIM5_FLAG_SHARED_QUEUE needs a lane mode (STEPWISE / SURFACE) and DEVICE_PTRS"); return SIM5_ERR_BAD_PARAM; }
+        shared_q = out->shared_counter;
+        if (!shared_q) {
+            /* the library's own queue word on devices[0], zeroed before the first device starts */
+            Context& c0 = select_ctx(devices[0]);
+            std::lock_guard<std::mutex> lk(c0.mu);
+            int rc0 = ensure_init(devices[0]);
+            if (!rc0) rc0 = reserve(c0.shared_q, 64);
+            if (!rc0 && !(cuda_ok(cudaMemsetAsync(c0.shared_q.p, 0, 64, c0.stream), "shared queue memset") && cuda_ok(cudaStreamSynchronize(c0.stream), "shared queue memset"))) rc0 = SIM5_ERR_CUDA;
+            if (rc0) { caller->last_error = c0.last_error; t_ctx = caller; return rc0; }
+            shared_q = (uint64_t*)c0.shared_q.p;
+            t_ctx = caller;
+        }
+    }
     std::vector<MultiJob> jobs((size_t)ndev);
     std::vector<std::thread> th;
     for (int i = 0; i < ndev; i++) {
-        jobs[i].device = devices[i]; jobs[i].index = i; jobs[i].ndev = ndev; jobs[i].p = p; jobs[i].out = out; jobs[i].dev0 = devices[0];
+        jobs[i].device = devices[i]; jobs[i].index = i; jobs[i].ndev = ndev; jobs[i].p = p; jobs[i].out = out; jobs[i].dev0 = devices[0]; jobs[i].shared_q = shared_q;
     }
     for (int i = 1; i < ndev; i++) th.emplace_back(multi_worker, &jobs[i]);
     multi_worker(&jobs[0]);                                  /* the calling thread drives devices[0] */

@@ -387,6 +387,12 @@ k_azimuth_fast(const __grid_constant__ S5ImageConsts gconsts, AzQueue q, double*
 #define S5_STEPS_PER_ROUND 16
 #define S5_REFILL_MIN 4
 
+/* n rays from the queue: the kernel's own counter, or (SIM5_FLAG_SHARED_QUEUE) one word that several GPUs pull from over NVLink */
+__device__ __forceinline__ unsigned long long take_rays(unsigned long long* counter, unsigned long long n, bool shared)
+{
+    return shared ? atomicAdd_system(counter, n) : atomicAdd(counter, n);
+}
+
 template <class PROG>
 __global__ void __launch_bounds__(PROG::THREADS, PROG::MIN_CTAS)
 k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigned long long* __restrict__ ray_counter, DevStats* __restrict__ gstats)
@@ -402,6 +408,7 @@ k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigne
     const long long nx = c.nx;
     const long long npix = (long long)c.nrows_local * nx;
     const bool refill = !(c.flags & SIM5_FLAG_NO_REFILL);
+    const bool shared_queue = (c.flags & SIM5_FLAG_SHARED_QUEUE) != 0;
 
     typename PROG::State s;
     long long mypix = -1;
@@ -418,7 +425,7 @@ k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigne
         __shared__ unsigned long long s_base;
         for (;;) {
             __syncthreads();
-            if (threadIdx.x == 0) s_base = atomicAdd(ray_counter, (unsigned long long)blockDim.x);
+            if (threadIdx.x == 0) s_base = take_rays(ray_counter, (unsigned long long)blockDim.x, shared_queue);
             __syncthreads();
             const long long base = (long long)s_base;
             if (base >= npix) break;
@@ -472,7 +479,7 @@ k_trace_lanes(const __grid_constant__ S5ImageConsts gconsts, DevOut out, unsigne
             int nreq = __popc(idle);
             unsigned long long base = 0;
             int leader = __ffs(idle) - 1;
-            if (lane == leader) base = atomicAdd(ray_counter, (unsigned long long)nreq);
+            if (lane == leader) base = take_rays(ray_counter, (unsigned long long)nreq, shared_queue);
             base = __shfl_sync(0xffffffffu, base, leader);
             if ((long long)base >= npix) drained = true;
             if (!live) {

@@ -144,3 +144,96 @@ def test_stage_copy_assembles_the_image_by_dma(gpu_api):
         finally:
             gpu_api.check(L.sim5_synchronize(), "sim5_synchronize")
             img.close()
+
+
+ALL_PLANES = tuple(name for name, _, _ in abi.PLANES)
+
+
+def _lane_image(gpu_api, cfg, nx, ny, counter_start=None, devices=None):
+    """cfg through SIM5_FLAG_SHARED_QUEUE into device planes pre-filled with 0xFF bytes; returns ({plane: flat array}, stats)."""
+    L = gpu_api.lib()
+    p = abi.default_params(cfg, nx, ny)
+    p.flags |= abi.FLAG_DEVICE_PTRS | abi.FLAG_SHARED_QUEUE
+    img = gpu_api.DevicePlanes(p, names=ALL_PLANES)
+    ctr = L.sim5_device_alloc(64)
+    try:
+        for name, ptr in img.ptrs.items():
+            gpu_api.check(L.sim5_device_memset(C.c_void_p(ptr), 0xFF, img.n * np.dtype(img.dtypes[name]).itemsize), "sim5_device_memset")
+        gpu_api.check(L.sim5_device_memset(C.c_void_p(ctr), 0, 64), "sim5_device_memset")
+        if counter_start is not None:
+            v = np.array([counter_start], dtype=np.uint64)
+            gpu_api.check(L.sim5_host_to_device(C.c_void_p(ctr), v.ctypes.data, 8), "sim5_host_to_device")
+        st = abi.TraceStats()
+        if devices is None:
+            img.out.shared_counter = ctr
+            gpu_api.check(L.sim5_trace_image(C.byref(p), C.byref(img.out), C.byref(st)), "sim5_trace_image")
+        else:
+            dl = (C.c_int * len(devices))(*devices)
+            gpu_api.check(L.sim5_trace_image_multi(C.byref(p), C.byref(img.out), C.byref(st), dl, len(devices)), "sim5_trace_image_multi")
+        return {k: img.to_host(k) for k in img.ptrs}, st
+    finally:
+        L.sim5_device_free(C.c_void_p(ctr))
+        img.close()
+
+
+@pytest.mark.parametrize("cfg,nx,ny", [(4, 48, 40), (7, 56, 33)])
+def test_shared_queue_image_equals_the_private_queue_image(gpu_api, cfg, nx, ny):
+    """SIM5_FLAG_SHARED_QUEUE: the rays come from the caller's counter (system-scope atomics) instead of the call's own -- same image;
+    through sim5_trace_image_multi every device pulls from one counter on devices[0] and stores into devices[0]'s planes."""
+    gpu_api.init(0)
+    p = abi.default_params(cfg, nx, ny)
+    ref, st0 = _single(gpu_api, p)
+    for devices in (None, [0], _devices(gpu_api)):
+        got, st = _lane_image(gpu_api, cfg, nx, ny, devices=devices)
+        assert st.rays == nx * ny and list(st.class_count) == list(st0.class_count) and st.total_steps == st0.total_steps, devices
+        for k in ref.arrays:
+            assert np.array_equal(got[k], np.asarray(ref[k]).reshape(-1), equal_nan=True), (cfg, devices, k)
+    gpu_api.init(0)
+
+
+def test_shared_queue_skips_the_rays_another_device_took(gpu_api):
+    """the counter starts at K, as if another GPU had pulled the first K rays: those pixels stay untouched, the rest is the image"""
+    gpu_api.init(0)
+    nx, ny, K = 64, 32, 700
+    p = abi.default_params(4, nx, ny)
+    p.flags |= abi.FLAG_ROW_MAJOR                 # ray k == pixel k
+    ref, _ = _single(gpu_api, p)
+    L = gpu_api.lib()
+    q = abi.ImageParams.from_buffer_copy(p)
+    q.flags |= abi.FLAG_DEVICE_PTRS | abi.FLAG_SHARED_QUEUE
+    img = gpu_api.DevicePlanes(q, names=ALL_PLANES)
+    ctr = L.sim5_device_alloc(64)
+    try:
+        for name, ptr in img.ptrs.items():
+            gpu_api.check(L.sim5_device_memset(C.c_void_p(ptr), 0xFF, img.n * np.dtype(img.dtypes[name]).itemsize), "sim5_device_memset")
+        v = np.array([K], dtype=np.uint64)
+        gpu_api.check(L.sim5_host_to_device(C.c_void_p(ctr), v.ctypes.data, 8), "sim5_host_to_device")
+        img.out.shared_counter = ctr
+        st = abi.TraceStats()
+        gpu_api.check(L.sim5_trace_image(C.byref(q), C.byref(img.out), C.byref(st)), "sim5_trace_image")
+        assert sum(st.class_count) == nx * ny - K
+        s = img.to_host("status")
+        assert np.all(s[:K] == 0xFF) and np.array_equal(s[K:], np.asarray(ref["status"]).reshape(-1)[K:])
+        for k in ("intensity", "tau"):
+            if k in img.ptrs:
+                assert np.array_equal(img.to_host(k)[K:], np.asarray(ref[k]).reshape(-1)[K:], equal_nan=True), k
+        # drained queue: a second call on the same counter traces nothing
+        st2 = abi.TraceStats()
+        gpu_api.check(L.sim5_trace_image(C.byref(q), C.byref(img.out), C.byref(st2)), "sim5_trace_image")
+        assert sum(st2.class_count) == 0
+    finally:
+        L.sim5_device_free(C.c_void_p(ctr))
+        img.close()
+
+
+def test_shared_queue_is_refused_where_it_cannot_work(gpu_api):
+    L = gpu_api.lib()
+    gpu_api.init(0)
+    for cfg, extra in ((2, abi.FLAG_DEVICE_PTRS), (4, 0)):
+        p = abi.default_params(cfg, 32, 32)
+        p.flags |= abi.FLAG_SHARED_QUEUE | extra
+        planes = gpu_api.HostPlanes(p, pinned=False)
+        st = abi.TraceStats()
+        assert L.sim5_trace_image(C.byref(p), C.byref(planes.out), C.byref(st)) == abi.ERR_BAD_PARAM
+        dl = (C.c_int * 1)(0)
+        assert L.sim5_trace_image_multi(C.byref(p), C.byref(planes.out), C.byref(st), dl, 1) == abi.ERR_BAD_PARAM
